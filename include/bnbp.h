@@ -1,0 +1,143 @@
+/* bnbp.h — C ABI of libbnbp: batched loopy belief propagation (Pearl pi/lambda) on B200.
+ *
+ * This is the only boundary between host code (the drop-in C++ headers under
+ * include/bayesian/, the Python host in bayesiannetwork_b200/, or any FFI) and the
+ * CUDA backend.  POD structs, plain pointers and sizes only; no STL, no torch types.
+ *
+ * Each entry point names the reference interface it replaces.  File:line citations are
+ * relative to the reference tree (godai0519/BayesianNetwork):
+ *
+ *   bnbp_create        <- belief_propagation::belief_propagation(graph_t const&)
+ *                         bayesian/inference/belief_propagation.hpp:16-19 (+ the topology
+ *                         queries graph.hpp:362-433 and CPT lookups graph.hpp:117-147 that
+ *                         the reference repeats on every sweep; here they run once)
+ *   bnbp_run_batch     <- belief_propagation::operator()(precondition, epsilon)
+ *                         belief_propagation.hpp:31-159, for n_cases evidence sets at once
+ *   bnbp_run_batch_device  same, evidence / marginals already resident in device memory
+ *   bnbp_destroy       <- belief_propagation::~belief_propagation()   :21
+ *   bnbp_last_error    <- (the reference has no error channel; UB / NaN / endless loop)
+ *
+ * Semantics reproduced exactly (belief_propagation.hpp:75-148): synchronous (Jacobi)
+ * schedule, no damping unless asked, evidence vector written into both pi and lambda of the
+ * node and never updated, delta = max(DBL_MIN, max |new-old| over all message entries) with
+ * NaN ignored, stop when delta < epsilon (strict), belief = normalize(pi .* lambda).
+ */
+#ifndef BNBP_H
+#define BNBP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define BNBP_VERSION 1
+
+/* status codes */
+enum {
+    BNBP_OK = 0,
+    BNBP_ERR_INVALID = 1,   /* bad argument / malformed network or evidence */
+    BNBP_ERR_CUDA = 2,      /* CUDA runtime error (message in bnbp_last_error) */
+    BNBP_ERR_NO_DEVICE = 3, /* no usable sm_100 device: there is NO CPU fallback */
+    BNBP_ERR_NOMEM = 4
+};
+
+enum { BNBP_FP64 = 0, BNBP_FP32 = 1 };
+
+/* Flat (CSR) description of a discrete Bayesian network.
+ *   node i      = i-th entry of graph_t::vertex_list()                (graph.hpp:214)
+ *   card[i]     = vertex_t::selectable_num                            (graph.hpp:159)
+ *   parents of i = graph_t::in_vertexes(vertex i), ascending index    (graph.hpp:389-413)
+ *   cpt         = row-major per node: cpt[cpt_off[i] + q*card[i] + x] = P(X_i = x | config q)
+ *                 q enumerates parent configurations in mixed radix with the FIRST parent
+ *                 slowest, the order of all_combination_pattern (belief_propagation.hpp:269-295)
+ * Children lists (graph_t::out_vertexes, graph.hpp:378-386) are derived by the library. */
+typedef struct bnbp_flat_network {
+    int32_t        n_nodes;
+    const int32_t* card;        /* [n_nodes]                        */
+    const int32_t* parent_off;  /* [n_nodes+1]                      */
+    const int32_t* parents;     /* [parent_off[n_nodes]]            */
+    const int64_t* cpt_off;     /* [n_nodes+1]                      */
+    const double*  cpt;         /* [cpt_off[n_nodes]]               */
+} bnbp_flat_network;
+
+typedef struct bnbp_options {
+    int32_t precision;          /* BNBP_FP64 (default, the reference's arithmetic) or BNBP_FP32 */
+    int32_t device;             /* CUDA device ordinal; -1 = current device                     */
+    int64_t max_resident_cases; /* cases kept in HBM at once (0 = pick from free memory)         */
+    int32_t reserved[8];
+} bnbp_options;
+
+/* Evidence for a batch, CSR over cases.  Entry e of case c (ev_off[c] <= e < ev_off[c+1])
+ * observes node ev_node[e]:
+ *   hard evidence (ev_values == NULL): one-hot row with state ev_state[e]
+ *                 (the condition_t form, graph.hpp:18 / example main.cpp:50-55);
+ *   soft evidence (ev_values != NULL): the row ev_values[ev_val_off[e] .. +card[node])
+ *                 (the unordered_map<vertex_type, matrix_type> form, belief_propagation.hpp:31,69-73).
+ * A node listed twice in one case: the last entry wins. */
+typedef struct bnbp_evidence {
+    int64_t        n_cases;
+    const int64_t* ev_off;      /* [n_cases+1]            */
+    const int32_t* ev_node;     /* [ev_off[n_cases]]      */
+    const int32_t* ev_state;    /* [nnz] or NULL          */
+    const int64_t* ev_val_off;  /* [nnz+1] or NULL        */
+    const double*  ev_values;   /* [ev_val_off[nnz]] or NULL */
+} bnbp_evidence;
+
+typedef struct bnbp_run_params {
+    double  epsilon;        /* stop a case when its delta < epsilon (reference default 0.001).
+                               epsilon <= 0 disables the test (fixed sweep count, no old-message reads) */
+    int32_t max_sweeps;     /* cap per case; <= 0 means 1<<30 (the reference has no cap)                */
+    double  damping;        /* 0 = reference behaviour; msg = (1-d)*new + d*old otherwise (extension)   */
+    int32_t check_interval; /* test convergence every n-th sweep; 1 = reference semantics                */
+    int32_t reserved[7];
+} bnbp_run_params;
+
+typedef struct bnbp_stats {
+    int64_t state_values_per_case;   /* S = 2*sum r_X + 2*sum_{U->X} r_U                        */
+    int64_t msg_values_per_case;     /* 2*sum_{U->X} r_U                                        */
+    int64_t belief_values_per_case;  /* sum r_X                                                  */
+    int64_t cpt_values;              /* reference-layout CPT entries                             */
+    int64_t bytes_per_value;         /* 8 or 4                                                   */
+    int64_t last_case_sweeps;        /* sum over cases of sweeps executed by the last run       */
+    int64_t last_sweep_launches;     /* sweep-kernel launches of the last run                   */
+    int64_t last_kernel_launches;    /* all kernel launches of the last run                     */
+    double  last_sweep_ms;           /* device time of the sweep launches (CUDA events)         */
+    double  last_total_ms;           /* device time init..beliefs of the last run               */
+    int64_t resident_cases;          /* cases per HBM-resident chunk                            */
+    int64_t reserved[8];
+} bnbp_stats;
+
+typedef struct bnbp_handle bnbp_handle;
+
+int  bnbp_device_count(void);
+const char* bnbp_last_error(void);           /* thread-local, never NULL */
+
+int  bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_handle** out);
+void bnbp_destroy(bnbp_handle* h);
+
+/* Host buffers in, host buffers out (copies are part of the call).
+ *   out_marginals [n_cases][belief_values_per_case] doubles, node i at offset sum_{j<i} card[j]
+ *   out_sweeps    [n_cases] sweeps executed per case (may be NULL)
+ *   out_converged [n_cases] 1 if the case's last tested delta < epsilon (may be NULL)   */
+int  bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm,
+                    double* out_marginals, int32_t* out_sweeps, uint8_t* out_converged);
+
+/* Same, but every pointer inside *ev and every out_* pointer is a DEVICE pointer on the
+ * handle's device; out_marginals has the handle's precision (double or float).  The work is
+ * enqueued on `stream` (a cudaStream_t passed as void*; NULL = the handle's own stream) and the
+ * call returns without synchronising unless epsilon > 0 forces host-side termination polls. */
+int  bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm,
+                           void* out_marginals, int32_t* out_sweeps, uint8_t* out_converged,
+                           void* stream);
+
+int  bnbp_get_stats(const bnbp_handle* h, bnbp_stats* out);
+
+/* Re-upload CPT values after the host network changed them (topology must be unchanged). */
+int  bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* BNBP_H */

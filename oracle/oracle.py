@@ -1,0 +1,100 @@
+"""ctypes bindings of the parity checkers -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+
+Importable only from tests/, __graft_entry__.smoke() and bench.py's cpu_baseline /
+--impl reference legs.  ``port``  = oracle/_build/libbp_oracle.so (C restatement, bp_oracle.c);
+``reference`` = oracle/_ref/libbnref.so (the reference's own headers compiled in place).
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+PORT_SO = os.path.join(HERE, "_build", "libbp_oracle.so")
+REF_SO = os.path.join(HERE, "_ref", "libbnref.so")
+REF_PURE_SO = os.path.join(HERE, "_ref", "libbnref_pure.so")
+
+
+def build(quiet: bool = True) -> None:
+    """Compile the checkers (the reference flavour only where /root/reference exists)."""
+    subprocess.run(["make", "-C", HERE, "all"], check=True,
+                   stdout=subprocess.DEVNULL if quiet else None)
+
+
+def _ptr(a, ctype):
+    if a is None:
+        return None
+    return a.ctypes.data_as(C.POINTER(ctype))
+
+
+def _net_args(net):
+    return (C.c_int32(net.n_nodes), _ptr(net.card, C.c_int32), _ptr(net.parent_off, C.c_int32),
+            _ptr(net.parents, C.c_int32), _ptr(net.cpt_off, C.c_int64), _ptr(net.cpt, C.c_double))
+
+
+def _ev_args(ev):
+    return (C.c_int64(ev.n_cases), _ptr(ev.ev_off, C.c_int64), _ptr(ev.ev_node, C.c_int32),
+            _ptr(ev.ev_state, C.c_int32) if not ev.is_soft else None,
+            _ptr(ev.ev_val_off, C.c_int64) if ev.is_soft else None,
+            _ptr(ev.ev_values, C.c_double) if ev.is_soft else None)
+
+
+_port = None
+
+
+def have_port() -> bool:
+    return os.path.exists(PORT_SO)
+
+
+def have_reference() -> bool:
+    return os.path.exists(REF_SO)
+
+
+def port_max_threads() -> int:
+    global _port
+    if _port is None:
+        _port = C.CDLL(PORT_SO)
+    return int(_port.bp_oracle_max_threads())
+
+
+def run_port(net, ev, eps=1e-3, max_sweeps=0, damping=0.0, check_interval=1, threads=1):
+    """C restatement.  Returns (marginals [B, sum r], sweeps [B], converged [B])."""
+    global _port
+    if _port is None:
+        _port = C.CDLL(PORT_SO)
+    out = np.empty((ev.n_cases, net.belief_values), dtype=np.float64)
+    sweeps = np.empty(ev.n_cases, dtype=np.int32)
+    conv = np.empty(ev.n_cases, dtype=np.uint8)
+    _port.bp_oracle_run.restype = C.c_int
+    rc = _port.bp_oracle_run(*_net_args(net), *_ev_args(ev), C.c_double(eps), C.c_int32(max_sweeps),
+                             C.c_double(damping), C.c_int32(check_interval), C.c_int32(threads),
+                             _ptr(out, C.c_double), _ptr(sweeps, C.c_int32), _ptr(conv, C.c_uint8))
+    if rc != 0:
+        raise RuntimeError("bp_oracle_run failed")
+    return out, sweeps, conv
+
+
+_ref = {}
+
+
+def run_reference(net, ev, eps=1e-3, max_sweeps=0, pure=False):
+    """The reference's own belief_propagation (oracle/_ref).  Returns
+    (marginals, sweeps, converged, seconds inside operator())."""
+    path = REF_PURE_SO if pure else REF_SO
+    if path not in _ref:
+        _ref[path] = C.CDLL(path)
+    lib = _ref[path]
+    out = np.empty((ev.n_cases, net.belief_values), dtype=np.float64)
+    sweeps = np.empty(ev.n_cases, dtype=np.int32)
+    conv = np.empty(ev.n_cases, dtype=np.uint8)
+    secs = C.c_double(0.0)
+    lib.bnref_run.restype = C.c_int
+    rc = lib.bnref_run(*_net_args(net), *_ev_args(ev), C.c_double(eps), C.c_int32(max_sweeps),
+                       _ptr(out, C.c_double), _ptr(sweeps, C.c_int32), _ptr(conv, C.c_uint8),
+                       C.byref(secs))
+    if rc != 0:
+        raise RuntimeError("bnref_run failed")
+    return out, sweeps, conv, secs.value

@@ -1,0 +1,122 @@
+"""Pins the oracle (CPU restatement, oracle/bp_oracle.c) -- runs without a GPU.
+
+1. against the reference's own test vectors (tests/golden/reference_tests.json),
+2. against fixtures produced by the reference itself (tests/golden/ref_fixtures.npz),
+3. live against the compiled reference (oracle/_ref) when it is present.
+"""
+import json
+import os
+
+import numpy as np
+import pytest
+
+from bayesiannetwork_b200 import synth
+from bayesiannetwork_b200.flat import EvidenceBatch
+from helpers import assert_close, load_fixture
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+SPEC = json.load(open(os.path.join(ROOT, "tests", "golden", "reference_tests.json")))
+NETS = {"pearl": synth.pearl_network, "resume": synth.resume_network}
+
+
+def boost_check_close(a, b, tol_percent):
+    """BOOST_CHECK_CLOSE: strong check, both relative differences within tol (percent)."""
+    if a == b:
+        return True
+    d = abs(a - b)
+    return d <= tol_percent / 100 * abs(a) and d <= tol_percent / 100 * abs(b)
+
+
+@pytest.mark.parametrize("case", SPEC["cases"], ids=[c["name"] for c in SPEC["cases"]])
+def test_reference_test_vectors(oracle_mod, case):
+    net = NETS[case["network"]]()
+    ev = EvidenceBatch.from_cases(net, [{int(k): v for k, v in case["evidence"].items()}])
+    m, sweeps, conv = oracle_mod.run_port(net, ev, eps=case["eps"])
+    off = net.belief_off
+    assert sweeps[0] == case["sweeps"] and conv[0] == 1
+    for node, teacher in case["teacher"].items():
+        got = m[0, off[int(node)]:off[int(node) + 1]]
+        for g, t in zip(got, teacher):
+            assert boost_check_close(float(g), t, case["tol_percent"]), (case["name"], node, got, teacher)
+    if case["beliefs"] is not None:
+        flat = np.concatenate([np.asarray(b, dtype=np.float64) for b in case["beliefs"]])
+        assert_close(m[0], flat, rtol=1e-12, atol=1e-15, what=case["name"])
+
+
+def test_fixture_names(ref_fixtures):
+    assert len(ref_fixtures["names"]) >= 15
+
+
+@pytest.mark.parametrize("name", [
+    "pearl_tests", "resume_tests", "resume_soft", "pearl_nan", "pearl_nan_fixed6", "pearl_one_sweep",
+    "polytree24_eps", "polytree24_soft", "grid4_eps", "grid4_fixed7", "grid6_fixed12", "dag40_eps",
+    "dag40_fixed5", "alarm37_eps", "alarm37_fixed20", "card6_fixed6"])
+def test_port_matches_reference_fixtures(oracle_mod, ref_fixtures, name):
+    f = load_fixture(ref_fixtures, name)
+    m, sweeps, conv = oracle_mod.run_port(f["net"], f["ev"], eps=f["eps"], max_sweeps=f["max_sweeps"])
+    assert np.array_equal(sweeps, f["sweeps"]), name
+    assert np.array_equal(conv, f["converged"]), name
+    assert_close(m, f["marginals"], rtol=1e-12, atol=1e-15, what=name)
+
+
+def test_nan_fixture_really_has_nan(ref_fixtures):
+    f = load_fixture(ref_fixtures, "pearl_nan_fixed6")
+    assert np.isnan(f["marginals"]).any()
+
+
+def test_port_threads_agree(oracle_mod):
+    net = synth.alarm37()
+    ev = synth.make_evidence(net, 64, exact_k=4)
+    a = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=100, threads=1)
+    b = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=100, threads=4)
+    assert np.array_equal(a[0], b[0]) and np.array_equal(a[1], b[1])
+
+
+def test_port_extensions_default_off(oracle_mod):
+    """damping=0 / check_interval=1 are the reference behaviour; check_interval only rounds the
+    stopping sweep up to a multiple."""
+    net = synth.grid(4, seed=5)
+    ev = synth.make_evidence(net, 8, p=0.2, seed=3)
+    m1, s1, _ = oracle_mod.run_port(net, ev, eps=1e-8, max_sweeps=400)
+    m4, s4, c4 = oracle_mod.run_port(net, ev, eps=1e-8, max_sweeps=400, check_interval=4)
+    assert np.all(s4 % 4 == 0) and np.all(s4 >= s1) and np.all(s4 < s1 + 4) and c4.all()
+    md, sd, cd = oracle_mod.run_port(net, ev, eps=1e-8, max_sweeps=400, damping=0.3)
+    assert cd.all()
+    assert_close(md, m1, rtol=1e-5, atol=1e-7, what="damped fixed point")
+
+
+def _have_ref(oracle_mod):
+    return oracle_mod.have_reference() and os.path.exists(oracle_mod.REF_PURE_SO)
+
+
+def test_live_reference_capped_equals_pure(oracle_mod):
+    """The sweep-cap shim does not change the reference's results (eps mode), and eps=1e300
+    means exactly one sweep."""
+    if not _have_ref(oracle_mod):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    net = synth.random_dag(30, max_parents=3, card_lo=2, card_hi=4, seed=5)
+    ev = synth.make_evidence(net, 6, p=0.15, seed=2)
+    mc, sc, cc, _ = oracle_mod.run_reference(net, ev, eps=1e-6, max_sweeps=1000)
+    mp, _, _, _ = oracle_mod.run_reference(net, ev, eps=1e-6, pure=True)
+    # not bit-equal: the reference multiplies in pointer-keyed unordered_map order
+    assert_close(mc, mp, rtol=1e-13, atol=1e-16, what="capped vs pure")
+    assert cc.all()
+    m1, s1, _, _ = oracle_mod.run_reference(net, ev, eps=1e300, max_sweeps=1000)
+    assert np.all(s1 == 1)
+    mport, sport, _ = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=1000)
+    assert np.array_equal(sport, sc)
+    assert_close(mport, mc, rtol=1e-12, atol=1e-15, what="live")
+
+
+@pytest.mark.parametrize("seed", [1, 2, 3])
+def test_live_reference_random_nets(oracle_mod, seed):
+    if not _have_ref(oracle_mod):
+        pytest.skip("oracle/_ref not built (no /root/reference here)")
+    net = synth.random_dag(25 + 5 * seed, max_parents=4, card_lo=2, card_hi=5, seed=seed)
+    for soft in (False, True):
+        ev = synth.make_evidence(net, 5, p=0.2, seed=seed, soft=soft)
+        for eps, cap in ((1e-7, 300), (0.0, 9)):
+            mr, sr, cr, _ = oracle_mod.run_reference(net, ev, eps=eps, max_sweeps=cap)
+            mp, sp, cp = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap)
+            assert np.array_equal(sr, sp) and np.array_equal(cr, cp)
+            assert_close(mp, mr, rtol=1e-12, atol=1e-15, what=f"seed{seed} soft{soft} eps{eps}")
