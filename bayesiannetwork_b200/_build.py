@@ -1,0 +1,85 @@
+"""Build recipe of lib/libbnbp.so (hand-written sm_100a kernels + the C ABI).  In-tree, so the
+built library travels to the GPU box with the repository snapshot.  The sweep kernel family is
+instantiated one (T, VEC, RMAX) per translation unit and compiled in parallel."""
+from __future__ import annotations
+
+import os
+import shutil
+import subprocess
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+CSRC = os.path.join(HERE, "csrc")
+LIBDIR = os.path.join(HERE, "lib")
+OBJDIR = os.path.join(LIBDIR, "obj")
+LIB = os.path.join(LIBDIR, "libbnbp.so")
+HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_sweep.cuh"),
+           os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
+# (T, VEC, RMAX) instantiations -- must match the dispatch in bnbp_api.cu
+SWEEP_VARIANTS = [(t, v, r) for t in ("double", "float")
+                  for (v, r) in ((2, 2), (2, 4), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (1, 64))]
+
+NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+
+
+def nvcc_path() -> str:
+    p = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    if not os.path.exists(p):
+        raise RuntimeError("nvcc not found: libbnbp cannot be built")
+    return p
+
+
+def _env():
+    env = dict(os.environ)
+    env.pop("CC", None)     # the image exports a CC wrapper nvcc should not pick up
+    env.pop("CXX", None)
+    return env
+
+
+def _units():
+    units = [(os.path.join(CSRC, "bnbp_api.cu"), os.path.join(OBJDIR, "bnbp_api.o"), [])]
+    for t, v, r in SWEEP_VARIANTS:
+        units.append((os.path.join(CSRC, "bnbp_sweep_inst.cu"),
+                      os.path.join(OBJDIR, f"sweep_{t}_v{v}_r{r}.o"),
+                      [f"-DBNBP_T={t}", f"-DBNBP_VEC={v}", f"-DBNBP_RMAX={r}"]))
+    return units
+
+
+def _stale(obj: str, src: str) -> bool:
+    if not os.path.exists(obj):
+        return True
+    t = os.path.getmtime(obj)
+    return any(os.path.getmtime(f) > t for f in [src] + HEADERS)
+
+
+def build(force: bool = False, verbose: bool = False, extra=()) -> str:
+    os.makedirs(OBJDIR, exist_ok=True)
+    nvcc = nvcc_path()
+    todo = [(s, o, d) for (s, o, d) in _units() if force or _stale(o, s)]
+
+    def compile_one(u):
+        src, obj, defs = u
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *defs, "-c", "-o", obj, src]
+        r = subprocess.run(cmd, env=_env(), capture_output=True, text=True)
+        if r.returncode != 0:
+            raise RuntimeError(f"nvcc failed for {os.path.basename(obj)}:\n{r.stdout}\n{r.stderr}")
+        if verbose:
+            sys.stdout.write(f"[bnbp build] {os.path.basename(obj)}\n{r.stderr}")
+        return obj
+
+    if todo:
+        with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 4))) as ex:
+            list(ex.map(compile_one, todo))
+    objs = [o for (_, o, _) in _units()]
+    if todo or not os.path.exists(LIB):
+        cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
+               "-o", LIB, *objs]
+        subprocess.run(cmd, check=True, env=_env())
+    return LIB
+
+
+if __name__ == "__main__":
+    print(build(force="--force" in sys.argv, verbose=True,
+                extra=["-Xptxas", "-v"] if "--ptxas" in sys.argv else ()))

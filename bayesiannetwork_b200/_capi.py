@@ -1,0 +1,89 @@
+"""ctypes binding of lib/libbnbp.so (the C ABI in include/bnbp.h).
+
+Fails loudly when the library is missing or cannot be loaded: there is no CPU fallback."""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+from . import _build
+
+_lib = None
+
+
+class BnbpError(RuntimeError):
+    def __init__(self, code: int, msg: str):
+        super().__init__(f"libbnbp error {code}: {msg}")
+        self.code = code
+
+
+class FlatNetworkC(C.Structure):
+    _fields_ = [("n_nodes", C.c_int32), ("card", C.c_void_p), ("parent_off", C.c_void_p),
+                ("parents", C.c_void_p), ("cpt_off", C.c_void_p), ("cpt", C.c_void_p)]
+
+
+class OptionsC(C.Structure):
+    _fields_ = [("precision", C.c_int32), ("device", C.c_int32), ("max_resident_cases", C.c_int64),
+                ("reserved", C.c_int32 * 8)]
+
+
+class EvidenceC(C.Structure):
+    _fields_ = [("n_cases", C.c_int64), ("ev_off", C.c_void_p), ("ev_node", C.c_void_p),
+                ("ev_state", C.c_void_p), ("ev_val_off", C.c_void_p), ("ev_values", C.c_void_p)]
+
+
+class RunParamsC(C.Structure):
+    _fields_ = [("epsilon", C.c_double), ("max_sweeps", C.c_int32), ("damping", C.c_double),
+                ("check_interval", C.c_int32), ("reserved", C.c_int32 * 7)]
+
+
+class StatsC(C.Structure):
+    _fields_ = [("state_values_per_case", C.c_int64), ("msg_values_per_case", C.c_int64),
+                ("belief_values_per_case", C.c_int64), ("cpt_values", C.c_int64),
+                ("bytes_per_value", C.c_int64), ("last_case_sweeps", C.c_int64),
+                ("last_sweep_launches", C.c_int64), ("last_kernel_launches", C.c_int64),
+                ("last_sweep_ms", C.c_double), ("last_total_ms", C.c_double),
+                ("resident_cases", C.c_int64), ("reserved", C.c_int64 * 8)]
+
+
+EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",
+           "bnbp_run_batch_device", "bnbp_get_stats", "bnbp_refresh_cpt"]
+
+
+def lib_path() -> str:
+    return _build.LIB
+
+
+def load():
+    """Load libbnbp.so (building it first if the sources are newer and nvcc is available)."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    path = lib_path()
+    if not os.path.exists(path):
+        raise BnbpError(-1, f"{path} is missing: run `python -c 'import __graft_entry__ as g; g.build()'` "
+                            "(needs nvcc). There is no CPU fallback.")
+    lib = C.CDLL(path)
+    lib.bnbp_last_error.restype = C.c_char_p
+    lib.bnbp_device_count.restype = C.c_int
+    lib.bnbp_create.restype = C.c_int
+    lib.bnbp_create.argtypes = [C.POINTER(FlatNetworkC), C.POINTER(OptionsC), C.POINTER(C.c_void_p)]
+    lib.bnbp_destroy.restype = None
+    lib.bnbp_destroy.argtypes = [C.c_void_p]
+    lib.bnbp_run_batch.restype = C.c_int
+    lib.bnbp_run_batch.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.POINTER(RunParamsC),
+                                   C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bnbp_run_batch_device.restype = C.c_int
+    lib.bnbp_run_batch_device.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.POINTER(RunParamsC),
+                                          C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bnbp_get_stats.restype = C.c_int
+    lib.bnbp_get_stats.argtypes = [C.c_void_p, C.POINTER(StatsC)]
+    lib.bnbp_refresh_cpt.restype = C.c_int
+    lib.bnbp_refresh_cpt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    _lib = lib
+    return lib
+
+
+def check(rc: int):
+    if rc != 0:
+        raise BnbpError(rc, load().bnbp_last_error().decode("utf-8", "replace"))

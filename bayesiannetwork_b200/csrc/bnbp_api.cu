@@ -1,0 +1,731 @@
+// bnbp_api.cu — C ABI of libbnbp (include/bnbp.h): network flattening into the device arena,
+// batch orchestration, error channel.  The reference keeps the network as hash maps of hash maps
+// and re-queries topology on every sweep (graph.hpp:362-481, :117-147); here all of that happens
+// ONCE in bnbp_create and the sweeps touch only flat device arrays.
+#include "../../include/bnbp.h"
+#include "bnbp_kernels.cuh"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <string>
+#include <vector>
+
+using namespace bnbp;
+
+namespace {
+
+thread_local std::string g_err = "";
+
+int fail(int code, const std::string& msg)
+{
+    g_err = msg;
+    return code;
+}
+
+#define CU_TRY(expr)                                                                      \
+    do {                                                                                  \
+        cudaError_t e__ = (expr);                                                         \
+        if (e__ != cudaSuccess) {                                                         \
+            return fail(e__ == cudaErrorMemoryAllocation ? BNBP_ERR_NOMEM : BNBP_ERR_CUDA, \
+                        std::string(#expr) + ": " + cudaGetErrorString(e__));             \
+        }                                                                                 \
+    } while (0)
+
+constexpr int TB = 128;   // cases per tile
+
+struct DevBuf {
+    void* p = nullptr;
+    size_t bytes = 0;
+    int ensure(size_t need)
+    {
+        if (need <= bytes) return BNBP_OK;
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+        CU_TRY(cudaMalloc(&p, need));
+        bytes = need;
+        return BNBP_OK;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        bytes = 0;
+    }
+};
+
+} // namespace
+
+struct bnbp_handle {
+    int device = 0;
+    int precision = BNBP_FP64;
+    size_t tsize = 8;
+    int N = 0, E = 0;
+    int PL = 0, M = 0, W = 0, V = 0;
+    int rmax = 2;              // template bound actually used (2,4,8,16,32,64)
+    int vec = 1;
+    int scratch_vals = 0;      // per-thread scratch values (x VEC)
+    int64_t cpt_values = 0;
+    int64_t max_resident = 0;
+    std::vector<NodeMeta> nodes;
+    std::vector<double> cost_prefix;   // [N+1]
+    std::vector<int32_t> card;
+    // device network
+    DevBuf d_nodes, d_e_card, d_e_lam_out, d_c_pi_out, d_cpt, d_pl_init;
+    // device state for the resident chunk
+    int64_t cap = 0;
+    DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
+    // staging for the host API
+    DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out, s_out_sweeps, s_out_conv;
+    int32_t* pinned_poll = nullptr;    // [4]
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev_total[2] = {nullptr, nullptr};
+    std::vector<cudaEvent_t> ev_sweep;  // pairs per chunk
+    int ev_sweep_used = 0;
+    cudaEvent_t ev_poll[2] = {nullptr, nullptr};
+    // stats of the last run
+    int64_t last_case_sweeps = -1, last_sweep_launches = 0, last_kernel_launches = 0;
+    bool total_recorded = false;
+};
+
+namespace {
+
+int pick_rmax(int maxcard)
+{
+    for (int r : {2, 4, 8, 16, 32, 64})
+        if (maxcard <= r) return r;
+    return -1;
+}
+
+// ---- launch dispatch ----------------------------------------------------------------------------
+template <typename T>
+cudaError_t launch_sweep(const bnbp_handle* h, const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze,
+                         bool check, cudaStream_t st)
+{
+    const int block = TB / h->vec;
+    if (h->vec == 2) {
+        switch (h->rmax) {
+        case 2: return launch_sweep_vr<T, 2, 2>(a, grid, block, smem, freeze, check, st);
+        case 4: return launch_sweep_vr<T, 2, 4>(a, grid, block, smem, freeze, check, st);
+        default: break;
+        }
+    }
+    switch (h->rmax) {
+    case 2: return launch_sweep_vr<T, 1, 2>(a, grid, block, smem, freeze, check, st);
+    case 4: return launch_sweep_vr<T, 1, 4>(a, grid, block, smem, freeze, check, st);
+    case 8: return launch_sweep_vr<T, 1, 8>(a, grid, block, smem, freeze, check, st);
+    case 16: return launch_sweep_vr<T, 1, 16>(a, grid, block, smem, freeze, check, st);
+    case 32: return launch_sweep_vr<T, 1, 32>(a, grid, block, smem, freeze, check, st);
+    default: return launch_sweep_vr<T, 1, 64>(a, grid, block, smem, freeze, check, st);
+    }
+}
+
+template <typename T>
+cudaError_t set_smem(const bnbp_handle* h, int bytes)
+{
+    if (h->vec == 2) {
+        if (h->rmax == 2) return set_sweep_smem<T, 2, 2>(bytes);
+        if (h->rmax == 4) return set_sweep_smem<T, 2, 4>(bytes);
+    }
+    switch (h->rmax) {
+    case 2: return set_sweep_smem<T, 1, 2>(bytes);
+    case 4: return set_sweep_smem<T, 1, 4>(bytes);
+    case 8: return set_sweep_smem<T, 1, 8>(bytes);
+    case 16: return set_sweep_smem<T, 1, 16>(bytes);
+    case 32: return set_sweep_smem<T, 1, 32>(bytes);
+    default: return set_sweep_smem<T, 1, 64>(bytes);
+    }
+}
+
+// node ranges of roughly equal cost for grid.y
+void make_chunks(const bnbp_handle* h, int n_chunks, int32_t* off)
+{
+    const double total = h->cost_prefix[h->N];
+    off[0] = 0;
+    int x = 0;
+    for (int c = 1; c < n_chunks; ++c) {
+        const double target = total * c / n_chunks;
+        while (x < h->N && h->cost_prefix[x + 1] <= target) ++x;
+        off[c] = std::max(x, off[c - 1]);
+    }
+    off[n_chunks] = h->N;
+}
+
+int ensure_state(bnbp_handle* h, int64_t n_cases)
+{
+    int64_t want = (n_cases + TB - 1) / TB * TB;
+    const size_t per_case = (size_t)(h->PL + 2 * (size_t)h->M) * h->tsize + (size_t)h->W * 4 + 3 * h->tsize + 8;
+    int64_t limit = h->max_resident;
+    if (limit <= 0) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        size_t held = h->d_pl.bytes + h->d_msg[0].bytes + h->d_msg[1].bytes + h->d_evbits.bytes;
+        // leave room for output staging (V doubles per case) and the caller's own buffers
+        double usable = 0.80 * (double)(free_b + held);
+        limit = (int64_t)(usable / (double)(per_case + (size_t)h->V * 8));
+    }
+    limit = std::max<int64_t>(TB, limit / TB * TB);
+    want = std::min(want, limit);
+    if (want <= h->cap) return BNBP_OK;
+    // grow: release first so the new allocation can reuse the space
+    h->d_pl.release(); h->d_msg[0].release(); h->d_msg[1].release(); h->d_evbits.release();
+    h->d_delta.release(); h->d_status.release(); h->d_sweeps.release();
+    h->cap = 0;
+    int rc;
+    if ((rc = h->d_pl.ensure((size_t)want * h->PL * h->tsize))) return rc;
+    if ((rc = h->d_msg[0].ensure(std::max<size_t>(16, (size_t)want * h->M * h->tsize)))) return rc;
+    if ((rc = h->d_msg[1].ensure(std::max<size_t>(16, (size_t)want * h->M * h->tsize)))) return rc;
+    if ((rc = h->d_evbits.ensure((size_t)want * h->W * 4))) return rc;
+    if ((rc = h->d_delta.ensure((size_t)want * 3 * h->tsize))) return rc;
+    if ((rc = h->d_status.ensure((size_t)want))) return rc;
+    if ((rc = h->d_sweeps.ensure((size_t)want * 4))) return rc;
+    h->cap = want;
+    return BNBP_OK;
+}
+
+struct DevEvidence {       // device pointers, offsets absolute with the given bases
+    const int64_t* ev_off; int64_t ev_base;
+    const int32_t* ev_node; const int32_t* ev_state;
+    const int64_t* ev_val_off; const double* ev_values; int64_t ev_val_base;
+};
+
+// Runs init -> sweeps -> beliefs for n (<= cap) cases whose evidence is on the device.
+template <typename T, typename OUT>
+int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_params& prm, OUT* d_out,
+              int32_t* d_out_sweeps, uint8_t* d_out_conv, cudaStream_t st, int64_t* planned_sweeps)
+{
+    const int tiles = (int)((n + TB - 1) / TB);
+    int32_t* d_last_active = reinterpret_cast<int32_t*>(h->d_misc.p);
+    int32_t* d_error = d_last_active + 1;
+    const bool eps_mode = prm.epsilon > 0.0;
+    const int max_sweeps = prm.max_sweeps > 0 ? prm.max_sweeps : (1 << 30);
+    const int interval = prm.check_interval > 0 ? prm.check_interval : 1;
+    if (!eps_mode && prm.max_sweeps <= 0)
+        return fail(BNBP_ERR_INVALID, "epsilon <= 0 needs a positive max_sweeps (the loop would never end)");
+
+    CU_TRY(cudaMemsetAsync(d_last_active, 0xFF, 4, st));   // -1
+    {
+        InitArgs<T> ia;
+        ia.nodes = (const NodeMeta*)h->d_nodes.p;
+        ia.pl_init = (const T*)h->d_pl_init.p;
+        ia.pl = (T*)h->d_pl.p; ia.msg0 = (T*)h->d_msg[0].p; ia.evbits = (uint32_t*)h->d_evbits.p;
+        ia.PL = h->PL; ia.M = h->M; ia.W = h->W; ia.TB = TB; ia.n_nodes = h->N;
+        ia.n_valid = n;
+        ia.ev_off = de.ev_off; ia.ev_base = de.ev_base; ia.ev_node = de.ev_node; ia.ev_state = de.ev_state;
+        ia.ev_val_off = de.ev_val_off; ia.ev_values = de.ev_values; ia.ev_val_base = de.ev_val_base;
+        ia.delta = (T*)h->d_delta.p; ia.cap = h->cap;
+        ia.status = (uint8_t*)h->d_status.p; ia.sweeps = (int32_t*)h->d_sweeps.p;
+        ia.error_flag = d_error;
+        init_kernel<T><<<tiles, TB, 0, st>>>(ia);
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+    }
+
+    SweepArgs<T> sa;
+    memset(&sa, 0, sizeof sa);
+    sa.nodes = (const NodeMeta*)h->d_nodes.p;
+    sa.e_card = (const int32_t*)h->d_e_card.p;
+    sa.e_lam_out = (const int32_t*)h->d_e_lam_out.p;
+    sa.c_pi_out = (const int32_t*)h->d_c_pi_out.p;
+    sa.cpt = (const T*)h->d_cpt.p;
+    sa.pl = (T*)h->d_pl.p;
+    sa.evbits = (const uint32_t*)h->d_evbits.p;
+    sa.PL = h->PL; sa.M = h->M; sa.W = h->W; sa.TB = TB;
+    // enough threads to fill 148 SMs a few times over: split the node walk when the batch is small
+    const int64_t threads_per_row = (int64_t)tiles * (TB / h->vec);
+    int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, h->N / 8)),
+                                          std::max<int64_t>(1, (148 * 2048 * 2 + threads_per_row - 1) / threads_per_row));
+    sa.n_chunks = n_chunks;
+    make_chunks(h, n_chunks, sa.chunk_off);
+    sa.status = (uint8_t*)h->d_status.p;
+    sa.sweeps = (int32_t*)h->d_sweeps.p;
+    sa.last_active = d_last_active;
+    sa.eps = (T)prm.epsilon;
+    sa.damping = (T)prm.damping;
+    T* delta = (T*)h->d_delta.p;
+    const size_t smem = (size_t)(TB / h->vec) * (size_t)h->scratch_vals * h->vec * sizeof(T);
+    dim3 grid(tiles, n_chunks);
+
+    // event pair around the sweeps of this chunk
+    if ((int)h->ev_sweep.size() < 2 * (h->ev_sweep_used + 1)) {
+        cudaEvent_t a, b;
+        CU_TRY(cudaEventCreate(&a));
+        CU_TRY(cudaEventCreate(&b));
+        h->ev_sweep.push_back(a);
+        h->ev_sweep.push_back(b);
+    }
+    CU_TRY(cudaEventRecord(h->ev_sweep[2 * h->ev_sweep_used], st));
+
+    int t = 0;
+    bool prev_tested = false;
+    const int POLL = 8;
+    int polls_issued = 0;
+    bool stop = false;
+    while (t < max_sweeps && !stop) {
+        const int t_end = (int)std::min<int64_t>((int64_t)t + POLL, max_sweeps);
+        for (; t < t_end; ++t) {
+            const bool tested = eps_mode && (((t + 1) % interval) == 0 || t + 1 >= max_sweeps);
+            const bool check = tested || prm.damping != 0.0;
+            sa.msg_cur = (const T*)h->d_msg[t & 1].p;
+            sa.msg_nxt = (T*)h->d_msg[(t + 1) & 1].p;
+            sa.delta_prev = delta + (size_t)((t + 2) % 3) * h->cap;
+            sa.delta_cur = delta + (size_t)(t % 3) * h->cap;
+            sa.delta_next = delta + (size_t)((t + 1) % 3) * h->cap;
+            sa.sweep_index = t;
+            sa.prev_tested = prev_tested ? 1 : 0;
+            cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode, check, st);
+            if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
+            prev_tested = tested;
+            h->last_sweep_launches++;
+            h->last_kernel_launches++;
+        }
+        if (eps_mode && t < max_sweeps) {
+            // asynchronous termination poll: keep one batch of launches in flight while the flag
+            // of the batch before travels back (speculative launches exit on the device at once)
+            const int slot = polls_issued & 1;
+            if (polls_issued >= 2) {
+                CU_TRY(cudaEventSynchronize(h->ev_poll[slot]));
+                // value copied after the sweeps [.., t_prev) of two batches ago
+                const int t_prev = t - 2 * POLL;
+                if (h->pinned_poll[slot] < t_prev - 1) stop = true;
+            }
+            if (!stop) {
+                CU_TRY(cudaMemcpyAsync(&h->pinned_poll[slot], d_last_active, 4, cudaMemcpyDeviceToHost, st));
+                CU_TRY(cudaEventRecord(h->ev_poll[slot], st));
+                polls_issued++;
+            }
+        }
+    }
+    const int total_sweeps = t;
+    CU_TRY(cudaEventRecord(h->ev_sweep[2 * h->ev_sweep_used + 1], st));
+    h->ev_sweep_used++;
+    if (eps_mode) {
+        const int last = total_sweeps - 1;
+        finalize_kernel<T><<<(unsigned)((h->cap + 255) / 256), 256, 0, st>>>(
+            (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta + (size_t)(last % 3) * h->cap,
+            prev_tested ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles * TB);
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+    } else {
+        CU_TRY(cudaMemsetAsync(h->d_status.p, 0, (size_t)tiles * TB, st));
+        // sweeps[] = total for every case
+        finalize_kernel<T><<<(unsigned)((h->cap + 255) / 256), 256, 0, st>>>(
+            (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta, 0, (T)0, total_sweeps, (int64_t)tiles * TB);
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+    }
+
+    belief_kernel<T, OUT><<<tiles, TB, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, TB,
+                                                h->V, n, d_out, (const uint8_t*)h->d_status.p,
+                                                (const int32_t*)h->d_sweeps.p, d_out_sweeps, d_out_conv);
+    CU_TRY(cudaGetLastError());
+    h->last_kernel_launches++;
+    if (planned_sweeps) *planned_sweeps = eps_mode ? -1 : (int64_t)total_sweeps * n;
+    return BNBP_OK;
+}
+
+int check_error_flag(bnbp_handle* h, cudaStream_t st)
+{
+    int32_t flag = 0;
+    int32_t* d_error = reinterpret_cast<int32_t*>(h->d_misc.p) + 1;
+    CU_TRY(cudaMemcpyAsync(&flag, d_error, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(cudaStreamSynchronize(st));
+    if (flag) {
+        cudaMemsetAsync(d_error, 0, 4, st);
+        const char* what = flag == 1 ? "evidence node id out of range"
+                         : flag == 2 ? "soft evidence row length != cardinality of the node"
+                                     : "hard evidence state out of range";
+        return fail(BNBP_ERR_INVALID, what);
+    }
+    return BNBP_OK;
+}
+
+int validate_params(const bnbp_run_params* prm)
+{
+    if (!prm) return fail(BNBP_ERR_INVALID, "run params are NULL");
+    if (std::isnan(prm->epsilon)) return fail(BNBP_ERR_INVALID, "epsilon is NaN");
+    if (!(prm->damping >= 0.0 && prm->damping < 1.0)) return fail(BNBP_ERR_INVALID, "damping must be in [0,1)");
+    return BNBP_OK;
+}
+
+template <typename T>
+int upload_cpt(bnbp_handle* h, const double* cpt, int64_t n)
+{
+    std::vector<T> tmp((size_t)std::max<int64_t>(n, 1));
+    for (int64_t i = 0; i < n; ++i) tmp[(size_t)i] = (T)cpt[i];
+    int rc = h->d_cpt.ensure(tmp.size() * sizeof(T));
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(h->d_cpt.p, tmp.data(), tmp.size() * sizeof(T), cudaMemcpyHostToDevice));
+    // pi of a root starts as the RAW prior row (belief_propagation.hpp:58-64)
+    std::vector<T> init((size_t)h->PL, T(1));
+    for (int x = 0; x < h->N; ++x)
+        if (h->nodes[x].k == 0)
+            for (int i = 0; i < h->nodes[x].card; ++i)
+                init[(size_t)h->nodes[x].pl_off + i] = (T)cpt[h->nodes[x].cpt_off + i];
+    rc = h->d_pl_init.ensure(init.size() * sizeof(T));
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(h->d_pl_init.p, init.data(), init.size() * sizeof(T), cudaMemcpyHostToDevice));
+    return BNBP_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* bnbp_last_error(void) { return g_err.c_str(); }
+
+int bnbp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_handle** out)
+{
+    if (!net || !out) return fail(BNBP_ERR_INVALID, "bnbp_create: NULL argument");
+    *out = nullptr;
+    const int N = net->n_nodes;
+    if (N <= 0 || !net->card || !net->parent_off || !net->cpt_off || !net->cpt)
+        return fail(BNBP_ERR_INVALID, "bnbp_create: empty or incomplete network");
+    const int E = net->parent_off[N];
+    if (net->parent_off[0] != 0 || net->cpt_off[0] != 0 || E < 0 || (E > 0 && !net->parents))
+        return fail(BNBP_ERR_INVALID, "bnbp_create: malformed offset arrays");
+
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BNBP_ERR_NO_DEVICE, "no CUDA device: libbnbp has no CPU fallback");
+    }
+    int dev = opt ? opt->device : -1;
+    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(BNBP_ERR_INVALID, "bnbp_create: device ordinal out of range");
+    CU_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(BNBP_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: kernels are built for sm_100a only");
+
+    std::unique_ptr<bnbp_handle> h(new bnbp_handle());
+    h->device = dev;
+    h->precision = (opt && opt->precision == BNBP_FP32) ? BNBP_FP32 : BNBP_FP64;
+    h->tsize = h->precision == BNBP_FP32 ? 4 : 8;
+    h->max_resident = opt ? opt->max_resident_cases : 0;
+    h->N = N;
+    h->E = E;
+    h->card.assign(net->card, net->card + N);
+
+    // ---- validate + derive topology (the checks the reference leaves as UB, graph.hpp:117-124) ----
+    int maxcard = 1;
+    for (int x = 0; x < N; ++x) {
+        if (net->card[x] < 1) return fail(BNBP_ERR_INVALID, "node " + std::to_string(x) + ": cardinality < 1");
+        maxcard = std::max(maxcard, (int)net->card[x]);
+    }
+    h->rmax = pick_rmax(maxcard);
+    if (h->rmax < 0) return fail(BNBP_ERR_INVALID, "cardinality > 64 is not supported");
+    std::vector<int> nchild(N, 0);
+    for (int x = 0; x < N; ++x) {
+        const int k = net->parent_off[x + 1] - net->parent_off[x];
+        if (k < 0) return fail(BNBP_ERR_INVALID, "parent_off not monotone");
+        if (k > KMAX) return fail(BNBP_ERR_INVALID, "node " + std::to_string(x) + ": in-degree > " + std::to_string(KMAX) + " is not supported");
+        int64_t Q = 1;
+        for (int e = net->parent_off[x]; e < net->parent_off[x + 1]; ++e) {
+            const int u = net->parents[e];
+            if (u < 0 || u >= N || u == x) return fail(BNBP_ERR_INVALID, "node " + std::to_string(x) + ": bad parent id");
+            if (e > net->parent_off[x] && net->parents[e - 1] >= u)
+                return fail(BNBP_ERR_INVALID, "node " + std::to_string(x) + ": parents must be strictly ascending");
+            Q *= net->card[u];
+            nchild[u]++;
+        }
+        if (net->cpt_off[x + 1] - net->cpt_off[x] != Q * net->card[x])
+            return fail(BNBP_ERR_INVALID, "node " + std::to_string(x) + ": CPT size does not match parent configurations (missing rows)");
+    }
+    {   // DAG check (graph_t::add_edge refuses cycles, graph.hpp:268-275)
+        std::vector<int> indeg(N), stack;
+        std::vector<std::vector<int>> ch(N);
+        for (int x = 0; x < N; ++x) {
+            indeg[x] = net->parent_off[x + 1] - net->parent_off[x];
+            for (int e = net->parent_off[x]; e < net->parent_off[x + 1]; ++e) ch[net->parents[e]].push_back(x);
+            if (!indeg[x]) stack.push_back(x);
+        }
+        int seen = 0;
+        while (!stack.empty()) {
+            int u = stack.back(); stack.pop_back(); ++seen;
+            for (int c : ch[u]) if (--indeg[c] == 0) stack.push_back(c);
+        }
+        if (seen != N) return fail(BNBP_ERR_INVALID, "network has a directed cycle");
+    }
+
+    // ---- slot layout -------------------------------------------------------------------------------
+    // pi/lambda region: [pi_X | lambda_X] per node.  Message buffer: pi-messages in in-edge order
+    // (grouped by child), then lambda-messages in out-edge order (grouped by parent), so that
+    // everything node X READS is contiguous; what it writes is scattered to its neighbours' blocks.
+    h->nodes.resize(N);
+    std::vector<int32_t> e_card(std::max(E, 1)), e_lam_out(std::max(E, 1)), c_pi_out(std::max(E, 1));
+    std::vector<int32_t> e_pin(std::max(E, 1));      // slot of pi-msg of in-edge e
+    int pl = 0, bel = 0, pin = 0;
+    for (int x = 0; x < N; ++x) {
+        NodeMeta& nd = h->nodes[x];
+        nd.card = net->card[x];
+        nd.k = net->parent_off[x + 1] - net->parent_off[x];
+        nd.m = nchild[x];
+        nd.pl_off = pl; pl += 2 * nd.card;
+        nd.bel_off = bel; bel += nd.card;
+        nd.e0 = net->parent_off[x];
+        nd.cpt_off = net->cpt_off[x];
+        nd.pin_off = pin;
+        nd.pad = 0;
+        for (int e = nd.e0; e < nd.e0 + nd.k; ++e) {
+            e_card[e] = net->card[net->parents[e]];
+            e_pin[e] = pin;
+            pin += e_card[e];
+        }
+    }
+    h->PL = pl;
+    h->V = bel;
+    int lin = pin, c0 = 0;
+    for (int x = 0; x < N; ++x) {
+        h->nodes[x].lin_off = lin; lin += nchild[x] * net->card[x];
+        h->nodes[x].c0 = c0; c0 += nchild[x];
+    }
+    h->M = lin;
+    h->W = (N + 31) / 32;
+    {   // children in ascending child index (graph_t::out_vertexes scans the adjacency row, graph.hpp:362-386)
+        std::vector<int> fill(N, 0);
+        for (int x = 0; x < N; ++x)
+            for (int e = h->nodes[x].e0; e < h->nodes[x].e0 + h->nodes[x].k; ++e) {
+                const int u = net->parents[e];
+                const int ci = fill[u]++;
+                e_lam_out[e] = h->nodes[u].lin_off + ci * net->card[u];   // X writes lambda-msg here, U reads it
+                c_pi_out[h->nodes[u].c0 + ci] = e_pin[e];                 // U writes pi-msg here, X reads it
+            }
+    }
+    // scratch: outer parents' messages + accumulators
+    int so_max = 0;
+    h->cost_prefix.assign(N + 1, 0.0);
+    for (int x = 0; x < N; ++x) {
+        const NodeMeta& nd = h->nodes[x];
+        int so = 0, sin = 0;
+        for (int j = 0; j < nd.k; ++j) { sin += e_card[nd.e0 + j]; if (j < nd.k - 1) so += e_card[nd.e0 + j]; }
+        so_max = std::max(so_max, so);
+        const double cptn = (double)(net->cpt_off[x + 1] - net->cpt_off[x]);
+        h->cost_prefix[x + 1] = h->cost_prefix[x] + 2.0 * (2 * nd.card + sin + nd.m * nd.card) + 0.5 * cptn +
+                                (double)nd.m * nd.m * nd.card;
+    }
+    h->scratch_vals = 2 * so_max;
+    h->vec = (h->rmax <= 4) ? 2 : 1;
+    h->cpt_values = net->cpt_off[N];
+    const size_t smem = (size_t)(TB / h->vec) * (size_t)h->scratch_vals * h->vec * h->tsize;
+    if (smem > 200 * 1024) return fail(BNBP_ERR_INVALID, "parent sets too wide for the shared-memory scratch");
+
+    // ---- upload -------------------------------------------------------------------------------------
+    int rc;
+    if ((rc = h->d_nodes.ensure(sizeof(NodeMeta) * N))) return rc;
+    CU_TRY(cudaMemcpy(h->d_nodes.p, h->nodes.data(), sizeof(NodeMeta) * N, cudaMemcpyHostToDevice));
+    const size_t eb = sizeof(int32_t) * std::max(E, 1);
+    if ((rc = h->d_e_card.ensure(eb)) || (rc = h->d_e_lam_out.ensure(eb)) || (rc = h->d_c_pi_out.ensure(eb))) return rc;
+    CU_TRY(cudaMemcpy(h->d_e_card.p, e_card.data(), eb, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_e_lam_out.p, e_lam_out.data(), eb, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(h->d_c_pi_out.p, c_pi_out.data(), eb, cudaMemcpyHostToDevice));
+    rc = h->precision == BNBP_FP32 ? upload_cpt<float>(h.get(), net->cpt, net->cpt_off[N])
+                                   : upload_cpt<double>(h.get(), net->cpt, net->cpt_off[N]);
+    if (rc) return rc;
+    if ((rc = h->d_misc.ensure(64))) return rc;
+    CU_TRY(cudaMemset(h->d_misc.p, 0, 64));
+    CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaEventCreate(&h->ev_total[i]));
+        CU_TRY(cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
+    }
+    CU_TRY(cudaMallocHost((void**)&h->pinned_poll, 4 * sizeof(int32_t)));
+    // opt in to the dynamic shared memory the scratch needs
+    if (smem > 48 * 1024) {
+        cudaError_t e = h->precision == BNBP_FP32 ? set_smem<float>(h.get(), (int)smem) : set_smem<double>(h.get(), (int)smem);
+        if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("shared-memory opt-in: ") + cudaGetErrorString(e));
+    }
+    *out = h.release();
+    return BNBP_OK;
+}
+
+void bnbp_destroy(bnbp_handle* h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    if (h->stream) cudaStreamSynchronize(h->stream);
+    for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
+                      &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
+                      &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out,
+                      &h->s_out_sweeps, &h->s_out_conv})
+        b->release();
+    for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_total[i]) cudaEventDestroy(h->ev_total[i]);
+        if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
+    }
+    if (h->pinned_poll) cudaFreeHost(h->pinned_poll);
+    if (h->stream) cudaStreamDestroy(h->stream);
+    delete h;
+}
+
+int bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values)
+{
+    if (!h || !cpt) return fail(BNBP_ERR_INVALID, "bnbp_refresh_cpt: NULL argument");
+    if (n_values != h->cpt_values) return fail(BNBP_ERR_INVALID, "bnbp_refresh_cpt: CPT size changed (topology edits need a new handle)");
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamSynchronize(h->stream));
+    return h->precision == BNBP_FP32 ? upload_cpt<float>(h, cpt, n_values) : upload_cpt<double>(h, cpt, n_values);
+}
+
+int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm, void* out_marginals,
+                          int32_t* out_sweeps, uint8_t* out_converged, void* stream)
+{
+    if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_run_batch_device: NULL argument");
+    int rc = validate_params(prm);
+    if (rc) return rc;
+    if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
+    if (ev->n_cases > 0 && !ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    h->last_sweep_launches = h->last_kernel_launches = 0;
+    h->last_case_sweeps = 0;
+    h->ev_sweep_used = 0;
+    if (ev->n_cases == 0) return BNBP_OK;
+    if ((rc = ensure_state(h, ev->n_cases))) return rc;
+    CU_TRY(cudaEventRecord(h->ev_total[0], st));
+    bool exact = true;
+    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += h->cap) {
+        const int64_t n = std::min<int64_t>(h->cap, ev->n_cases - c0);
+        DevEvidence de{ev->ev_off + c0, 0, ev->ev_node, ev->ev_state, ev->ev_val_off, ev->ev_values, 0};
+        int64_t planned = 0;
+        if (h->precision == BNBP_FP32)
+            rc = run_chunk<float, float>(h, n, de, *prm, (float*)out_marginals + (size_t)c0 * h->V,
+                                         out_sweeps ? out_sweeps + c0 : nullptr,
+                                         out_converged ? out_converged + c0 : nullptr, st, &planned);
+        else
+            rc = run_chunk<double, double>(h, n, de, *prm, (double*)out_marginals + (size_t)c0 * h->V,
+                                           out_sweeps ? out_sweeps + c0 : nullptr,
+                                           out_converged ? out_converged + c0 : nullptr, st, &planned);
+        if (rc) return rc;
+        if (planned < 0) exact = false; else h->last_case_sweeps += planned;
+    }
+    if (!exact) h->last_case_sweeps = -1;
+    CU_TRY(cudaEventRecord(h->ev_total[1], st));
+    h->total_recorded = true;
+    return BNBP_OK;
+}
+
+int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm, double* out_marginals,
+                   int32_t* out_sweeps, uint8_t* out_converged)
+{
+    if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_run_batch: NULL argument");
+    int rc = validate_params(prm);
+    if (rc) return rc;
+    if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
+    if (ev->n_cases > 0 && !ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
+    const int64_t nnz = ev->n_cases ? ev->ev_off[ev->n_cases] : 0;
+    if (nnz > 0 && !ev->ev_node) return fail(BNBP_ERR_INVALID, "ev_node is NULL");
+    const bool soft = ev->ev_values != nullptr;
+    if (nnz > 0 && !soft && !ev->ev_state) return fail(BNBP_ERR_INVALID, "neither ev_state nor ev_values given");
+    if (soft && !ev->ev_val_off) return fail(BNBP_ERR_INVALID, "ev_val_off is NULL");
+    for (int64_t c = 0; c < ev->n_cases; ++c)
+        if (ev->ev_off[c + 1] < ev->ev_off[c]) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    h->last_sweep_launches = h->last_kernel_launches = 0;
+    h->last_case_sweeps = 0;
+    h->ev_sweep_used = 0;
+    if (ev->n_cases == 0) return BNBP_OK;
+    if ((rc = ensure_state(h, ev->n_cases))) return rc;
+    const int64_t cap = h->cap;
+    if ((rc = h->s_out.ensure((size_t)cap * h->V * 8))) return rc;
+    if ((rc = h->s_out_sweeps.ensure((size_t)cap * 4))) return rc;
+    if ((rc = h->s_out_conv.ensure((size_t)cap))) return rc;
+    CU_TRY(cudaEventRecord(h->ev_total[0], st));
+    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += cap) {
+        const int64_t n = std::min<int64_t>(cap, ev->n_cases - c0);
+        const int64_t a = ev->ev_off[c0], b = ev->ev_off[c0 + n];
+        if ((rc = h->s_ev_off.ensure((size_t)(n + 1) * 8))) return rc;
+        if ((rc = h->s_ev_node.ensure(std::max<size_t>(16, (size_t)(b - a) * 4)))) return rc;
+        CU_TRY(cudaMemcpyAsync(h->s_ev_off.p, ev->ev_off + c0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
+        if (b > a) CU_TRY(cudaMemcpyAsync(h->s_ev_node.p, ev->ev_node + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
+        DevEvidence de{(const int64_t*)h->s_ev_off.p, a, (const int32_t*)h->s_ev_node.p, nullptr, nullptr, nullptr, 0};
+        if (soft) {
+            const int64_t va = ev->ev_val_off[a], vb = ev->ev_val_off[b];
+            if ((rc = h->s_ev_val_off.ensure((size_t)(b - a + 1) * 8))) return rc;
+            if ((rc = h->s_ev_values.ensure(std::max<size_t>(16, (size_t)(vb - va) * 8)))) return rc;
+            CU_TRY(cudaMemcpyAsync(h->s_ev_val_off.p, ev->ev_val_off + a, (size_t)(b - a + 1) * 8, cudaMemcpyHostToDevice, st));
+            if (vb > va) CU_TRY(cudaMemcpyAsync(h->s_ev_values.p, ev->ev_values + va, (size_t)(vb - va) * 8, cudaMemcpyHostToDevice, st));
+            de.ev_val_off = (const int64_t*)h->s_ev_val_off.p;
+            de.ev_values = (const double*)h->s_ev_values.p;
+            de.ev_val_base = va;
+        } else {
+            if ((rc = h->s_ev_state.ensure(std::max<size_t>(16, (size_t)(b - a) * 4)))) return rc;
+            if (b > a) CU_TRY(cudaMemcpyAsync(h->s_ev_state.p, ev->ev_state + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
+            de.ev_state = (const int32_t*)h->s_ev_state.p;
+        }
+        if (h->precision == BNBP_FP32)
+            rc = run_chunk<float, double>(h, n, de, *prm, (double*)h->s_out.p, (int32_t*)h->s_out_sweeps.p,
+                                          (uint8_t*)h->s_out_conv.p, st, nullptr);
+        else
+            rc = run_chunk<double, double>(h, n, de, *prm, (double*)h->s_out.p, (int32_t*)h->s_out_sweeps.p,
+                                           (uint8_t*)h->s_out_conv.p, st, nullptr);
+        if (rc) return rc;
+        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, h->s_out.p, (size_t)n * h->V * 8, cudaMemcpyDeviceToHost, st));
+        std::vector<int32_t> sw;
+        if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps + c0, h->s_out_sweeps.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
+        if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged + c0, h->s_out_conv.p, (size_t)n, cudaMemcpyDeviceToHost, st));
+        // staging buffers are reused by the next chunk
+        CU_TRY(cudaStreamSynchronize(st));
+    }
+    CU_TRY(cudaEventRecord(h->ev_total[1], st));
+    h->total_recorded = true;
+    if ((rc = check_error_flag(h, st))) return rc;
+    if (out_sweeps) {
+        int64_t s = 0;
+        for (int64_t c = 0; c < ev->n_cases; ++c) s += out_sweeps[c];
+        h->last_case_sweeps = s;
+    } else {
+        h->last_case_sweeps = -1;
+    }
+    return BNBP_OK;
+}
+
+int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
+{
+    if (!hc || !out) return fail(BNBP_ERR_INVALID, "bnbp_get_stats: NULL argument");
+    bnbp_handle* h = const_cast<bnbp_handle*>(hc);
+    memset(out, 0, sizeof *out);
+    out->state_values_per_case = (int64_t)h->PL + h->M;
+    out->msg_values_per_case = h->M;
+    out->belief_values_per_case = h->V;
+    out->cpt_values = h->cpt_values;
+    out->bytes_per_value = (int64_t)h->tsize;
+    out->last_case_sweeps = h->last_case_sweeps;
+    out->last_sweep_launches = h->last_sweep_launches;
+    out->last_kernel_launches = h->last_kernel_launches;
+    out->resident_cases = h->cap;
+    out->last_sweep_ms = -1.0;
+    out->last_total_ms = -1.0;
+    if (h->total_recorded) {
+        cudaSetDevice(h->device);
+        if (cudaEventSynchronize(h->ev_total[1]) == cudaSuccess) {
+            float ms = 0;
+            if (cudaEventElapsedTime(&ms, h->ev_total[0], h->ev_total[1]) == cudaSuccess) out->last_total_ms = ms;
+            double sw = 0;
+            bool ok = h->ev_sweep_used > 0;
+            for (int i = 0; i < h->ev_sweep_used; ++i) {
+                if (cudaEventElapsedTime(&ms, h->ev_sweep[2 * i], h->ev_sweep[2 * i + 1]) == cudaSuccess) sw += ms;
+                else ok = false;
+            }
+            if (ok) out->last_sweep_ms = sw;
+        }
+        cudaGetLastError();
+    }
+    return BNBP_OK;
+}
+
+} // extern "C"

@@ -1,0 +1,204 @@
+// bnbp_kernels.cuh — sm_100a kernels of the batched loopy-BP path.
+//
+// Work decomposition: one thread owns VEC evidence cases and walks a
+// contiguous range of nodes; a block owns one TILE of TB cases.  All per-case state lives in HBM
+// as batch-minor SoA tiles  state[tile][slot][TB]  so that a warp reading one slot touches
+// 32*VEC consecutive values (coalesced double2 / float4 accesses).  Everything that does not
+// depend on the case (topology, cardinalities, CPT entries) is warp-uniform and is fetched
+// through the read-only path as broadcast loads.
+//
+// One sweep = one launch of sweep_kernel = the whole body of the reference's while(true)
+// (bayesian/inference/belief_propagation.hpp:75-148) for every resident case:
+//   per node X (a "gather" formulation, every state slot is read once and written once):
+//     reads   pi_X, lambda_X, pi-messages X<-parents, lambda-messages children->X   (time t)
+//     writes  pi_X, lambda_X (in place: X is their only reader),
+//             lambda-messages X->parents, pi-messages X->children                  (time t+1 buffer)
+//   :202-218 calculate_pi_i, :240-266 calculate_lambda_k, :174-200 calculate_pi,
+//   :220-238 calculate_lambda, :105-131 delta, :135-143 commit (= buffer swap), :298-311 normalize.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <float.h>
+
+namespace bnbp {
+
+constexpr int KMAX = 8;        // max in-degree handled by the templated recursion
+constexpr int MAX_CHUNKS = 192;
+
+struct NodeMeta {              // 48 bytes, warp-uniform
+    int32_t card;              // r_X
+    int32_t k;                 // number of parents
+    int32_t m;                 // number of children
+    int32_t pl_off;            // slot of pi_X in the pi/lambda region (lambda_X at pl_off + card)
+    int32_t pin_off;           // msg-buffer slot of the first pi-message into X (in-edge order)
+    int32_t lin_off;           // msg-buffer slot of the first lambda-message into X (m blocks of r_X)
+    int32_t e0;                // first in-edge index
+    int32_t c0;                // first out-edge index
+    int64_t cpt_off;           // offset into the device CPT arena
+    int32_t bel_off;           // offset of X in a row of marginals
+    int32_t pad;
+};
+
+template <typename T> struct SweepArgs {
+    const NodeMeta* nodes;
+    const int32_t*  e_card;     // [E] cardinality of the parent of in-edge e
+    const int32_t*  e_lam_out;  // [E] msg slot where the child writes lambda-msg (child->parent)
+    const int32_t*  c_pi_out;   // [E] msg slot where the parent writes pi-msg (parent->child), out-edge order
+    const T*        cpt;
+    T*              pl;         // [tiles][PL][TB]
+    const T*        msg_cur;    // [tiles][M][TB]
+    T*              msg_nxt;
+    const uint32_t* evbits;     // [tiles][W][TB]
+    int32_t PL, M, W, TB;
+    int32_t n_chunks;
+    int32_t chunk_off[MAX_CHUNKS + 1];
+    // convergence bookkeeping (only touched when FREEZE / CHECK)
+    const T* delta_prev;        // delta of the previous sweep (valid if prev_tested)
+    T*       delta_cur;         // atomicMax target of this sweep (CHECK)
+    T*       delta_next;        // reset to the :105 floor for the next sweep
+    uint8_t* status;            // 0 active, 1 converged (frozen)
+    int32_t* sweeps;            // sweeps executed when the case froze
+    int32_t* last_active;       // largest sweep index that still had an active case (-1 at start)
+    int32_t  sweep_index;       // t (0-based)
+    int32_t  prev_tested;
+    T eps;
+    T damping;
+};
+
+template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pk { T v[VEC]; };
+
+template <typename T, int VEC> __device__ __forceinline__ Pk<T, VEC> ldp(const T* p)
+{
+    return *reinterpret_cast<const Pk<T, VEC>*>(p);
+}
+template <typename T, int VEC> __device__ __forceinline__ void stp(T* p, const Pk<T, VEC>& x)
+{
+    *reinterpret_cast<Pk<T, VEC>*>(p) = x;
+}
+
+template <typename T> struct Lim;
+template <> struct Lim<double> { static __device__ __forceinline__ double floor_() { return DBL_MIN; } };
+template <> struct Lim<float>  { static __device__ __forceinline__ float floor_() { return FLT_MIN; } };
+
+// max |new-old| with std::max(running, NaN) == running (:113-116): fmax ignores NaN.
+__device__ __forceinline__ double absdiff_max(double run, double a, double b) { return fmax(run, fabs(a - b)); }
+__device__ __forceinline__ float  absdiff_max(float run, float a, float b) { return fmaxf(run, fabsf(a - b)); }
+
+// non-negative IEEE values order like their bit patterns
+__device__ __forceinline__ void atomic_max_nonneg(double* p, double v)
+{
+    atomicMax(reinterpret_cast<unsigned long long*>(p), (unsigned long long)__double_as_longlong(v));
+}
+__device__ __forceinline__ void atomic_max_nonneg(float* p, float v)
+{
+    atomicMax(reinterpret_cast<unsigned int*>(p), __float_as_uint(v));
+}
+
+// Sweep launchers: defined in bnbp_sweep.cuh, explicitly instantiated one (T, VEC, RMAX) per
+// translation unit (bnbp_sweep_inst.cu) so the build parallelises.
+template <typename T, int VEC, int RMAX>
+cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, int block, size_t smem, bool freeze, bool check,
+                            cudaStream_t st);
+template <typename T, int VEC, int RMAX> cudaError_t set_sweep_smem(int bytes);
+
+// ------------------------------------------------------------------------------------------------
+// K0: initial state of one tile (belief_propagation.hpp:33-73).  One thread per case.
+template <typename T> struct InitArgs {
+    const NodeMeta* nodes;
+    const T* pl_init;           // [PL] 1 everywhere, raw prior row for the pi of roots (:58-64)
+    T* pl; T* msg0; uint32_t* evbits;
+    int32_t PL, M, W, TB, n_nodes;
+    int64_t n_valid;            // cases actually present in this chunk (rest is padding)
+    const int64_t* ev_off;      // [n_valid+1], absolute offsets
+    int64_t ev_base;            // ev_off value of the first case of the chunk in the arrays below
+    const int32_t* ev_node; const int32_t* ev_state;
+    const int64_t* ev_val_off; const double* ev_values; int64_t ev_val_base;
+    T* delta; int64_t cap;      // delta[3][cap]
+    uint8_t* status; int32_t* sweeps;
+    int32_t* error_flag;
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128) init_kernel(const InitArgs<T> a)
+{
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const size_t TB = (size_t)a.TB;
+    const int64_t c = (int64_t)tile * a.TB + lane;
+    T* pl = a.pl + ((size_t)tile * a.PL) * TB + lane;
+    T* msg = a.msg0 + ((size_t)tile * a.M) * TB + lane;
+    uint32_t* evb = a.evbits + ((size_t)tile * a.W) * TB + lane;
+    for (int s = 0; s < a.PL; ++s) pl[(size_t)s * TB] = __ldg(a.pl_init + s);
+    for (int s = 0; s < a.M; ++s) msg[(size_t)s * TB] = T(1);
+    for (int w = 0; w < a.W; ++w) evb[(size_t)w * TB] = 0u;
+    for (int i = 0; i < 3; ++i) a.delta[(size_t)i * a.cap + c] = Lim<T>::floor_();
+    a.sweeps[c] = 0;
+    a.status[c] = (c < a.n_valid) ? 0 : 1;
+    if (c >= a.n_valid) return;
+    // evidence goes into BOTH pi and lambda (:69-73); the same thread wrote the defaults above
+    const int64_t e0 = a.ev_off[c] - a.ev_base, e1 = a.ev_off[c + 1] - a.ev_base;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int node = a.ev_node[e];
+        if (node < 0 || node >= a.n_nodes) { *a.error_flag = 1; continue; }
+        const NodeMeta nd = a.nodes[node];
+        const int r = nd.card;
+        if (a.ev_values) {
+            const int64_t vo = a.ev_val_off[e] - a.ev_val_base;
+            if (a.ev_val_off[e + 1] - a.ev_val_off[e] != r) { *a.error_flag = 2; continue; }
+            for (int i = 0; i < r; ++i) {
+                const T val = (T)a.ev_values[vo + i];
+                pl[(size_t)(nd.pl_off + i) * TB] = val;
+                pl[(size_t)(nd.pl_off + r + i) * TB] = val;
+            }
+        } else {
+            const int st = a.ev_state[e];
+            if (st < 0 || st >= r) { *a.error_flag = 3; continue; }
+            for (int i = 0; i < r; ++i) {
+                const T val = (i == st) ? T(1) : T(0);
+                pl[(size_t)(nd.pl_off + i) * TB] = val;
+                pl[(size_t)(nd.pl_off + r + i) * TB] = val;
+            }
+        }
+        evb[(size_t)(node >> 5) * TB] |= 1u << (node & 31);
+    }
+}
+
+// After the last sweep: cases still active get their sweep count and converged flag.
+template <typename T>
+__global__ void finalize_kernel(uint8_t* status, int32_t* sweeps, const T* delta_last, int last_tested,
+                                T eps, int32_t total_sweeps, int64_t n)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    if (status[c] == 0) {
+        sweeps[c] = total_sweeps;
+        if (last_tested && delta_last[c] < eps) status[c] = 1;
+    }
+}
+
+// K4: belief = normalize(pi .* lambda) (:151-158), written case-major [case][sum r].
+template <typename T, typename OUT>
+__global__ void __launch_bounds__(128)
+belief_kernel(const NodeMeta* nodes, int n_nodes, const T* pl_all, int PL, int TBi, int V,
+              int64_t n_valid, OUT* out, const uint8_t* status, const int32_t* sweeps,
+              int32_t* out_sweeps, uint8_t* out_conv)
+{
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const size_t TB = (size_t)TBi;
+    const int64_t c = (int64_t)tile * TBi + lane;
+    if (c >= n_valid) return;
+    const T* pl = pl_all + ((size_t)tile * PL) * TB + lane;
+    OUT* o = out + (size_t)c * V;
+    for (int X = 0; X < n_nodes; ++X) {
+        const NodeMeta nd = nodes[X];
+        const int r = nd.card;
+        T s = T(0);
+        for (int x = 0; x < r; ++x)
+            s += pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB];
+        for (int x = 0; x < r; ++x)
+            o[nd.bel_off + x] = (OUT)((pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB]) / s);
+    }
+    if (out_sweeps) out_sweeps[c] = sweeps[c];
+    if (out_conv) out_conv[c] = status[c];
+}
+
+} // namespace bnbp

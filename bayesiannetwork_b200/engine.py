@@ -1,0 +1,113 @@
+"""Host-side mirror of ``bn::inference::belief_propagation`` (belief_propagation.hpp:12-34) for
+batches of evidence cases.  Construction flattens nothing itself -- it takes a ``FlatNetwork`` --
+and uploads the device arena through ``bnbp_create``; calls go through ``bnbp_run_batch`` (host
+buffers) or ``bnbp_run_batch_device`` (torch CUDA tensors: device memory and streams are the only
+things torch is used for)."""
+from __future__ import annotations
+
+import ctypes as C
+from dataclasses import dataclass
+from typing import Optional
+
+import numpy as np
+
+from . import _capi
+from ._capi import BnbpError  # noqa: F401
+from .flat import EvidenceBatch, FlatNetwork
+
+FP64, FP32 = 0, 1
+
+
+@dataclass
+class BPResult:
+    marginals: np.ndarray      # [n_cases, sum r_X] (float64 on the host path)
+    sweeps: np.ndarray         # [n_cases] int32
+    converged: np.ndarray      # [n_cases] uint8
+
+    def node(self, net: FlatNetwork, x: int) -> np.ndarray:
+        off = net.belief_off
+        return self.marginals[:, off[x]:off[x + 1]]
+
+
+def _vp(a) -> Optional[int]:
+    return None if a is None else a.ctypes.data
+
+
+class BeliefPropagation:
+    """``bp = BeliefPropagation(net); bp(evidence, epsilon)`` -- the reference call shape
+    (belief_propagation.hpp:24,31) with a batch in place of one evidence map."""
+
+    def __init__(self, net: FlatNetwork, precision: str = "fp64", device: int = -1,
+                 max_resident_cases: int = 0):
+        self.net = net
+        self.precision = {"fp64": FP64, "fp32": FP32, "f64": FP64, "f32": FP32}[precision]
+        lib = _capi.load()
+        self._lib = lib
+        self._h = C.c_void_p()
+        fn = _capi.FlatNetworkC(net.n_nodes, _vp(net.card), _vp(net.parent_off), _vp(net.parents),
+                                _vp(net.cpt_off), _vp(net.cpt))
+        opt = _capi.OptionsC(self.precision, device, max_resident_cases)
+        _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
+
+    def close(self):
+        if getattr(self, "_h", None) is not None and self._h:
+            self._lib.bnbp_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # ---- host buffers ---------------------------------------------------------------------------
+    def __call__(self, evidence: Optional[EvidenceBatch] = None, epsilon: float = 0.001, *,
+                 max_sweeps: int = 0, damping: float = 0.0, check_interval: int = 1,
+                 out: Optional[np.ndarray] = None) -> BPResult:
+        if evidence is None:
+            evidence = EvidenceBatch.empty(1)   # operator()(epsilon) by-pass (:24-28)
+        ev = evidence
+        n, V = ev.n_cases, self.net.belief_values
+        if out is None:
+            out = np.empty((n, V), dtype=np.float64)
+        assert out.dtype == np.float64 and out.size == n * V and out.flags.c_contiguous
+        sweeps = np.empty(n, dtype=np.int32)
+        conv = np.empty(n, dtype=np.uint8)
+        evc = _capi.EvidenceC(n, _vp(ev.ev_off), _vp(ev.ev_node),
+                              None if ev.is_soft else _vp(ev.ev_state),
+                              _vp(ev.ev_val_off) if ev.is_soft else None,
+                              _vp(ev.ev_values) if ev.is_soft else None)
+        prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval))
+        _capi.check(self._lib.bnbp_run_batch(self._h, C.byref(evc), C.byref(prm), _vp(out), _vp(sweeps), _vp(conv)))
+        return BPResult(out.reshape(n, V), sweeps, conv)
+
+    # ---- device-resident buffers (torch tensors on the handle's device) --------------------------
+    def run_device(self, n_cases: int, ev_off, ev_node, ev_state, out, *, ev_val_off=None, ev_values=None,
+                   epsilon: float = 0.0, max_sweeps: int = 20, damping: float = 0.0, check_interval: int = 1,
+                   out_sweeps=None, out_converged=None, stream: int = 0) -> None:
+        """All tensor arguments are CUDA tensors (int64 / int32 / float64 offsets and values as in
+        ``bnbp_evidence``); ``out`` has the handle's precision, shape [n_cases, sum r_X].
+        Work is enqueued on ``stream`` (a raw cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
+        def dp(t):
+            return None if t is None else int(t.data_ptr())
+        evc = _capi.EvidenceC(int(n_cases), dp(ev_off), dp(ev_node), dp(ev_state), dp(ev_val_off), dp(ev_values))
+        prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval))
+        _capi.check(self._lib.bnbp_run_batch_device(self._h, C.byref(evc), C.byref(prm), dp(out), dp(out_sweeps),
+                                                    dp(out_converged), C.c_void_p(stream) if stream else None))
+
+    def stats(self) -> dict:
+        st = _capi.StatsC()
+        _capi.check(self._lib.bnbp_get_stats(self._h, C.byref(st)))
+        return {k: getattr(st, k) for k, _ in st._fields_ if k != "reserved"}
+
+    def refresh_cpt(self, cpt: np.ndarray) -> None:
+        cpt = np.ascontiguousarray(cpt, dtype=np.float64)
+        _capi.check(self._lib.bnbp_refresh_cpt(self._h, _vp(cpt), cpt.size))
+
+
+# the name the north star uses (the reference class is belief_propagation)
+loopy_belief_propagation = BeliefPropagation
+
+
+def device_count() -> int:
+    return int(_capi.load().bnbp_device_count())
