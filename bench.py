@@ -1,0 +1,361 @@
+#!/usr/bin/env python
+"""bench.py -- evidence-case BP sweeps/sec of the batched loopy-BP path (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload alarm37] [--precision fp64]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+    python bench.py --impl reference ...      # the reference's own CPU implementation, same metric
+
+One "step" = one pass of the hot path over one batch of synthetic evidence cases: init (K0),
+`sweeps` synchronous sweeps (K1), beliefs (K4) -- belief_propagation.hpp:31-159 for every case.
+`value` = case-sweeps/s with the evidence already resident in HBM (bnbp_run_batch_device);
+`e2e`   = the same metric through the host-buffer C-ABI call (bnbp_run_batch) with pinned host
+          evidence in and host marginals out, copies inside the timed region.
+Multi-GPU: one process per GPU, cases sharded by contiguous ranges (weak scaling: every rank runs
+the full per-GPU batch), no data-path collective; NCCL only all-reduces the sweep / convergence
+summary each step (and all-gathers marginals with --gather).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+from bayesiannetwork_b200 import synth  # noqa: E402
+from bayesiannetwork_b200.flat import EvidenceBatch  # noqa: E402
+
+METRIC = "evidence-case BP sweeps/sec"
+UNIT = "case-sweeps/s"
+
+
+def measured_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        try:
+            return float(json.load(open(path))["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+        except Exception:
+            pass
+    return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+    NAMES = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+
+    def __init__(self, gpu_index: int):
+        self.rows, self.proc, self.thr = [], None, None
+        try:
+            self.proc = subprocess.Popen(
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                 "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thr = threading.Thread(target=self._pump, daemon=True)
+            self.thr.start()
+        except Exception:
+            self.proc = None
+
+    def _pump(self):
+        for line in self.proc.stdout:
+            self.rows.append(line.strip())
+
+    def stop(self) -> dict:
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons, power = [], [], set(), []
+        for row in self.rows:
+            f = [x.strip() for x in row.split(",")]
+            if len(f) < 7:
+                continue
+            try:
+                sm.append(float(f[0])); mx.append(float(f[1])); power.append(float(f[2]))
+            except ValueError:
+                continue
+            for name, val in zip(self.NAMES, f[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["no samples"]}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons),
+                "samples": len(sm), "power_w_max": max(power)}
+
+
+def build_workload(name: str, n_cases: int | None, rank: int):
+    factory, default_cases, evkw, sweeps = synth.WORKLOADS[name]
+    net = factory()
+    n = n_cases or default_cases
+    ev = synth.make_evidence(net, n, case_offset=rank * n, **evkw)
+    return net, ev, sweeps
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU legs (the only places that touch oracle/): cpu_baseline of the main line, and --impl reference.
+def _ref_worker(args):
+    net, ev, sweeps = args
+    from oracle import oracle
+    t0 = time.perf_counter()
+    oracle.run_reference(net, ev, eps=0.0, max_sweeps=sweeps)
+    return time.perf_counter() - t0
+
+
+def cpu_cores() -> int:
+    try:
+        return len(os.sched_getaffinity(0))
+    except Exception:
+        return os.cpu_count() or 1
+
+
+def time_port(net, ev_sample, sweeps, threads):
+    from oracle import oracle
+    if not oracle.have_port():
+        oracle.build()
+    t0 = time.perf_counter()
+    oracle.run_port(net, ev_sample, eps=0.0, max_sweeps=sweeps, threads=threads)
+    dt = time.perf_counter() - t0
+    return ev_sample.n_cases * sweeps / dt, dt
+
+
+def run_reference_arm(args, rank: int, world: int):
+    """The reference's own CPU implementation of the path (oracle/_ref = its unmodified headers
+    compiled in place), one PROCESS per host core (its shared_ptr graph is not thread-friendly),
+    each step a bounded sample of the same workload."""
+    if rank != 0:
+        return
+    import multiprocessing as mp
+    from oracle import oracle
+    net, _, sweeps = build_workload(args.workload, 8, 0)
+    sweeps = args.sweeps or sweeps
+    cores = cpu_cores()
+    use_ref = oracle.have_reference()
+    # size the per-step sample for ~1 s: probe one core
+    probe = synth.make_evidence(net, 2, case_offset=0, **synth.WORKLOADS[args.workload][2])
+    if use_ref:
+        t = _ref_worker((net, probe, sweeps)) / 2
+    else:
+        t = time_port(net, probe, sweeps, 1)[1] / 2
+    per_core = max(1, min(4096, int(1.0 / max(t, 1e-6))))
+    evkw = synth.WORKLOADS[args.workload][2]
+    shards = [synth.make_evidence(net, per_core, case_offset=i * per_core, **evkw) for i in range(cores)]
+    total_cases = per_core * cores
+
+    def one_step():
+        if use_ref:
+            with mp.get_context("fork").Pool(cores) as pool:
+                t0 = time.perf_counter()
+                pool.map(_ref_worker, [(net, s, sweeps) for s in shards])
+                return time.perf_counter() - t0
+        big = synth.make_evidence(net, total_cases, **evkw)
+        return time_port(net, big, sweeps, cores)[1]
+
+    for _ in range(args.warmup):
+        one_step()
+    times = [one_step() for _ in range(args.steps)]
+    dt = sum(times)
+    value = total_cases * sweeps * args.steps / dt
+    kind = "reference" if use_ref else "port"
+    sample = (f"{total_cases} cases x {sweeps} sweeps per step ({per_core} per core), "
+              f"{'oracle/_ref: unmodified reference headers' if use_ref else 'oracle C port (reference not compiled here)'}")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": args.workload, "nodes": net.n_nodes, "edges": net.n_edges, "sweeps": sweeps,
+                   "cases_per_step": total_cases},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="bnbp", choices=["bnbp", "reference"])
+    ap.add_argument("--workload", default="alarm37", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--cases", type=int, default=0, help="cases per GPU (default: the workload's)")
+    ap.add_argument("--sweeps", type=int, default=0, help="fixed sweeps per step (default: the workload's)")
+    ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "bnbp" else args.warmup
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    if args.impl == "reference":
+        run_reference_arm(args, rank, world)
+        return
+
+    import torch
+    import torch.distributed as dist
+    from bayesiannetwork_b200.engine import BeliefPropagation
+    from bayesiannetwork_b200 import dist as bdist
+
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device -- the bnbp path has no CPU fallback")
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
+        dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+
+    net, ev, sweeps = build_workload(args.workload, args.cases or None, rank)
+    sweeps = args.sweeps or sweeps
+    n, V = ev.n_cases, net.belief_values
+    tdtype = torch.float64 if args.precision == "fp64" else torch.float32
+    tsize = 8 if args.precision == "fp64" else 4
+    bp = BeliefPropagation(net, args.precision, device=local_rank)
+
+    # ---- device-resident inputs --------------------------------------------------------------------
+    d_off = torch.from_numpy(ev.ev_off).to(dev)
+    d_node = torch.from_numpy(ev.ev_node).to(dev)
+    d_state = torch.from_numpy(ev.ev_state).to(dev)
+    d_out = torch.empty((n, V), dtype=tdtype, device=dev)
+    d_sw = torch.empty(n, dtype=torch.int32, device=dev)
+    d_cv = torch.empty(n, dtype=torch.uint8, device=dev)
+    summary = torch.zeros(2, dtype=torch.int64, device=dev)
+    gathered = torch.empty((world * n, V), dtype=tdtype, device=dev) if (args.gather and world > 1) else None
+    # a dedicated (non-default) stream: the library enqueues on it and the CUDA events below see it
+    tstream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(tstream)
+    stream = tstream.cuda_stream
+
+    def step():
+        bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=0.0, max_sweeps=sweeps,
+                      out_sweeps=d_sw, out_converged=d_cv, stream=stream)
+        if world > 1:
+            # the only collectives of the path: global sweep count + all-converged flag (and,
+            # on request, the marginals)
+            bdist.reduce_summary(d_sw, d_cv, summary)
+            if gathered is not None:
+                dist.all_gather_into_tensor(gathered, d_out)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(args.steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st = bp.stats()
+    launches_per_step = int(st["last_kernel_launches"])
+    sweep_ms_per_launch = st["last_sweep_ms"] / max(1, st["last_sweep_launches"])
+    if world > 1:
+        t = torch.tensor([ms, sweep_ms_per_launch], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, sweep_ms_per_launch = float(t[0]), float(t[1])
+    clocks = sampler.stop() if sampler else None
+    value = world * n * sweeps * args.steps / (ms * 1e-3)
+
+    # ---- roofline of the dominant kernel (sweep_kernel) ----------------------------------------------
+    S = net.state_values
+    peak, peak_src = measured_peaks()
+    bytes_per_launch = 2.0 * S * tsize * n           # every state value read once and written once
+    achieved = bytes_per_launch / (sweep_ms_per_launch * 1e-3) / 1e9
+    traffic = None
+    tpath = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(tpath):
+        try:
+            tj = json.load(open(tpath))
+            key = f"{args.workload}:{args.precision}:{n}"
+            traffic = tj.get(key)
+        except Exception:
+            traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                "traffic": traffic, "kernel": "sweep_kernel", "peak_source": peak_src,
+                "algorithmic_bytes_per_case_sweep": 2 * S * tsize, "ms_per_launch": sweep_ms_per_launch}
+
+    # ---- end to end through the host-buffer C ABI (pinned host memory both ways) ----------------------
+    e2e = None
+    if not args.no_e2e:
+        def pin(a):
+            t = torch.empty(a.shape, dtype=torch.from_numpy(a[:0]).dtype, pin_memory=True)
+            t.numpy()[...] = a
+            return t
+        p_off, p_node, p_state = pin(ev.ev_off), pin(ev.ev_node), pin(ev.ev_state)
+        p_out = torch.empty((n, V), dtype=torch.float64, pin_memory=True)
+        ev_pinned = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
+        out_np = p_out.numpy()
+        e2e_steps = max(1, min(args.steps, 5))
+        bp(ev_pinned, 0.0, max_sweeps=sweeps, out=out_np)      # warm-up (staging buffers)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(e2e_steps):
+            bp(ev_pinned, 0.0, max_sweeps=sweeps, out=out_np)
+        torch.cuda.synchronize()
+        dt = time.perf_counter() - t0
+        if world > 1:
+            t = torch.tensor([dt], dtype=torch.float64, device=dev)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            dt = float(t[0])
+        e2e = {"value": world * n * sweeps * e2e_steps / dt, "unit": UNIT,
+               "h2d_bytes_per_step": int(ev.nbytes()), "d2h_bytes_per_step": int(n * V * 8 + n * 5),
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
+
+    # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle port on all host cores ---------------
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu:
+        cores = cpu_cores()
+        sample_cases = 256
+        rate, dt = time_port(net, ev.slice(0, sample_cases), sweeps, cores)
+        while dt < 5.0 and sample_cases < n and sample_cases < (1 << 18):
+            sample_cases = min(n, sample_cases * max(2, int(10.0 / max(dt, 1e-3))))
+            rate, dt = time_port(net, ev.slice(0, sample_cases), sweeps, cores)
+        cpu = {"value": rate, "unit": UNIT, "cores": cores, "kind": "port",
+               "sample": f"first {sample_cases} cases of the workload x {sweeps} sweeps, oracle/bp_oracle.c "
+                         f"(OpenMP, {cores} threads), {dt:.1f} s"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": ms / args.steps, "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64" if args.precision == "fp64" else "f32",
+            "data": "synthetic",
+            "config": {"workload": args.workload, "nodes": net.n_nodes, "edges": net.n_edges,
+                       "max_card": int(net.card.max()), "cases_per_gpu": n, "sweeps": sweeps,
+                       "state_values_per_case": S, "schedule": "synchronous, fixed sweeps, no damping",
+                       "sharding": f"cases x{world}", "gather": bool(gathered is not None),
+                       "l2": f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
+                             f"of per-case state per GPU vs 126 MB"},
+            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+        }
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
