@@ -15,10 +15,16 @@ LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libbnbp.so")
 HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_sweep.cuh"),
-           os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
-# (T, VEC, RMAX) instantiations -- must match the dispatch in bnbp_api.cu
-SWEEP_VARIANTS = [(t, v, r) for t in ("double", "float")
-                  for (v, r) in ((2, 2), (2, 4), (1, 2), (1, 4), (1, 8), (1, 16), (1, 32), (1, 64))]
+           os.path.join(CSRC, "bnbp_variants.h"), os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
+
+
+def sweep_variants():
+    """(T, VEC, RMAX, KNET) instantiations: the X-macro list in csrc/bnbp_variants.h, the same
+    list bnbp_api.cu dispatches over."""
+    import re
+    txt = open(os.path.join(CSRC, "bnbp_variants.h")).read()
+    trip = re.findall(r"X\(T,\s*(\d+),\s*(\d+),\s*(\d+)\)", txt)
+    return [(t, int(v), int(r), int(k)) for t in ("double", "float") for (v, r, k) in trip]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
@@ -40,10 +46,10 @@ def _env():
 
 def _units():
     units = [(os.path.join(CSRC, "bnbp_api.cu"), os.path.join(OBJDIR, "bnbp_api.o"), [])]
-    for t, v, r in SWEEP_VARIANTS:
+    for t, v, r, k in sweep_variants():
         units.append((os.path.join(CSRC, "bnbp_sweep_inst.cu"),
-                      os.path.join(OBJDIR, f"sweep_{t}_v{v}_r{r}.o"),
-                      [f"-DBNBP_T={t}", f"-DBNBP_VEC={v}", f"-DBNBP_RMAX={r}"]))
+                      os.path.join(OBJDIR, f"sweep_{t}_v{v}_r{r}_k{k}.o"),
+                      [f"-DBNBP_T={t}", f"-DBNBP_VEC={v}", f"-DBNBP_RMAX={r}", f"-DBNBP_KNET={k}"]))
     return units
 
 
@@ -73,6 +79,9 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
         with ThreadPoolExecutor(max_workers=max(1, min(len(todo), os.cpu_count() or 4))) as ex:
             list(ex.map(compile_one, todo))
     objs = [o for (_, o, _) in _units()]
+    for f in os.listdir(OBJDIR):                      # drop objects of variants that no longer exist
+        if os.path.join(OBJDIR, f) not in objs:
+            os.remove(os.path.join(OBJDIR, f))
     if todo or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
                "-o", LIB, *objs]

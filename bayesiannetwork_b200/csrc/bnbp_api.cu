@@ -4,6 +4,7 @@
 // ONCE in bnbp_create and the sweeps touch only flat device arrays.
 #include "../../include/bnbp.h"
 #include "bnbp_kernels.cuh"
+#include "bnbp_variants.h"
 
 #include <algorithm>
 #include <cmath>
@@ -34,7 +35,7 @@ int fail(int code, const std::string& msg)
         }                                                                                 \
     } while (0)
 
-constexpr int TB = 128;   // cases per tile
+constexpr int BLOCK_THREADS = 128;   // sweep-kernel block; a tile holds BLOCK_THREADS * vec cases
 
 struct DevBuf {
     void* p = nullptr;
@@ -66,7 +67,9 @@ struct bnbp_handle {
     int N = 0, E = 0;
     int PL = 0, M = 0, W = 0, V = 0;
     int rmax = 2;              // template bound actually used (2,4,8,16,32,64)
+    int knet = 2;              // in-degree bound actually used (2,4,8)
     int vec = 1;
+    int tb = 128;              // cases per tile = BLOCK_THREADS * vec
     int scratch_vals = 0;      // per-thread scratch values (x VEC)
     int64_t cpt_values = 0;
     int64_t max_resident = 0;
@@ -105,39 +108,21 @@ template <typename T>
 cudaError_t launch_sweep(const bnbp_handle* h, const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze,
                          bool check, cudaStream_t st)
 {
-    const int block = TB / h->vec;
-    if (h->vec == 2) {
-        switch (h->rmax) {
-        case 2: return launch_sweep_vr<T, 2, 2>(a, grid, block, smem, freeze, check, st);
-        case 4: return launch_sweep_vr<T, 2, 4>(a, grid, block, smem, freeze, check, st);
-        default: break;
-        }
-    }
-    switch (h->rmax) {
-    case 2: return launch_sweep_vr<T, 1, 2>(a, grid, block, smem, freeze, check, st);
-    case 4: return launch_sweep_vr<T, 1, 4>(a, grid, block, smem, freeze, check, st);
-    case 8: return launch_sweep_vr<T, 1, 8>(a, grid, block, smem, freeze, check, st);
-    case 16: return launch_sweep_vr<T, 1, 16>(a, grid, block, smem, freeze, check, st);
-    case 32: return launch_sweep_vr<T, 1, 32>(a, grid, block, smem, freeze, check, st);
-    default: return launch_sweep_vr<T, 1, 64>(a, grid, block, smem, freeze, check, st);
-    }
+#define BNBP_X(TT, V, R, K) \
+    if (h->vec == V && h->rmax == R && h->knet == K) return launch_sweep_vr<TT, V, R, K>(a, grid, smem, freeze, check, st);
+    BNBP_SWEEP_VARIANTS(BNBP_X, T)
+#undef BNBP_X
+    return cudaErrorInvalidConfiguration;
 }
 
 template <typename T>
 cudaError_t set_smem(const bnbp_handle* h, int bytes)
 {
-    if (h->vec == 2) {
-        if (h->rmax == 2) return set_sweep_smem<T, 2, 2>(bytes);
-        if (h->rmax == 4) return set_sweep_smem<T, 2, 4>(bytes);
-    }
-    switch (h->rmax) {
-    case 2: return set_sweep_smem<T, 1, 2>(bytes);
-    case 4: return set_sweep_smem<T, 1, 4>(bytes);
-    case 8: return set_sweep_smem<T, 1, 8>(bytes);
-    case 16: return set_sweep_smem<T, 1, 16>(bytes);
-    case 32: return set_sweep_smem<T, 1, 32>(bytes);
-    default: return set_sweep_smem<T, 1, 64>(bytes);
-    }
+#define BNBP_X(TT, V, R, K) \
+    if (h->vec == V && h->rmax == R && h->knet == K) return set_sweep_smem<TT, V, R, K>(bytes);
+    BNBP_SWEEP_VARIANTS(BNBP_X, T)
+#undef BNBP_X
+    return cudaErrorInvalidConfiguration;
 }
 
 // node ranges of roughly equal cost for grid.y
@@ -156,7 +141,7 @@ void make_chunks(const bnbp_handle* h, int n_chunks, int32_t* off)
 
 int ensure_state(bnbp_handle* h, int64_t n_cases)
 {
-    int64_t want = (n_cases + TB - 1) / TB * TB;
+    int64_t want = (n_cases + h->tb - 1) / h->tb * h->tb;
     const size_t per_case = (size_t)(h->PL + 2 * (size_t)h->M) * h->tsize + (size_t)h->W * 4 + 3 * h->tsize + 8;
     int64_t limit = h->max_resident;
     if (limit <= 0) {
@@ -167,7 +152,7 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
         double usable = 0.80 * (double)(free_b + held);
         limit = (int64_t)(usable / (double)(per_case + (size_t)h->V * 8));
     }
-    limit = std::max<int64_t>(TB, limit / TB * TB);
+    limit = std::max<int64_t>(h->tb, limit / h->tb * h->tb);
     want = std::min(want, limit);
     if (want <= h->cap) return BNBP_OK;
     // grow: release first so the new allocation can reuse the space
@@ -197,7 +182,7 @@ template <typename T, typename OUT>
 int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_params& prm, OUT* d_out,
               int32_t* d_out_sweeps, uint8_t* d_out_conv, cudaStream_t st, int64_t* planned_sweeps)
 {
-    const int tiles = (int)((n + TB - 1) / TB);
+    const int tiles = (int)((n + h->tb - 1) / h->tb);
     int32_t* d_last_active = reinterpret_cast<int32_t*>(h->d_misc.p);
     int32_t* d_error = d_last_active + 1;
     const bool eps_mode = prm.epsilon > 0.0;
@@ -212,14 +197,14 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         ia.nodes = (const NodeMeta*)h->d_nodes.p;
         ia.pl_init = (const T*)h->d_pl_init.p;
         ia.pl = (T*)h->d_pl.p; ia.msg0 = (T*)h->d_msg[0].p; ia.evbits = (uint32_t*)h->d_evbits.p;
-        ia.PL = h->PL; ia.M = h->M; ia.W = h->W; ia.TB = TB; ia.n_nodes = h->N;
+        ia.PL = h->PL; ia.M = h->M; ia.W = h->W; ia.TB = h->tb; ia.n_nodes = h->N;
         ia.n_valid = n;
         ia.ev_off = de.ev_off; ia.ev_base = de.ev_base; ia.ev_node = de.ev_node; ia.ev_state = de.ev_state;
         ia.ev_val_off = de.ev_val_off; ia.ev_values = de.ev_values; ia.ev_val_base = de.ev_val_base;
         ia.delta = (T*)h->d_delta.p; ia.cap = h->cap;
         ia.status = (uint8_t*)h->d_status.p; ia.sweeps = (int32_t*)h->d_sweeps.p;
         ia.error_flag = d_error;
-        init_kernel<T><<<tiles, TB, 0, st>>>(ia);
+        init_kernel<T><<<tiles, h->tb, 0, st>>>(ia);
         CU_TRY(cudaGetLastError());
         h->last_kernel_launches++;
     }
@@ -233,9 +218,9 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.cpt = (const T*)h->d_cpt.p;
     sa.pl = (T*)h->d_pl.p;
     sa.evbits = (const uint32_t*)h->d_evbits.p;
-    sa.PL = h->PL; sa.M = h->M; sa.W = h->W; sa.TB = TB;
+    sa.PL = h->PL; sa.M = h->M; sa.W = h->W;
     // enough threads to fill 148 SMs a few times over: split the node walk when the batch is small
-    const int64_t threads_per_row = (int64_t)tiles * (TB / h->vec);
+    const int64_t threads_per_row = (int64_t)tiles * BLOCK_THREADS;
     int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, h->N / 8)),
                                           std::max<int64_t>(1, (148 * 2048 * 2 + threads_per_row - 1) / threads_per_row));
     sa.n_chunks = n_chunks;
@@ -246,7 +231,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.eps = (T)prm.epsilon;
     sa.damping = (T)prm.damping;
     T* delta = (T*)h->d_delta.p;
-    const size_t smem = (size_t)(TB / h->vec) * (size_t)h->scratch_vals * h->vec * sizeof(T);
+    const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * sizeof(T);
     dim3 grid(tiles, n_chunks);
 
     // event pair around the sweeps of this chunk
@@ -306,19 +291,19 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         const int last = total_sweeps - 1;
         finalize_kernel<T><<<(unsigned)((h->cap + 255) / 256), 256, 0, st>>>(
             (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta + (size_t)(last % 3) * h->cap,
-            prev_tested ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles * TB);
+            prev_tested ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles * h->tb);
         CU_TRY(cudaGetLastError());
         h->last_kernel_launches++;
     } else {
-        CU_TRY(cudaMemsetAsync(h->d_status.p, 0, (size_t)tiles * TB, st));
+        CU_TRY(cudaMemsetAsync(h->d_status.p, 0, (size_t)tiles * h->tb, st));
         // sweeps[] = total for every case
         finalize_kernel<T><<<(unsigned)((h->cap + 255) / 256), 256, 0, st>>>(
-            (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta, 0, (T)0, total_sweeps, (int64_t)tiles * TB);
+            (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta, 0, (T)0, total_sweeps, (int64_t)tiles * h->tb);
         CU_TRY(cudaGetLastError());
         h->last_kernel_launches++;
     }
 
-    belief_kernel<T, OUT><<<tiles, TB, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, TB,
+    belief_kernel<T, OUT><<<tiles, h->tb, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, h->tb,
                                                 h->V, n, d_out, (const uint8_t*)h->d_status.p,
                                                 (const int32_t*)h->d_sweeps.p, d_out_sweeps, d_out_conv);
     CU_TRY(cudaGetLastError());
@@ -478,7 +463,7 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
         nd.e0 = net->parent_off[x];
         nd.cpt_off = net->cpt_off[x];
         nd.pin_off = pin;
-        nd.pad = 0;
+        nd.scr_half = 0;
         for (int e = nd.e0; e < nd.e0 + nd.k; ++e) {
             e_card[e] = net->card[net->parents[e]];
             e_pin[e] = pin;
@@ -517,9 +502,20 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
                                 (double)nd.m * nd.m * nd.card;
     }
     h->scratch_vals = 2 * so_max;
+    for (int x = 0; x < N; ++x) h->nodes[x].scr_half = so_max;
+    int kmax = 0;
+    for (int x = 0; x < N; ++x) kmax = std::max(kmax, (int)h->nodes[x].k);
+    h->knet = kmax <= 2 ? 2 : (kmax <= 4 ? 4 : 8);
+    if (h->rmax == 8 && h->knet < 4) h->knet = 4;
+    if (h->rmax > 8) h->knet = 8;
     h->vec = (h->rmax <= 4) ? 2 : 1;
+    if (const char* ev = getenv("BNBP_VEC")) {           // tuning knob: cases per thread
+        const int v = atoi(ev);
+        if ((v == 1 || v == 2) && h->rmax <= 4) h->vec = v;
+    }
+    h->tb = BLOCK_THREADS * h->vec;
     h->cpt_values = net->cpt_off[N];
-    const size_t smem = (size_t)(TB / h->vec) * (size_t)h->scratch_vals * h->vec * h->tsize;
+    const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * h->tsize;
     if (smem > 200 * 1024) return fail(BNBP_ERR_INVALID, "parent sets too wide for the shared-memory scratch");
 
     // ---- upload -------------------------------------------------------------------------------------

@@ -36,7 +36,7 @@ struct NodeMeta {              // 48 bytes, warp-uniform
     int32_t c0;                // first out-edge index
     int64_t cpt_off;           // offset into the device CPT arena
     int32_t bel_off;           // offset of X in a row of marginals
-    int32_t pad;
+    int32_t scr_half;          // scratch values reserved for the outer parents' messages (accumulators follow)
 };
 
 template <typename T> struct SweepArgs {
@@ -49,7 +49,7 @@ template <typename T> struct SweepArgs {
     const T*        msg_cur;    // [tiles][M][TB]
     T*              msg_nxt;
     const uint32_t* evbits;     // [tiles][W][TB]
-    int32_t PL, M, W, TB;
+    int32_t PL, M, W;
     int32_t n_chunks;
     int32_t chunk_off[MAX_CHUNKS + 1];
     // convergence bookkeeping (only touched when FREEZE / CHECK)
@@ -96,10 +96,9 @@ __device__ __forceinline__ void atomic_max_nonneg(float* p, float v)
 
 // Sweep launchers: defined in bnbp_sweep.cuh, explicitly instantiated one (T, VEC, RMAX) per
 // translation unit (bnbp_sweep_inst.cu) so the build parallelises.
-template <typename T, int VEC, int RMAX>
-cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, int block, size_t smem, bool freeze, bool check,
-                            cudaStream_t st);
-template <typename T, int VEC, int RMAX> cudaError_t set_sweep_smem(int bytes);
+template <typename T, int VEC, int RMAX, int KNET>
+cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze, bool check, cudaStream_t st);
+template <typename T, int VEC, int RMAX, int KNET> cudaError_t set_sweep_smem(int bytes);
 
 // ------------------------------------------------------------------------------------------------
 // K0: initial state of one tile (belief_propagation.hpp:33-73).  One thread per case.
@@ -119,7 +118,7 @@ template <typename T> struct InitArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(128) init_kernel(const InitArgs<T> a)
+__global__ void __launch_bounds__(256) init_kernel(const InitArgs<T> a)
 {
     const int tile = blockIdx.x, lane = threadIdx.x;
     const size_t TB = (size_t)a.TB;
@@ -177,7 +176,7 @@ __global__ void finalize_kernel(uint8_t* status, int32_t* sweeps, const T* delta
 
 // K4: belief = normalize(pi .* lambda) (:151-158), written case-major [case][sum r].
 template <typename T, typename OUT>
-__global__ void __launch_bounds__(128)
+__global__ void __launch_bounds__(256)
 belief_kernel(const NodeMeta* nodes, int n_nodes, const T* pl_all, int PL, int TBi, int V,
               int64_t n_valid, OUT* out, const uint8_t* status, const int32_t* sweeps,
               int32_t* out_sweeps, uint8_t* out_conv)

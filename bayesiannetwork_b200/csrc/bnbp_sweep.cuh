@@ -1,9 +1,20 @@
 // bnbp_sweep.cuh — the sweep kernel (one launch = one iteration of the reference's while(true),
 // belief_propagation.hpp:75-148, for every resident case) and its launchers.
+//
+// Thread = VEC cases, block = 128 threads = one tile of TBC = 128*VEC cases, grid.y = node chunks.
+// Per node X the thread gathers everything X reads (pi_X, lambda_X, pi-messages from the parents,
+// lambda-messages from the children -- all time t), and produces everything X owns at time t+1:
+//   lambda_X (:220-238), pi-messages to the children (:202-218)            "child side"
+//   pi_X (:174-200), lambda-messages to the parents (:240-266)             "parent side"
+// Normalisation (:298-311) multiplies by one reciprocal of the plain sum per vector (the reference
+// divides entry by entry; the difference is <= 1 ulp, far inside the 1e-9 parity bound, and fp64
+// division was 30 % of the instruction stream in profiles/r01a).
 #pragma once
 #include "bnbp_kernels.cuh"
 
 namespace bnbp {
+
+constexpr int BLOCK = 128;
 
 // ------------------------------------------------------------------------------------------------
 // Parent side of one node: pi_X and all lambda-messages X->U_j from ONE pass over the CPT.
@@ -11,18 +22,17 @@ namespace bnbp {
 //   pi_X(x)   = sum_u P(x|u) prod_j m_j(u_j)
 //   lmsg_j(a) = sum_{u:u_j=a} w(u) prod_{i!=j} m_i(u_i)
 // evaluated by a depth-K recursion over the parents (compile-time depth, runtime cardinalities):
-// each level passes down the prefix product P and returns the message-weighted sum of its
-// subtree R, so the leave-one-out product for level j is simply P*R -- (2k+2)|CPT| flops instead
+// each level passes down the prefix product P and returns the message-weighted sum R of its
+// subtree, so the leave-one-out product for level j is simply P*R -- (2k+2)|CPT| flops instead
 // of the reference's (k^2+k+1)|CPT|.  The last parent and the states of X are unrolled to RMAX
-// and live in registers; the outer parents' messages / accumulators sit in a per-thread shared
-// memory scratch (dynamic index, conflict-free [value][thread] layout).
+// and live in registers; parents further out keep their messages / accumulators in a per-thread
+// shared-memory scratch column (dynamic index, conflict-free [value][thread] layout).
 template <typename T, int VEC, int RMAX> struct ParentCtx {
     const T* cpt;
     int r, rk;
     int rj[KMAX];
     int soff[KMAX];
-    T* scr;            // this thread's scratch column: scr[(i*VEC+v)*BD]
-    int BD;
+    T* scr;            // this thread's scratch column: scr[(i*VEC+v)*BLOCK]
     int sacc_base;     // value index where the outer accumulators start
     T lam[RMAX][VEC], pacc[RMAX][VEC], mk[RMAX][VEC], lacck[RMAX][VEC];
 };
@@ -34,11 +44,12 @@ __device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T 
 #pragma unroll
     for (int v = 0; v < VEC; ++v) ret[v] = T(0);
     auto body = [&](int b) {
+        const T* row = blk + b * c.r;
         T w[VEC], pm[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { w[v] = T(0); pm[v] = P[v] * c.mk[b][v]; }
         auto inner = [&](int x) {
-            const T p = __ldg(blk + b * c.r + x);
+            const T p = __ldg(row + x);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 w[v] = fma(c.lam[x][v], p, w[v]);
@@ -80,13 +91,13 @@ __device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX>& c, const T (
             T mv[VEC], P2[VEC], R[VEC];
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                mv[v] = c.scr[((c.soff[LEVEL] + a) * VEC + v) * c.BD];
+                mv[v] = c.scr[((c.soff[LEVEL] + a) * VEC + v) * BLOCK];
                 P2[v] = P[v] * mv[v];
             }
             parent_rec<LEVEL + 1, K, T, VEC, RMAX>(c, P2, q * rl + a, R);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                T* acc = &c.scr[((c.sacc_base + c.soff[LEVEL] + a) * VEC + v) * c.BD];
+                T* acc = &c.scr[((c.sacc_base + c.soff[LEVEL] + a) * VEC + v) * BLOCK];
                 *acc = fma(P[v], R[v], *acc);
                 ret[v] = fma(mv[v], R[v], ret[v]);
             }
@@ -103,19 +114,20 @@ __device__ __forceinline__ void parent_run(ParentCtx<T, VEC, RMAX>& c)
     parent_rec<0, K, T, VEC, RMAX>(c, one, 0, ret);
 }
 
+template <typename T> __device__ __forceinline__ T recip(T s) { return T(1) / s; }
+
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int RMAX, bool FREEZE, bool CHECK>
-__global__ void __launch_bounds__(128)
+template <typename T, int VEC, int RMAX, int KNET, bool FREEZE, bool CHECK>
+__global__ void __launch_bounds__(BLOCK)
 sweep_kernel(const SweepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];
-    T* smem = reinterpret_cast<T*>(smem_raw);
-    const int BD = blockDim.x;
+    constexpr size_t TBC = (size_t)BLOCK * VEC;        // cases per tile = slot stride
     const int tid = threadIdx.x;
     const int tile = blockIdx.x;
     const int chunk = blockIdx.y;
     const int lane0 = tid * VEC;                       // first case (within the tile) of this thread
-    const size_t case0 = (size_t)tile * a.TB + lane0;  // index into per-case arrays
+    const size_t case0 = (size_t)tile * TBC + lane0;   // index into per-case arrays
 
     bool act[VEC];
 #pragma unroll
@@ -149,16 +161,71 @@ sweep_kernel(const SweepArgs<T> a)
         }
     }
 
-    T* pl = a.pl + ((size_t)tile * a.PL) * a.TB + lane0;
-    const T* cur = a.msg_cur + ((size_t)tile * a.M) * a.TB + lane0;
-    T* nxt = a.msg_nxt + ((size_t)tile * a.M) * a.TB + lane0;
-    const uint32_t* evb = a.evbits + ((size_t)tile * a.W) * a.TB + lane0;
-    const size_t TB = (size_t)a.TB;
-    T* scr = smem + tid;
+    T* const pl = a.pl + ((size_t)tile * a.PL) * TBC + lane0;
+    const T* const cur = a.msg_cur + ((size_t)tile * a.M) * TBC + lane0;
+    T* const nxt = a.msg_nxt + ((size_t)tile * a.M) * TBC + lane0;
+    const uint32_t* const evb = a.evbits + ((size_t)tile * a.W) * TBC + lane0;
+    T* const scr = reinterpret_cast<T*>(smem_raw) + tid;
 
     T dmax[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) dmax[v] = Lim<T>::floor_();
+
+    // normalise a message (RMAX-padded register vector), damp / delta it against the time-t value
+    // when CHECK, store it to the time-(t+1) buffer
+    auto emit_msg = [&](int out, const T (&val)[RMAX][VEC], int rr) {
+        T s[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = T(0);
+#pragma unroll
+        for (int x = 0; x < RMAX; ++x)
+            if (x < rr) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) s[v] += val[x][v];
+            }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = recip(s[v]);
+        T* dst = nxt + (size_t)out * TBC;
+        const T* oldp = cur + (size_t)out * TBC;
+#pragma unroll
+        for (int x = 0; x < RMAX; ++x)
+            if (x < rr) {
+                Pk<T, VEC> o;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) o.v[v] = val[x][v] * s[v];
+                if constexpr (CHECK) {
+                    const Pk<T, VEC> old = ldp<T, VEC>(oldp + x * TBC);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        if (a.damping != T(0)) o.v[v] = (T(1) - a.damping) * o.v[v] + a.damping * old.v[v];
+                        dmax[v] = absdiff_max(dmax[v], o.v[v], old.v[v]);
+                    }
+                }
+                stp<T, VEC>(dst + x * TBC, o);
+            }
+    };
+    // normalise pi_X / lambda_X and store in place; evidence nodes and frozen cases keep the old row
+    auto emit_node = [&](T* dst, const T (&val)[RMAX][VEC], const T (&oldv)[RMAX][VEC], const bool (&upd)[VEC], int rr) {
+        T s[VEC];
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = T(0);
+#pragma unroll
+        for (int x = 0; x < RMAX; ++x)
+            if (x < rr) {
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) s[v] += val[x][v];
+            }
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) s[v] = recip(s[v]);
+#pragma unroll
+        for (int x = 0; x < RMAX; ++x)
+            if (x < rr) {
+                Pk<T, VEC> o;
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) o.v[v] = upd[v] ? val[x][v] * s[v] : oldv[x][v];
+                stp<T, VEC>(dst + x * TBC, o);
+            }
+    };
 
     const int n0 = a.chunk_off[chunk], n1 = a.chunk_off[chunk + 1];
     Pk<uint32_t, VEC> evw;
@@ -167,19 +234,21 @@ sweep_kernel(const SweepArgs<T> a)
     for (int X = n0; X < n1; ++X) {
         const NodeMeta nd = a.nodes[X];
         const int r = nd.card, k = nd.k, m = nd.m;
-        if ((X >> 5) != evw_idx) { evw_idx = X >> 5; evw = ldp<uint32_t, VEC>(evb + (size_t)evw_idx * TB); }
+        if ((X >> 5) != evw_idx) { evw_idx = X >> 5; evw = ldp<uint32_t, VEC>(evb + (size_t)evw_idx * TBC); }
         bool upd[VEC];                                  // may pi_X / lambda_X be rewritten?
 #pragma unroll
         for (int v = 0; v < VEC; ++v) upd[v] = act[v] && !((evw.v[v] >> (X & 31)) & 1u);
 
         // ---- time-t pi_X and lambda_X ------------------------------------------------------------
+        T* const pX = pl + (size_t)nd.pl_off * TBC;
+        T* const lX = pX + (size_t)r * TBC;
         T pi[RMAX][VEC];
         ParentCtx<T, VEC, RMAX> pc;
 #pragma unroll
         for (int x = 0; x < RMAX; ++x) {
             if (x < r) {
-                Pk<T, VEC> p = ldp<T, VEC>(pl + (size_t)(nd.pl_off + x) * TB);
-                Pk<T, VEC> l = ldp<T, VEC>(pl + (size_t)(nd.pl_off + r + x) * TB);
+                const Pk<T, VEC> p = ldp<T, VEC>(pX + x * TBC);
+                const Pk<T, VEC> l = ldp<T, VEC>(lX + x * TBC);
 #pragma unroll
                 for (int v = 0; v < VEC; ++v) { pi[x][v] = p.v[v]; pc.lam[x][v] = l.v[v]; }
             } else {
@@ -190,90 +259,93 @@ sweep_kernel(const SweepArgs<T> a)
 
         // ---- child side: lambda_X (:220-238) and pi-messages X->children (:202-218) -------------
         {
+            const T* const Lb = cur + (size_t)nd.lin_off * TBC;
+            const int32_t* const outs = a.c_pi_out + nd.c0;
             T ln[RMAX][VEC];
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
-            for (int c = 0; c < m; ++c) {
-#pragma unroll
-                for (int x = 0; x < RMAX; ++x) {
-                    if (x < r) {
-                        Pk<T, VEC> L = ldp<T, VEC>(cur + (size_t)(nd.lin_off + c * r + x) * TB);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) ln[x][v] *= L.v[v];
-                    }
-                }
-            }
-            T s[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) s[v] = T(0);
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-                if (x < r) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) s[v] += ln[x][v];
-                }
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x) {
-                if (x < r) {
-                    T* dst = pl + (size_t)(nd.pl_off + r + x) * TB;
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (upd[v]) dst[v] = ln[x][v] / s[v];
-                }
-            }
-            for (int c = 0; c < m; ++c) {
-                T pv[RMAX][VEC];
+            if (m == 0) {
 #pragma unroll
                 for (int x = 0; x < RMAX; ++x)
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v];
-                for (int c2 = 0; c2 < m; ++c2) {
-                    if (c2 == c) continue;
+                    for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
+            } else if (m == 1) {
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x) {
+                    if (x < r) {
+                        const Pk<T, VEC> L = ldp<T, VEC>(Lb + x * TBC);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) ln[x][v] = L.v[v];
+                    }
+                }
+                emit_msg(outs[0], pi, r);                       // no other child: N(pi_X)
+            } else if (m == 2) {
+                T L1[RMAX][VEC], pv[RMAX][VEC];
+                const T* const Lb1 = Lb + (size_t)r * TBC;
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x) {
+                    if (x < r) {
+                        const Pk<T, VEC> A = ldp<T, VEC>(Lb + x * TBC);
+                        const Pk<T, VEC> B = ldp<T, VEC>(Lb1 + x * TBC);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { ln[x][v] = A.v[v]; L1[x][v] = B.v[v]; }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { ln[x][v] = T(0); L1[x][v] = T(0); }
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v] * L1[x][v];
+                emit_msg(outs[0], pv, r);
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { pv[x][v] = pi[x][v] * ln[x][v]; ln[x][v] *= L1[x][v]; }
+                emit_msg(outs[1], pv, r);
+            } else {
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
+                for (int c = 0; c < m; ++c) {
+                    const T* const Lc = Lb + (size_t)(c * r) * TBC;
 #pragma unroll
                     for (int x = 0; x < RMAX; ++x) {
                         if (x < r) {
-                            Pk<T, VEC> L = ldp<T, VEC>(cur + (size_t)(nd.lin_off + c2 * r + x) * TB);
+                            const Pk<T, VEC> L = ldp<T, VEC>(Lc + x * TBC);
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) pv[x][v] *= L.v[v];
+                            for (int v = 0; v < VEC; ++v) ln[x][v] *= L.v[v];
                         }
                     }
                 }
+                for (int c = 0; c < m; ++c) {
+                    T pv[RMAX][VEC];
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) s[v] = T(0);
+                    for (int x = 0; x < RMAX; ++x)
 #pragma unroll
-                for (int x = 0; x < RMAX; ++x)
-                    if (x < r) {
+                        for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v];
+                    for (int c2 = 0; c2 < m; ++c2) {
+                        if (c2 == c) continue;
+                        const T* const Lc = Lb + (size_t)(c2 * r) * TBC;
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) s[v] += pv[x][v];
-                    }
-                const int out = a.c_pi_out[nd.c0 + c];
+                        for (int x = 0; x < RMAX; ++x) {
+                            if (x < r) {
+                                const Pk<T, VEC> L = ldp<T, VEC>(Lc + x * TBC);
 #pragma unroll
-                for (int x = 0; x < RMAX; ++x) {
-                    if (x < r) {
-                        Pk<T, VEC> o;
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) o.v[v] = pv[x][v] / s[v];
-                        if constexpr (CHECK) {
-                            Pk<T, VEC> old = ldp<T, VEC>(cur + (size_t)(out + x) * TB);
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                if (a.damping != T(0)) o.v[v] = (T(1) - a.damping) * o.v[v] + a.damping * old.v[v];
-                                dmax[v] = absdiff_max(dmax[v], o.v[v], old.v[v]);
+                                for (int v = 0; v < VEC; ++v) pv[x][v] *= L.v[v];
                             }
                         }
-                        stp<T, VEC>(nxt + (size_t)(out + x) * TB, o);
                     }
+                    emit_msg(outs[c], pv, r);
                 }
             }
+            emit_node(lX, ln, pc.lam, upd, r);
         }
 
         // ---- parent side: pi_X (:174-200) and lambda-messages X->parents (:240-266) ---------------
         pc.cpt = a.cpt + nd.cpt_off;
         pc.r = r;
         pc.scr = scr;
-        pc.BD = BD;
 #pragma unroll
         for (int x = 0; x < RMAX; ++x)
 #pragma unroll
@@ -288,115 +360,81 @@ sweep_kernel(const SweepArgs<T> a)
                     for (int v = 0; v < VEC; ++v) pc.pacc[x][v] = p;
                 }
         } else {
+            const int32_t* const ecard = a.e_card + nd.e0;
+            const int32_t* const louts = a.e_lam_out + nd.e0;
             // stage the outer parents' messages in scratch, the last parent's in registers
             int so = 0, slot = nd.pin_off;
+            if (k > 1) {
 #pragma unroll
-            for (int j = 0; j < KMAX; ++j) {
-                if (j < k - 1) {
-                    const int rjj = a.e_card[nd.e0 + j];
-                    pc.rj[j] = rjj;
-                    pc.soff[j] = so;
-                    for (int u = 0; u < rjj; ++u) {
-                        Pk<T, VEC> mm = ldp<T, VEC>(cur + (size_t)(slot + u) * TB);
+                for (int j = 0; j < KNET - 1; ++j) {
+                    if (j < k - 1) {
+                        const int rjj = ecard[j];
+                        pc.rj[j] = rjj;
+                        pc.soff[j] = so;
+                        const T* const mp = cur + (size_t)slot * TBC;
+                        for (int u = 0; u < rjj; ++u) {
+                            const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) scr[((so + u) * VEC + v) * BD] = mm.v[v];
+                            for (int v = 0; v < VEC; ++v) {
+                                scr[((so + u) * VEC + v) * BLOCK] = mm.v[v];
+                                scr[((nd.scr_half + so + u) * VEC + v) * BLOCK] = T(0);
+                            }
+                        }
+                        so += rjj;
+                        slot += rjj;
                     }
-                    so += rjj;
-                    slot += rjj;
                 }
             }
-            pc.sacc_base = so;
-            for (int i = 0; i < so; ++i)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) scr[((so + i) * VEC + v) * BD] = T(0);
-            const int rk = a.e_card[nd.e0 + k - 1];
+            pc.sacc_base = nd.scr_half;
+            const int rk = ecard[k - 1];
             pc.rk = rk;
+            {
+                const T* const mp = cur + (size_t)slot * TBC;
 #pragma unroll
-            for (int u = 0; u < RMAX; ++u)
-                if (u < rk) {
-                    Pk<T, VEC> mm = ldp<T, VEC>(cur + (size_t)(slot + u) * TB);
+                for (int u = 0; u < RMAX; ++u)
+                    if (u < rk) {
+                        const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
-                }
-            switch (k) {
-            case 1: parent_run<1, T, VEC, RMAX>(pc); break;
-            case 2: parent_run<2, T, VEC, RMAX>(pc); break;
-            case 3: parent_run<3, T, VEC, RMAX>(pc); break;
-            case 4: parent_run<4, T, VEC, RMAX>(pc); break;
-            case 5: parent_run<5, T, VEC, RMAX>(pc); break;
-            case 6: parent_run<6, T, VEC, RMAX>(pc); break;
-            case 7: parent_run<7, T, VEC, RMAX>(pc); break;
-            default: parent_run<8, T, VEC, RMAX>(pc); break;
+                        for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
+                    }
             }
-            // lambda-messages to the parents: normalise, (damp, delta), store
+            if (k == 1) parent_run<1, T, VEC, RMAX>(pc);
+            else if (k == 2) parent_run<2, T, VEC, RMAX>(pc);
+            else if constexpr (KNET > 2) {
+                if (k == 3) parent_run<3, T, VEC, RMAX>(pc);
+                else if (k == 4) parent_run<4, T, VEC, RMAX>(pc);
+                else if constexpr (KNET > 4) {
+                    if (k == 5) parent_run<5, T, VEC, RMAX>(pc);
+                    else if (k == 6) parent_run<6, T, VEC, RMAX>(pc);
+                    else if (k == 7) parent_run<7, T, VEC, RMAX>(pc);
+                    else parent_run<8, T, VEC, RMAX>(pc);
+                }
+            }
+            // lambda-messages to the outer parents (accumulated in scratch) ...
             int so2 = 0;
-            for (int j = 0; j < k; ++j) {
-                const int rjj = a.e_card[nd.e0 + j];
-                const int out = a.e_lam_out[nd.e0 + j];
-                T s[VEC];
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) s[v] = T(0);
-                if (j == k - 1) {
+            for (int j = 0; j < k - 1; ++j) {
+                const int rjj = ecard[j];
+                T val[RMAX][VEC];
+                if constexpr (RMAX <= 8) {
 #pragma unroll
                     for (int u = 0; u < RMAX; ++u)
-                        if (u < rk) {
+                        if (u < rjj) {
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) s[v] += pc.lacck[u][v];
+                            for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
                         }
                 } else {
                     for (int u = 0; u < rjj; ++u)
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) s[v] += scr[((pc.sacc_base + so2 + u) * VEC + v) * BD];
+                        for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
                 }
-                auto emit = [&](int u, const T (&val)[VEC]) {
-                    Pk<T, VEC> o;
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) o.v[v] = val[v] / s[v];
-                    if constexpr (CHECK) {
-                        Pk<T, VEC> old = ldp<T, VEC>(cur + (size_t)(out + u) * TB);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            if (a.damping != T(0)) o.v[v] = (T(1) - a.damping) * o.v[v] + a.damping * old.v[v];
-                            dmax[v] = absdiff_max(dmax[v], o.v[v], old.v[v]);
-                        }
-                    }
-                    stp<T, VEC>(nxt + (size_t)(out + u) * TB, o);
-                };
-                if (j == k - 1) {
-#pragma unroll
-                    for (int u = 0; u < RMAX; ++u)
-                        if (u < rk) emit(u, pc.lacck[u]);
-                } else {
-                    for (int u = 0; u < rjj; ++u) {
-                        T val[VEC];
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) val[v] = scr[((pc.sacc_base + so2 + u) * VEC + v) * BD];
-                        emit(u, val);
-                    }
-                    so2 += rjj;
-                }
+                emit_msg(louts[j], val, rjj);
+                so2 += rjj;
             }
+            // ... and to the last parent (accumulated in registers)
+            emit_msg(louts[k - 1], pc.lacck, rk);
         }
         // pi_X = normalize(acc) unless X is evidence (:177) or the case is frozen
-        {
-            T s[VEC];
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) s[v] = T(0);
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-                if (x < r) {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) s[v] += pc.pacc[x][v];
-                }
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-                if (x < r) {
-                    T* dst = pl + (size_t)(nd.pl_off + x) * TB;
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v)
-                        if (upd[v]) dst[v] = pc.pacc[x][v] / s[v];
-                }
-        }
+        emit_node(pX, pc.pacc, pi, upd, r);
     }
 
     if constexpr (CHECK) {
@@ -409,24 +447,23 @@ sweep_kernel(const SweepArgs<T> a)
     }
 }
 
-template <typename T, int VEC, int RMAX>
-cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, int block, size_t smem, bool freeze, bool check,
-                            cudaStream_t st)
+template <typename T, int VEC, int RMAX, int KNET>
+cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze, bool check, cudaStream_t st)
 {
-    if (check) sweep_kernel<T, VEC, RMAX, true, true><<<grid, block, smem, st>>>(a);
-    else if (freeze) sweep_kernel<T, VEC, RMAX, true, false><<<grid, block, smem, st>>>(a);
-    else sweep_kernel<T, VEC, RMAX, false, false><<<grid, block, smem, st>>>(a);
+    if (check) sweep_kernel<T, VEC, RMAX, KNET, true, true><<<grid, BLOCK, smem, st>>>(a);
+    else if (freeze) sweep_kernel<T, VEC, RMAX, KNET, true, false><<<grid, BLOCK, smem, st>>>(a);
+    else sweep_kernel<T, VEC, RMAX, KNET, false, false><<<grid, BLOCK, smem, st>>>(a);
     return cudaGetLastError();
 }
 
-template <typename T, int VEC, int RMAX> cudaError_t set_sweep_smem(int bytes)
+template <typename T, int VEC, int RMAX, int KNET> cudaError_t set_sweep_smem(int bytes)
 {
     cudaError_t e;
-    e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
-    return cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    return cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }
 
 } // namespace bnbp
