@@ -67,7 +67,8 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
 
     def compile_one(u):
         src, obj, defs = u
-        cmd = [nvcc, *NVCC_FLAGS, *extra, *defs, "-c", "-o", obj, src]
+        tune = [f"-DBNBP_MINB={os.environ['BNBP_MINB']}"] if os.environ.get("BNBP_MINB") else []
+        cmd = [nvcc, *NVCC_FLAGS, *extra, *defs, *tune, "-c", "-o", obj, src]
         r = subprocess.run(cmd, env=_env(), capture_output=True, text=True)
         if r.returncode != 0:
             raise RuntimeError(f"nvcc failed for {os.path.basename(obj)}:\n{r.stdout}\n{r.stderr}")

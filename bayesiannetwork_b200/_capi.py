@@ -51,7 +51,8 @@ EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy"
 
 
 def lib_path() -> str:
-    return _build.LIB
+    # BNBP_LIB: kernel-tuning knob (an alternative build of the same library), not a fallback
+    return os.environ.get("BNBP_LIB") or _build.LIB
 
 
 def load():

@@ -75,9 +75,13 @@ struct bnbp_handle {
     int64_t max_resident = 0;
     std::vector<NodeMeta> nodes;
     std::vector<double> cost_prefix;   // [N+1]
+    std::vector<StageMeta> stages;     // TMA stages (groups of consecutive nodes)
+    std::vector<double> stage_cost;    // prefix cost per stage, [n_stages+1]
+    int stage_rows = 0, n_stage_bufs = 3;
+    size_t sweep_smem = 0;
     std::vector<int32_t> card;
     // device network
-    DevBuf d_nodes, d_e_card, d_e_lam_out, d_c_pi_out, d_cpt, d_pl_init;
+    DevBuf d_stages, d_nodes, d_e_card, d_e_lam_out, d_c_pi_out, d_cpt, d_pl_init;
     // device state for the resident chunk
     int64_t cap = 0;
     DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
@@ -125,18 +129,64 @@ cudaError_t set_smem(const bnbp_handle* h, int bytes)
     return cudaErrorInvalidConfiguration;
 }
 
-// node ranges of roughly equal cost for grid.y
+// stage ranges of roughly equal cost for grid.y
 void make_chunks(const bnbp_handle* h, int n_chunks, int32_t* off)
 {
-    const double total = h->cost_prefix[h->N];
+    const int S = (int)h->stages.size();
+    const double total = h->stage_cost[S];
     off[0] = 0;
     int x = 0;
     for (int c = 1; c < n_chunks; ++c) {
         const double target = total * c / n_chunks;
-        while (x < h->N && h->cost_prefix[x + 1] <= target) ++x;
+        while (x < S && h->stage_cost[x + 1] <= target) ++x;
         off[c] = std::max(x, off[c - 1]);
     }
-    off[n_chunks] = h->N;
+    off[n_chunks] = S;
+}
+
+// Partition the nodes into TMA stages: consecutive nodes whose read set (pi/lambda rows, incoming
+// pi-message rows, incoming lambda-message rows -- each contiguous by construction of the slot
+// layout) fits one stage buffer of stage_rows rows.
+void make_stages(bnbp_handle* h, const std::vector<int32_t>& e_card)
+{
+    h->stages.clear();
+    auto rows_of = [&](int x, int& plr, int& pmr, int& lmr) {
+        const NodeMeta& nd = h->nodes[x];
+        plr = 2 * nd.card;
+        pmr = 0;
+        for (int j = 0; j < nd.k; ++j) pmr += e_card[nd.e0 + j];
+        lmr = nd.m * nd.card;
+    };
+    int x = 0;
+    while (x < h->N) {
+        StageMeta st;
+        memset(&st, 0, sizeof st);
+        st.g0 = x;
+        st.pl_row0 = h->nodes[x].pl_off; st.pm_row0 = h->nodes[x].pin_off; st.lm_row0 = h->nodes[x].lin_off;
+        int plr, pmr, lmr;
+        rows_of(x, plr, pmr, lmr);
+        if (plr + pmr + lmr > h->stage_rows) {           // too large to stage: plain loads for this node
+            st.g1 = x + 1; st.staged = 0;
+            h->stages.push_back(st);
+            ++x;
+            continue;
+        }
+        st.staged = 1;
+        int tot = 0;
+        while (x < h->N) {
+            rows_of(x, plr, pmr, lmr);
+            if (tot + plr + pmr + lmr > h->stage_rows) break;
+            tot += plr + pmr + lmr;
+            st.pl_rows += plr; st.pm_rows += pmr; st.lm_rows += lmr;
+            ++x;
+        }
+        st.g1 = x;
+        h->stages.push_back(st);
+    }
+    const int S = (int)h->stages.size();
+    h->stage_cost.assign(S + 1, 0.0);
+    for (int s = 0; s < S; ++s)
+        h->stage_cost[s + 1] = h->stage_cost[s] + (h->cost_prefix[h->stages[s].g1] - h->cost_prefix[h->stages[s].g0]);
 }
 
 int ensure_state(bnbp_handle* h, int64_t n_cases)
@@ -212,6 +262,9 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     SweepArgs<T> sa;
     memset(&sa, 0, sizeof sa);
     sa.nodes = (const NodeMeta*)h->d_nodes.p;
+    sa.stages = (const StageMeta*)h->d_stages.p;
+    sa.stage_rows = h->stage_rows;
+    sa.n_stage_bufs = h->n_stage_bufs;
     sa.e_card = (const int32_t*)h->d_e_card.p;
     sa.e_lam_out = (const int32_t*)h->d_e_lam_out.p;
     sa.c_pi_out = (const int32_t*)h->d_c_pi_out.p;
@@ -221,7 +274,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.PL = h->PL; sa.M = h->M; sa.W = h->W;
     // enough threads to fill 148 SMs a few times over: split the node walk when the batch is small
     const int64_t threads_per_row = (int64_t)tiles * BLOCK_THREADS;
-    int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, h->N / 8)),
+    int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, (int)h->stages.size() / 2)),
                                           std::max<int64_t>(1, (148 * 2048 * 2 + threads_per_row - 1) / threads_per_row));
     sa.n_chunks = n_chunks;
     make_chunks(h, n_chunks, sa.chunk_off);
@@ -231,7 +284,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.eps = (T)prm.epsilon;
     sa.damping = (T)prm.damping;
     T* delta = (T*)h->d_delta.p;
-    const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * sizeof(T);
+    const size_t smem = h->sweep_smem;
     dim3 grid(tiles, n_chunks);
 
     // event pair around the sweeps of this chunk
@@ -515,12 +568,26 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     }
     h->tb = BLOCK_THREADS * h->vec;
     h->cpt_values = net->cpt_off[N];
-    const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * h->tsize;
-    if (smem > 200 * 1024) return fail(BNBP_ERR_INVALID, "parent sets too wide for the shared-memory scratch");
+    const size_t scratch_bytes = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * h->tsize;
+    if (scratch_bytes > 160 * 1024) return fail(BNBP_ERR_INVALID, "parent sets too wide for the shared-memory scratch");
+    {   // TMA pipeline geometry: n_stage_bufs buffers of stage_rows rows (one row = one slot of a tile)
+        const size_t rowb = (size_t)h->tb * h->tsize;
+        size_t budget = 48 * 1024;
+        if (const char* ev = getenv("BNBP_STAGE_KB")) budget = (size_t)std::max(4, atoi(ev)) * 1024;
+        if (const char* ev = getenv("BNBP_NST")) h->n_stage_bufs = std::min(8, std::max(1, atoi(ev)));
+        budget = std::min(budget, (size_t)(220 * 1024) - scratch_bytes - 128);
+        h->stage_rows = (int)std::max<size_t>(4, budget / h->n_stage_bufs / rowb);
+        h->sweep_smem = 128 + (size_t)h->n_stage_bufs * h->stage_rows * rowb + scratch_bytes;
+        if (h->sweep_smem > 227 * 1024) return fail(BNBP_ERR_INVALID, "shared-memory budget exceeded");
+        make_stages(h.get(), e_card);
+    }
+    const size_t smem = h->sweep_smem;
 
     // ---- upload -------------------------------------------------------------------------------------
     int rc;
     if ((rc = h->d_nodes.ensure(sizeof(NodeMeta) * N))) return rc;
+    if ((rc = h->d_stages.ensure(sizeof(StageMeta) * h->stages.size()))) return rc;
+    CU_TRY(cudaMemcpy(h->d_stages.p, h->stages.data(), sizeof(StageMeta) * h->stages.size(), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->d_nodes.p, h->nodes.data(), sizeof(NodeMeta) * N, cudaMemcpyHostToDevice));
     const size_t eb = sizeof(int32_t) * std::max(E, 1);
     if ((rc = h->d_e_card.ensure(eb)) || (rc = h->d_e_lam_out.ensure(eb)) || (rc = h->d_c_pi_out.ensure(eb))) return rc;
@@ -539,7 +606,7 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     }
     CU_TRY(cudaMallocHost((void**)&h->pinned_poll, 4 * sizeof(int32_t)));
     // opt in to the dynamic shared memory the scratch needs
-    if (smem > 48 * 1024) {
+    {
         cudaError_t e = h->precision == BNBP_FP32 ? set_smem<float>(h.get(), (int)smem) : set_smem<double>(h.get(), (int)smem);
         if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("shared-memory opt-in: ") + cudaGetErrorString(e));
     }
@@ -552,7 +619,7 @@ void bnbp_destroy(bnbp_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
+    for (DevBuf* b : {&h->d_stages, &h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
                       &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out,
                       &h->s_out_sweeps, &h->s_out_conv})

@@ -39,8 +39,20 @@ struct NodeMeta {              // 48 bytes, warp-uniform
     int32_t scr_half;          // scratch values reserved for the outer parents' messages (accumulators follow)
 };
 
+struct StageMeta {             // 48 bytes, warp-uniform: one TMA stage = nodes [g0, g1)
+    int32_t g0, g1;
+    int32_t pl_row0, pl_rows;   // pi/lambda rows      [pl_row0, pl_row0 + pl_rows) of the tile
+    int32_t pm_row0, pm_rows;   // pi-message rows     (msg buffer)
+    int32_t lm_row0, lm_rows;   // lambda-message rows (msg buffer)
+    int32_t staged;             // 0: read set too large for a stage buffer -> plain loads
+    int32_t pad[3];
+};
+
 template <typename T> struct SweepArgs {
     const NodeMeta* nodes;
+    const StageMeta* stages;
+    int32_t stage_rows;         // capacity of one stage buffer, in rows
+    int32_t n_stage_bufs;       // pipeline depth
     const int32_t*  e_card;     // [E] cardinality of the parent of in-edge e
     const int32_t*  e_lam_out;  // [E] msg slot where the child writes lambda-msg (child->parent)
     const int32_t*  c_pi_out;   // [E] msg slot where the parent writes pi-msg (parent->child), out-edge order
@@ -51,7 +63,7 @@ template <typename T> struct SweepArgs {
     const uint32_t* evbits;     // [tiles][W][TB]
     int32_t PL, M, W;
     int32_t n_chunks;
-    int32_t chunk_off[MAX_CHUNKS + 1];
+    int32_t chunk_off[MAX_CHUNKS + 1];   // STAGE index ranges per grid.y chunk
     // convergence bookkeeping (only touched when FREEZE / CHECK)
     const T* delta_prev;        // delta of the previous sweep (valid if prev_tested)
     T*       delta_cur;         // atomicMax target of this sweep (CHECK)

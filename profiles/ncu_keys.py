@@ -1,0 +1,28 @@
+"""Key metrics of an ncu report (raw page), one column per captured launch.
+Usage: python profiles/ncu_keys.py rep.ncu-rep"""
+import csv
+import io
+import subprocess
+import sys
+
+txt = subprocess.run(["ncu", "-i", sys.argv[1], "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+rows = list(csv.reader(io.StringIO(txt)))
+hdr, units = rows[0], rows[1]
+want = ["Kernel Name", "gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum",
+        "gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed", "sm__throughput.avg.pct_of_peak_sustained_elapsed",
+        "sm__warps_active.avg.pct_of_peak_sustained_active", "launch__registers_per_thread",
+        "launch__occupancy_limit_registers", "launch__occupancy_limit_shared_mem", "launch__waves_per_multiprocessor",
+        "smsp__inst_executed.sum", "smsp__issue_active.avg.pct_of_peak_sustained_active",
+        "sm__pipe_fp64_cycles_active.avg.pct_of_peak_sustained_active",
+        "sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active",
+        "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct", "launch__shared_mem_per_block_dynamic",
+        "l1tex__data_pipe_lsu_wavefronts.avg.pct_of_peak_sustained_elapsed",
+        "lts__throughput.avg.pct_of_peak_sustained_elapsed", "l1tex__throughput.avg.pct_of_peak_sustained_elapsed"]
+for w in want:
+    if w not in hdr:
+        continue
+    i = hdr.index(w)
+    vals = [r[i] for r in rows[2:]]
+    if w == "Kernel Name":
+        vals = [v.split("(")[0].replace("void bnbp::", "")[:34] for v in vals]
+    print(f"{w:72s} {units[i]:10s} " + " | ".join(f"{v:>14s}" for v in vals))
