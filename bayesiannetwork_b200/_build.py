@@ -14,8 +14,21 @@ CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
 OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libbnbp.so")
+SPEC_SRC = os.path.join(CSRC, "bnbp_spec.cuh")           # compiled at run time by NVRTC ...
+SPEC_EMBED = os.path.join(CSRC, "bnbp_spec_embed.inc")   # ... from this generated raw-string copy
 HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_sweep.cuh"),
-           os.path.join(CSRC, "bnbp_variants.h"), os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
+           os.path.join(CSRC, "bnbp_variants.h"), os.path.join(CSRC, "bnbp_jit.h"), SPEC_SRC,
+           os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
+
+
+def embed_spec_header() -> None:
+    """bnbp_spec.cuh -> bnbp_spec_embed.inc (a C++ raw string literal #included by bnbp_jit.cu)."""
+    text = open(SPEC_SRC).read()
+    assert ')BNBPSPEC"' not in text
+    out = 'R"BNBPSPEC(' + text + ')BNBPSPEC"\n'
+    if not os.path.exists(SPEC_EMBED) or open(SPEC_EMBED).read() != out:
+        with open(SPEC_EMBED, "w") as f:
+            f.write(out)
 
 
 def sweep_variants():
@@ -45,7 +58,8 @@ def _env():
 
 
 def _units():
-    units = [(os.path.join(CSRC, "bnbp_api.cu"), os.path.join(OBJDIR, "bnbp_api.o"), [])]
+    units = [(os.path.join(CSRC, "bnbp_api.cu"), os.path.join(OBJDIR, "bnbp_api.o"), []),
+             (os.path.join(CSRC, "bnbp_jit.cu"), os.path.join(OBJDIR, "bnbp_jit.o"), [])]
     for t, v, r, k in sweep_variants():
         units.append((os.path.join(CSRC, "bnbp_sweep_inst.cu"),
                       os.path.join(OBJDIR, f"sweep_{t}_v{v}_r{r}_k{k}.o"),
@@ -63,6 +77,7 @@ def _stale(obj: str, src: str) -> bool:
 def build(force: bool = False, verbose: bool = False, extra=()) -> str:
     os.makedirs(OBJDIR, exist_ok=True)
     nvcc = nvcc_path()
+    embed_spec_header()
     todo = [(s, o, d) for (s, o, d) in _units() if force or _stale(o, s)]
 
     def compile_one(u):
@@ -85,7 +100,7 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
             os.remove(os.path.join(OBJDIR, f))
     if todo or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", LIB, *objs]
+               "-o", LIB, *objs, "-ldl"]
         subprocess.run(cmd, check=True, env=_env())
     return LIB
 

@@ -24,7 +24,7 @@ class FlatNetworkC(C.Structure):
 
 class OptionsC(C.Structure):
     _fields_ = [("precision", C.c_int32), ("device", C.c_int32), ("max_resident_cases", C.c_int64),
-                ("reserved", C.c_int32 * 8)]
+                ("specialize", C.c_int32), ("reserved", C.c_int32 * 7)]
 
 
 class EvidenceC(C.Structure):
@@ -43,11 +43,12 @@ class StatsC(C.Structure):
                 ("bytes_per_value", C.c_int64), ("last_case_sweeps", C.c_int64),
                 ("last_sweep_launches", C.c_int64), ("last_kernel_launches", C.c_int64),
                 ("last_sweep_ms", C.c_double), ("last_total_ms", C.c_double),
-                ("resident_cases", C.c_int64), ("reserved", C.c_int64 * 8)]
+                ("resident_cases", C.c_int64), ("last_specialised", C.c_int64), ("cases_per_tile", C.c_int64),
+                ("spec_compile_ms", C.c_double), ("reserved", C.c_int64 * 5)]
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",
-           "bnbp_run_batch_device", "bnbp_get_stats", "bnbp_refresh_cpt"]
+           "bnbp_run_batch_device", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source"]
 
 
 def lib_path() -> str:
@@ -81,6 +82,11 @@ def load():
     lib.bnbp_get_stats.argtypes = [C.c_void_p, C.POINTER(StatsC)]
     lib.bnbp_refresh_cpt.restype = C.c_int
     lib.bnbp_refresh_cpt.argtypes = [C.c_void_p, C.c_void_p, C.c_int64]
+    lib.bnbp_precompile.restype = C.c_int
+    lib.bnbp_precompile.argtypes = [C.POINTER(FlatNetworkC), C.POINTER(OptionsC), C.c_int32]
+    lib.bnbp_spec_source.restype = C.c_int
+    lib.bnbp_spec_source.argtypes = [C.POINTER(FlatNetworkC), C.POINTER(OptionsC), C.c_int32, C.c_char_p, C.c_int64,
+                                     C.POINTER(C.c_int64)]
     _lib = lib
     return lib
 

@@ -5,6 +5,7 @@
 #include "../../include/bnbp.h"
 #include "bnbp_kernels.cuh"
 #include "bnbp_variants.h"
+#include "bnbp_jit.h"
 
 #include <algorithm>
 #include <cmath>
@@ -75,13 +76,21 @@ struct bnbp_handle {
     int64_t max_resident = 0;
     std::vector<NodeMeta> nodes;
     std::vector<double> cost_prefix;   // [N+1]
-    std::vector<StageMeta> stages;     // TMA stages (groups of consecutive nodes)
-    std::vector<double> stage_cost;    // prefix cost per stage, [n_stages+1]
-    int stage_rows = 0, n_stage_bufs = 3;
-    size_t sweep_smem = 0;
     std::vector<int32_t> card;
+    std::vector<int32_t> e_card, e_lam_out, c_pi_out;   // per in-edge / out-edge tables (host copies)
+    std::vector<double> cpt_host;      // reference-layout CPT values (for the specialised kernels' constant bank)
+    // network-specialised sweep kernels (bnbp_jit.h); index = variant 0 plain, 1 freeze, 2 freeze+check
+    int specialize = 0;                // BNBP_SPEC_AUTO / ALWAYS / NEVER
+    bool spec_eligible_ = false;
+    std::string spec_why;              // why the network is not specialised
+    int spec_vec = 1, spec_minb = 1, spec_ahead = 1;
+    SpecKernel spec[3];
+    int spec_state[3] = {0, 0, 0};     // 0 untried, 1 loaded, -1 failed
+    bool run_spec = false;             // kernel family of the current run
+    int last_specialised = 0;
+    double spec_compile_ms = 0.0;
     // device network
-    DevBuf d_stages, d_nodes, d_e_card, d_e_lam_out, d_c_pi_out, d_cpt, d_pl_init;
+    DevBuf d_nodes, d_e_card, d_e_lam_out, d_c_pi_out, d_cpt, d_pl_init;
     // device state for the resident chunk
     int64_t cap = 0;
     DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
@@ -129,69 +138,24 @@ cudaError_t set_smem(const bnbp_handle* h, int bytes)
     return cudaErrorInvalidConfiguration;
 }
 
-// stage ranges of roughly equal cost for grid.y
+// node ranges of roughly equal cost for grid.y
 void make_chunks(const bnbp_handle* h, int n_chunks, int32_t* off)
 {
-    const int S = (int)h->stages.size();
-    const double total = h->stage_cost[S];
+    const double total = h->cost_prefix[h->N];
     off[0] = 0;
     int x = 0;
     for (int c = 1; c < n_chunks; ++c) {
         const double target = total * c / n_chunks;
-        while (x < S && h->stage_cost[x + 1] <= target) ++x;
+        while (x < h->N && h->cost_prefix[x + 1] <= target) ++x;
         off[c] = std::max(x, off[c - 1]);
     }
-    off[n_chunks] = S;
-}
-
-// Partition the nodes into TMA stages: consecutive nodes whose read set (pi/lambda rows, incoming
-// pi-message rows, incoming lambda-message rows -- each contiguous by construction of the slot
-// layout) fits one stage buffer of stage_rows rows.
-void make_stages(bnbp_handle* h, const std::vector<int32_t>& e_card)
-{
-    h->stages.clear();
-    auto rows_of = [&](int x, int& plr, int& pmr, int& lmr) {
-        const NodeMeta& nd = h->nodes[x];
-        plr = 2 * nd.card;
-        pmr = 0;
-        for (int j = 0; j < nd.k; ++j) pmr += e_card[nd.e0 + j];
-        lmr = nd.m * nd.card;
-    };
-    int x = 0;
-    while (x < h->N) {
-        StageMeta st;
-        memset(&st, 0, sizeof st);
-        st.g0 = x;
-        st.pl_row0 = h->nodes[x].pl_off; st.pm_row0 = h->nodes[x].pin_off; st.lm_row0 = h->nodes[x].lin_off;
-        int plr, pmr, lmr;
-        rows_of(x, plr, pmr, lmr);
-        if (plr + pmr + lmr > h->stage_rows) {           // too large to stage: plain loads for this node
-            st.g1 = x + 1; st.staged = 0;
-            h->stages.push_back(st);
-            ++x;
-            continue;
-        }
-        st.staged = 1;
-        int tot = 0;
-        while (x < h->N) {
-            rows_of(x, plr, pmr, lmr);
-            if (tot + plr + pmr + lmr > h->stage_rows) break;
-            tot += plr + pmr + lmr;
-            st.pl_rows += plr; st.pm_rows += pmr; st.lm_rows += lmr;
-            ++x;
-        }
-        st.g1 = x;
-        h->stages.push_back(st);
-    }
-    const int S = (int)h->stages.size();
-    h->stage_cost.assign(S + 1, 0.0);
-    for (int s = 0; s < S; ++s)
-        h->stage_cost[s + 1] = h->stage_cost[s] + (h->cost_prefix[h->stages[s].g1] - h->cost_prefix[h->stages[s].g0]);
+    off[n_chunks] = h->N;
 }
 
 int ensure_state(bnbp_handle* h, int64_t n_cases)
 {
-    int64_t want = (n_cases + h->tb - 1) / h->tb * h->tb;
+    const int64_t TBMAX = 512;          // every kernel family's tile width divides this
+    int64_t want = (n_cases + TBMAX - 1) / TBMAX * TBMAX;
     const size_t per_case = (size_t)(h->PL + 2 * (size_t)h->M) * h->tsize + (size_t)h->W * 4 + 3 * h->tsize + 8;
     int64_t limit = h->max_resident;
     if (limit <= 0) {
@@ -202,7 +166,7 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
         double usable = 0.80 * (double)(free_b + held);
         limit = (int64_t)(usable / (double)(per_case + (size_t)h->V * 8));
     }
-    limit = std::max<int64_t>(h->tb, limit / h->tb * h->tb);
+    limit = std::max<int64_t>(TBMAX, limit / TBMAX * TBMAX);
     want = std::min(want, limit);
     if (want <= h->cap) return BNBP_OK;
     // grow: release first so the new allocation can reuse the space
@@ -218,6 +182,76 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
     if ((rc = h->d_status.ensure((size_t)want))) return rc;
     if ((rc = h->d_sweeps.ensure((size_t)want * 4))) return rc;
     h->cap = want;
+    return BNBP_OK;
+}
+
+SpecLayout spec_layout(const bnbp_handle* h)
+{
+    SpecLayout L;
+    L.N = h->N; L.PL = h->PL; L.M = h->M; L.W = h->W;
+    L.cpt_values = h->cpt_values;
+    L.nodes = h->nodes.data();
+    L.e_card = h->e_card.data();
+    L.e_lam_out = h->e_lam_out.data();
+    L.c_pi_out = h->c_pi_out.data();
+    return L;
+}
+
+// Make variant v of the specialised kernel available (compile or fetch from the cache, load, upload
+// the CPT arena into its constant bank).
+int ensure_spec(bnbp_handle* h, int v)
+{
+    if (h->spec_state[v] == 1) return BNBP_OK;
+    if (h->spec_state[v] < 0) return fail(BNBP_ERR_INVALID, "specialised kernel unavailable: " + h->spec_why);
+    h->spec_state[v] = -1;
+    SpecConfig cfg;
+    cfg.fp32 = h->precision == BNBP_FP32;
+    cfg.vec = h->spec_vec; cfg.minb = h->spec_minb; cfg.variant = v; cfg.ahead = h->spec_ahead;
+    const std::string src = spec_source(spec_layout(h), cfg);
+    std::vector<char> cubin;
+    std::string err;
+    bool cached = false;
+    double ms = 0;
+    if (!spec_compile(src, &cubin, &cached, &ms, &err)) { h->spec_why = err; return fail(BNBP_ERR_CUDA, err); }
+    h->spec_compile_ms += ms;
+    if (!spec_load(cubin, &h->spec[v], &err)) { h->spec_why = err; return fail(BNBP_ERR_CUDA, err); }
+    h->spec[v].from_cache = cached;
+    h->spec[v].compile_ms = ms;
+    bool ok;
+    if (cfg.fp32) {
+        std::vector<float> tmp(h->cpt_host.begin(), h->cpt_host.end());
+        ok = spec_upload_cpt(h->spec[v], tmp.data(), tmp.size() * 4, &err);
+    } else {
+        ok = spec_upload_cpt(h->spec[v], h->cpt_host.data(), h->cpt_host.size() * 8, &err);
+    }
+    if (!ok) { spec_unload(&h->spec[v]); h->spec_why = err; return fail(BNBP_ERR_CUDA, err); }
+    h->spec_state[v] = 1;
+    return BNBP_OK;
+}
+
+// Kernel family of one run.  Decided before the state is initialised because the tile width
+// (cases per thread) belongs to the family.  ALWAYS: failure is an error; AUTO: the generic GPU
+// kernel takes over (still CUDA: there is no CPU path).
+int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm)
+{
+    h->run_spec = false;
+    const bool want = h->specialize == BNBP_SPEC_ALWAYS ||
+                      (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
+    if (want) {
+        if (!h->spec_eligible_)
+            return fail(BNBP_ERR_INVALID, "specialize=ALWAYS but the network is not eligible: " + h->spec_why);
+        const bool eps_mode = prm.epsilon > 0.0;
+        const int interval = prm.check_interval > 0 ? prm.check_interval : 1;
+        bool need[3] = {!eps_mode && prm.damping == 0.0, eps_mode && interval > 1 && prm.damping == 0.0,
+                        eps_mode || prm.damping != 0.0};
+        bool ok = true;
+        for (int v = 0; v < 3 && ok; ++v)
+            if (need[v] && ensure_spec(h, v) != BNBP_OK) ok = false;
+        if (!ok && h->specialize == BNBP_SPEC_ALWAYS) return BNBP_ERR_CUDA;   // message already set
+        h->run_spec = ok;
+    }
+    h->tb = BLOCK_THREADS * (h->run_spec ? h->spec_vec : h->vec);
+    h->last_specialised = h->run_spec ? 1 : 0;
     return BNBP_OK;
 }
 
@@ -262,9 +296,6 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     SweepArgs<T> sa;
     memset(&sa, 0, sizeof sa);
     sa.nodes = (const NodeMeta*)h->d_nodes.p;
-    sa.stages = (const StageMeta*)h->d_stages.p;
-    sa.stage_rows = h->stage_rows;
-    sa.n_stage_bufs = h->n_stage_bufs;
     sa.e_card = (const int32_t*)h->d_e_card.p;
     sa.e_lam_out = (const int32_t*)h->d_e_lam_out.p;
     sa.c_pi_out = (const int32_t*)h->d_c_pi_out.p;
@@ -274,7 +305,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.PL = h->PL; sa.M = h->M; sa.W = h->W;
     // enough threads to fill 148 SMs a few times over: split the node walk when the batch is small
     const int64_t threads_per_row = (int64_t)tiles * BLOCK_THREADS;
-    int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, (int)h->stages.size() / 2)),
+    int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, h->N / 8)),
                                           std::max<int64_t>(1, (148 * 2048 * 2 + threads_per_row - 1) / threads_per_row));
     sa.n_chunks = n_chunks;
     make_chunks(h, n_chunks, sa.chunk_off);
@@ -284,7 +315,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.eps = (T)prm.epsilon;
     sa.damping = (T)prm.damping;
     T* delta = (T*)h->d_delta.p;
-    const size_t smem = h->sweep_smem;
+    const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * sizeof(T);
     dim3 grid(tiles, n_chunks);
 
     // event pair around the sweeps of this chunk
@@ -314,8 +345,20 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             sa.delta_next = delta + (size_t)((t + 1) % 3) * h->cap;
             sa.sweep_index = t;
             sa.prev_tested = prev_tested ? 1 : 0;
-            cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode, check, st);
-            if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
+            if (h->run_spec) {
+                // network-specialised kernel: variant 0 plain, 1 freeze, 2 freeze + check
+                const int variant = check ? 2 : (eps_mode ? 1 : 0);
+                SpecAux<T> ax;
+                ax.delta_prev = sa.delta_prev; ax.delta_cur = sa.delta_cur; ax.delta_next = sa.delta_next;
+                ax.status = sa.status; ax.sweeps = sa.sweeps; ax.last_active = sa.last_active;
+                ax.sweep_index = sa.sweep_index; ax.prev_tested = sa.prev_tested; ax.eps = sa.eps; ax.damping = sa.damping;
+                std::string err;
+                if (!spec_launch(h->spec[variant], (unsigned)tiles, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
+                    return fail(BNBP_ERR_CUDA, err);
+            } else {
+                cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode, check, st);
+                if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
+            }
             prev_tested = tested;
             h->last_sweep_launches++;
             h->last_kernel_launches++;
@@ -409,50 +452,33 @@ int upload_cpt(bnbp_handle* h, const double* cpt, int64_t n)
     return BNBP_OK;
 }
 
-} // namespace
-
-// =================================================================================================
-extern "C" {
-
-const char* bnbp_last_error(void) { return g_err.c_str(); }
-
-int bnbp_device_count(void)
+// Host-only part of bnbp_create: validation, slot layout, kernel-family choice.  No CUDA calls, so
+// bnbp_precompile / bnbp_spec_source can run it on a machine without a GPU.
+size_t generic_smem(const bnbp_handle* h)
 {
-    int n = 0;
-    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
-    return n;
+    return (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * h->tsize;
 }
 
-int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_handle** out)
+int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_handle* h)
 {
-    if (!net || !out) return fail(BNBP_ERR_INVALID, "bnbp_create: NULL argument");
-    *out = nullptr;
+    if (!net) return fail(BNBP_ERR_INVALID, "network is NULL");
     const int N = net->n_nodes;
     if (N <= 0 || !net->card || !net->parent_off || !net->cpt_off || !net->cpt)
         return fail(BNBP_ERR_INVALID, "bnbp_create: empty or incomplete network");
     const int E = net->parent_off[N];
     if (net->parent_off[0] != 0 || net->cpt_off[0] != 0 || E < 0 || (E > 0 && !net->parents))
         return fail(BNBP_ERR_INVALID, "bnbp_create: malformed offset arrays");
-
-    int ndev = 0;
-    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
-        cudaGetLastError();
-        return fail(BNBP_ERR_NO_DEVICE, "no CUDA device: libbnbp has no CPU fallback");
-    }
-    int dev = opt ? opt->device : -1;
-    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
-    if (dev >= ndev) return fail(BNBP_ERR_INVALID, "bnbp_create: device ordinal out of range");
-    CU_TRY(cudaSetDevice(dev));
-    cudaDeviceProp prop;
-    CU_TRY(cudaGetDeviceProperties(&prop, dev));
-    if (prop.major < 10)
-        return fail(BNBP_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: kernels are built for sm_100a only");
-
-    std::unique_ptr<bnbp_handle> h(new bnbp_handle());
-    h->device = dev;
     h->precision = (opt && opt->precision == BNBP_FP32) ? BNBP_FP32 : BNBP_FP64;
     h->tsize = h->precision == BNBP_FP32 ? 4 : 8;
     h->max_resident = opt ? opt->max_resident_cases : 0;
+    h->specialize = opt ? opt->specialize : BNBP_SPEC_AUTO;
+    if (const char* ev = getenv("BNBP_SPECIALIZE")) {      // tuning / test knob, overrides the option
+        if (!strcmp(ev, "always")) h->specialize = BNBP_SPEC_ALWAYS;
+        else if (!strcmp(ev, "never")) h->specialize = BNBP_SPEC_NEVER;
+        else if (!strcmp(ev, "auto")) h->specialize = BNBP_SPEC_AUTO;
+    }
+    if (h->specialize < BNBP_SPEC_AUTO || h->specialize > BNBP_SPEC_NEVER)
+        return fail(BNBP_ERR_INVALID, "bnbp_options.specialize out of range");
     h->N = N;
     h->E = E;
     h->card.assign(net->card, net->card + N);
@@ -503,7 +529,10 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     // (grouped by child), then lambda-messages in out-edge order (grouped by parent), so that
     // everything node X READS is contiguous; what it writes is scattered to its neighbours' blocks.
     h->nodes.resize(N);
-    std::vector<int32_t> e_card(std::max(E, 1)), e_lam_out(std::max(E, 1)), c_pi_out(std::max(E, 1));
+    std::vector<int32_t>& e_card = h->e_card;
+    std::vector<int32_t>& e_lam_out = h->e_lam_out;
+    std::vector<int32_t>& c_pi_out = h->c_pi_out;
+    e_card.assign(std::max(E, 1), 0); e_lam_out.assign(std::max(E, 1), 0); c_pi_out.assign(std::max(E, 1), 0);
     std::vector<int32_t> e_pin(std::max(E, 1));      // slot of pi-msg of in-edge e
     int pl = 0, bel = 0, pin = 0;
     for (int x = 0; x < N; ++x) {
@@ -568,26 +597,71 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     }
     h->tb = BLOCK_THREADS * h->vec;
     h->cpt_values = net->cpt_off[N];
-    const size_t scratch_bytes = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * h->tsize;
-    if (scratch_bytes > 160 * 1024) return fail(BNBP_ERR_INVALID, "parent sets too wide for the shared-memory scratch");
-    {   // TMA pipeline geometry: n_stage_bufs buffers of stage_rows rows (one row = one slot of a tile)
-        const size_t rowb = (size_t)h->tb * h->tsize;
-        size_t budget = 48 * 1024;
-        if (const char* ev = getenv("BNBP_STAGE_KB")) budget = (size_t)std::max(4, atoi(ev)) * 1024;
-        if (const char* ev = getenv("BNBP_NST")) h->n_stage_bufs = std::min(8, std::max(1, atoi(ev)));
-        budget = std::min(budget, (size_t)(220 * 1024) - scratch_bytes - 128);
-        h->stage_rows = (int)std::max<size_t>(4, budget / h->n_stage_bufs / rowb);
-        h->sweep_smem = 128 + (size_t)h->n_stage_bufs * h->stage_rows * rowb + scratch_bytes;
-        if (h->sweep_smem > 227 * 1024) return fail(BNBP_ERR_INVALID, "shared-memory budget exceeded");
-        make_stages(h.get(), e_card);
+    if (generic_smem(h) > 200 * 1024) return fail(BNBP_ERR_INVALID, "parent sets too wide for the shared-memory scratch");
+
+
+    h->cpt_host.assign(net->cpt, net->cpt + net->cpt_off[N]);
+    // ---- network-specialised kernel: eligibility and tuning ---------------------------------------
+    {
+        SpecLayout L = spec_layout(h);
+        h->spec_eligible_ = spec_eligible(L, h->precision == BNBP_FP32, &h->spec_why);
+        h->spec_vec = h->precision == BNBP_FP32 ? 2 : 1;
+        h->spec_minb = h->precision == BNBP_FP32 ? 4 : 3;
+        h->spec_ahead = 1;
+        if (const char* ev = getenv("BNBP_SPEC_VEC")) {
+            const int v = atoi(ev);
+            if (v == 1 || v == 2 || (v == 4 && h->tsize == 4)) h->spec_vec = v;
+        }
+        if (const char* ev = getenv("BNBP_SPEC_MINB")) h->spec_minb = std::min(16, std::max(1, atoi(ev)));
+        if (const char* ev = getenv("BNBP_SPEC_AHEAD")) h->spec_ahead = std::min(4, std::max(0, atoi(ev)));
     }
-    const size_t smem = h->sweep_smem;
+    return BNBP_OK;
+}
+
+} // namespace
+
+// =================================================================================================
+extern "C" {
+
+const char* bnbp_last_error(void) { return g_err.c_str(); }
+
+int bnbp_device_count(void)
+{
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    return n;
+}
+
+int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_handle** out)
+{
+    if (!net || !out) return fail(BNBP_ERR_INVALID, "bnbp_create: NULL argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BNBP_ERR_NO_DEVICE, "no CUDA device: libbnbp has no CPU fallback");
+    }
+    int dev = opt ? opt->device : -1;
+    if (dev < 0) CU_TRY(cudaGetDevice(&dev));
+    if (dev >= ndev) return fail(BNBP_ERR_INVALID, "bnbp_create: device ordinal out of range");
+    CU_TRY(cudaSetDevice(dev));
+    cudaDeviceProp prop;
+    CU_TRY(cudaGetDeviceProperties(&prop, dev));
+    if (prop.major < 10)
+        return fail(BNBP_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: kernels are built for sm_100a only");
+
+    std::unique_ptr<bnbp_handle> h(new bnbp_handle());
+    h->device = dev;
+    int rc = build_layout(net, opt, h.get());
+    if (rc) return rc;
+    const int N = h->N, E = h->E;
+    const std::vector<int32_t>& e_card = h->e_card;
+    const std::vector<int32_t>& e_lam_out = h->e_lam_out;
+    const std::vector<int32_t>& c_pi_out = h->c_pi_out;
+    const size_t smem = generic_smem(h.get());
 
     // ---- upload -------------------------------------------------------------------------------------
-    int rc;
     if ((rc = h->d_nodes.ensure(sizeof(NodeMeta) * N))) return rc;
-    if ((rc = h->d_stages.ensure(sizeof(StageMeta) * h->stages.size()))) return rc;
-    CU_TRY(cudaMemcpy(h->d_stages.p, h->stages.data(), sizeof(StageMeta) * h->stages.size(), cudaMemcpyHostToDevice));
     CU_TRY(cudaMemcpy(h->d_nodes.p, h->nodes.data(), sizeof(NodeMeta) * N, cudaMemcpyHostToDevice));
     const size_t eb = sizeof(int32_t) * std::max(E, 1);
     if ((rc = h->d_e_card.ensure(eb)) || (rc = h->d_e_lam_out.ensure(eb)) || (rc = h->d_c_pi_out.ensure(eb))) return rc;
@@ -606,7 +680,7 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     }
     CU_TRY(cudaMallocHost((void**)&h->pinned_poll, 4 * sizeof(int32_t)));
     // opt in to the dynamic shared memory the scratch needs
-    {
+    if (smem > 48 * 1024) {
         cudaError_t e = h->precision == BNBP_FP32 ? set_smem<float>(h.get(), (int)smem) : set_smem<double>(h.get(), (int)smem);
         if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("shared-memory opt-in: ") + cudaGetErrorString(e));
     }
@@ -619,11 +693,12 @@ void bnbp_destroy(bnbp_handle* h)
     if (!h) return;
     cudaSetDevice(h->device);
     if (h->stream) cudaStreamSynchronize(h->stream);
-    for (DevBuf* b : {&h->d_stages, &h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
+    for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
                       &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out,
                       &h->s_out_sweeps, &h->s_out_conv})
         b->release();
+    for (int v = 0; v < 3; ++v) spec_unload(&h->spec[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_total[i]) cudaEventDestroy(h->ev_total[i]);
@@ -639,8 +714,60 @@ int bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values)
     if (!h || !cpt) return fail(BNBP_ERR_INVALID, "bnbp_refresh_cpt: NULL argument");
     if (n_values != h->cpt_values) return fail(BNBP_ERR_INVALID, "bnbp_refresh_cpt: CPT size changed (topology edits need a new handle)");
     CU_TRY(cudaSetDevice(h->device));
-    CU_TRY(cudaStreamSynchronize(h->stream));
+    CU_TRY(cudaDeviceSynchronize());          // runs may have been enqueued on caller streams
+    h->cpt_host.assign(cpt, cpt + n_values);
+    for (int v = 0; v < 3; ++v) {             // constant banks of the loaded specialised kernels
+        if (h->spec_state[v] != 1) continue;
+        std::string err;
+        bool ok;
+        if (h->precision == BNBP_FP32) {
+            std::vector<float> tmp(h->cpt_host.begin(), h->cpt_host.end());
+            ok = spec_upload_cpt(h->spec[v], tmp.data(), tmp.size() * 4, &err);
+        } else {
+            ok = spec_upload_cpt(h->spec[v], h->cpt_host.data(), h->cpt_host.size() * 8, &err);
+        }
+        if (!ok) return fail(BNBP_ERR_CUDA, err);
+    }
     return h->precision == BNBP_FP32 ? upload_cpt<float>(h, cpt, n_values) : upload_cpt<double>(h, cpt, n_values);
+}
+
+int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant_mask)
+{
+    bnbp_handle h;
+    int rc = build_layout(net, opt, &h);
+    if (rc) return rc;
+    if (!h.spec_eligible_) return fail(BNBP_ERR_INVALID, "network is not eligible for specialisation: " + h.spec_why);
+    for (int v = 0; v < 3; ++v) {
+        if (!(variant_mask & (1 << v))) continue;
+        SpecConfig cfg;
+        cfg.fp32 = h.precision == BNBP_FP32;
+        cfg.vec = h.spec_vec; cfg.minb = h.spec_minb; cfg.variant = v; cfg.ahead = h.spec_ahead;
+        std::vector<char> cubin;
+        std::string err;
+        if (!spec_compile(spec_source(spec_layout(&h), cfg), &cubin, nullptr, nullptr, &err)) return fail(BNBP_ERR_CUDA, err);
+    }
+    return BNBP_OK;
+}
+
+int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant, char* buf, int64_t cap,
+                     int64_t* needed)
+{
+    if (variant < 0 || variant > 2) return fail(BNBP_ERR_INVALID, "variant must be 0, 1 or 2");
+    bnbp_handle h;
+    int rc = build_layout(net, opt, &h);
+    if (rc) return rc;
+    if (!h.spec_eligible_) return fail(BNBP_ERR_INVALID, "network is not eligible for specialisation: " + h.spec_why);
+    SpecConfig cfg;
+    cfg.fp32 = h.precision == BNBP_FP32;
+    cfg.vec = h.spec_vec; cfg.minb = h.spec_minb; cfg.variant = variant; cfg.ahead = h.spec_ahead;
+    const std::string src = spec_source(spec_layout(&h), cfg);
+    if (needed) *needed = (int64_t)src.size() + 1;
+    if (buf && cap > 0) {
+        const size_t n = std::min<size_t>(src.size(), (size_t)cap - 1);
+        memcpy(buf, src.data(), n);
+        buf[n] = 0;
+    }
+    return BNBP_OK;
 }
 
 int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm, void* out_marginals,
@@ -657,6 +784,7 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
+    if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
     if ((rc = ensure_state(h, ev->n_cases))) return rc;
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
     bool exact = true;
@@ -702,6 +830,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
+    if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
     if ((rc = ensure_state(h, ev->n_cases))) return rc;
     const int64_t cap = h->cap;
     if ((rc = h->s_out.ensure((size_t)cap * h->V * 8))) return rc;
@@ -771,6 +900,9 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->last_sweep_launches = h->last_sweep_launches;
     out->last_kernel_launches = h->last_kernel_launches;
     out->resident_cases = h->cap;
+    out->last_specialised = h->last_specialised;
+    out->cases_per_tile = h->tb;
+    out->spec_compile_ms = h->spec_compile_ms;
     out->last_sweep_ms = -1.0;
     out->last_total_ms = -1.0;
     if (h->total_recorded) {

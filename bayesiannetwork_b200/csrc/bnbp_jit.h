@@ -1,0 +1,78 @@
+// bnbp_jit.h — run-time specialisation of the sweep kernel to one network ("network compiler").
+//
+// spec_source() turns the flat layout of a network into CUDA source: one trait struct per node in
+// front of the hand-written templates of bnbp_spec.cuh.  SpecCompiler compiles it with NVRTC
+// (dlopen'ed: the library loads without it and then only the generic kernel is available) to an
+// sm_100a cubin, keeps cubins in an on-disk cache keyed by the source hash, and loads / launches
+// them through the driver API (entry points fetched with cudaGetDriverEntryPoint, so libbnbp
+// does not link libcuda either).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "bnbp_kernels.cuh"
+
+namespace bnbp {
+
+struct SpecLayout {                 // host view of the network the generator needs
+    int N = 0, PL = 0, M = 0, W = 0;
+    int64_t cpt_values = 0;
+    const NodeMeta* nodes = nullptr;
+    const int32_t* e_card = nullptr;      // [E] parent cardinality per in-edge
+    const int32_t* e_lam_out = nullptr;   // [E] slot of the lambda-message child -> parent
+    const int32_t* c_pi_out = nullptr;    // [E] slot of the pi-message parent -> child (out-edge order)
+};
+
+struct SpecConfig {
+    bool fp32 = false;
+    int vec = 1;        // cases per thread
+    int minb = 1;       // __launch_bounds__ min blocks per SM
+    int variant = 0;    // 0 plain, 1 freeze, 2 freeze + check
+    int ahead = 1;      // software-pipeline depth of the input loads
+};
+
+// Can (and should) this network be specialised?  why != nullptr receives the reason when not.
+bool spec_eligible(const SpecLayout& L, bool fp32, std::string* why);
+
+std::string spec_source(const SpecLayout& L, const SpecConfig& cfg);
+
+// mirrors bnbp_spec::Aux (device side) for T = double / float
+template <typename T> struct SpecAux {
+    const T* delta_prev;
+    T* delta_cur;
+    T* delta_next;
+    unsigned char* status;
+    int* sweeps;
+    int* last_active;
+    int sweep_index;
+    int prev_tested;
+    T eps;
+    T damping;
+};
+
+struct SpecKernel {                 // one loaded cubin
+    void* module = nullptr;         // CUmodule
+    void* function = nullptr;       // CUfunction
+    uint64_t cpt_dptr = 0;          // address of bnbp_cpt in the module
+    size_t cpt_bytes = 0;
+    bool from_cache = false;
+    double compile_ms = 0.0;
+};
+
+// Compile (or fetch from the cache) without touching a GPU.  Returns false and fills err on failure.
+bool spec_compile(const std::string& source, std::vector<char>* cubin, bool* from_cache, double* ms, std::string* err);
+
+// Load a cubin into the current context and resolve the kernel + the CPT constant.
+bool spec_load(const std::vector<char>& cubin, SpecKernel* out, std::string* err);
+void spec_unload(SpecKernel* k);
+bool spec_upload_cpt(const SpecKernel& k, const void* host, size_t bytes, std::string* err);
+
+// <<<tiles, 128, 0, st>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux)
+bool spec_launch(const SpecKernel& k, unsigned tiles, cudaStream_t st, void* pl, const void* cur, void* nxt,
+                 const void* evbits, const void* aux, std::string* err);
+
+std::string spec_cache_dir();
+
+} // namespace bnbp

@@ -39,20 +39,8 @@ struct NodeMeta {              // 48 bytes, warp-uniform
     int32_t scr_half;          // scratch values reserved for the outer parents' messages (accumulators follow)
 };
 
-struct StageMeta {             // 48 bytes, warp-uniform: one TMA stage = nodes [g0, g1)
-    int32_t g0, g1;
-    int32_t pl_row0, pl_rows;   // pi/lambda rows      [pl_row0, pl_row0 + pl_rows) of the tile
-    int32_t pm_row0, pm_rows;   // pi-message rows     (msg buffer)
-    int32_t lm_row0, lm_rows;   // lambda-message rows (msg buffer)
-    int32_t staged;             // 0: read set too large for a stage buffer -> plain loads
-    int32_t pad[3];
-};
-
 template <typename T> struct SweepArgs {
     const NodeMeta* nodes;
-    const StageMeta* stages;
-    int32_t stage_rows;         // capacity of one stage buffer, in rows
-    int32_t n_stage_bufs;       // pipeline depth
     const int32_t*  e_card;     // [E] cardinality of the parent of in-edge e
     const int32_t*  e_lam_out;  // [E] msg slot where the child writes lambda-msg (child->parent)
     const int32_t*  c_pi_out;   // [E] msg slot where the parent writes pi-msg (parent->child), out-edge order
@@ -63,7 +51,7 @@ template <typename T> struct SweepArgs {
     const uint32_t* evbits;     // [tiles][W][TB]
     int32_t PL, M, W;
     int32_t n_chunks;
-    int32_t chunk_off[MAX_CHUNKS + 1];   // STAGE index ranges per grid.y chunk
+    int32_t chunk_off[MAX_CHUNKS + 1];
     // convergence bookkeeping (only touched when FREEZE / CHECK)
     const T* delta_prev;        // delta of the previous sweep (valid if prev_tested)
     T*       delta_cur;         // atomicMax target of this sweep (CHECK)
@@ -130,7 +118,7 @@ template <typename T> struct InitArgs {
 };
 
 template <typename T>
-__global__ void __launch_bounds__(256) init_kernel(const InitArgs<T> a)
+__global__ void __launch_bounds__(512) init_kernel(const InitArgs<T> a)
 {
     const int tile = blockIdx.x, lane = threadIdx.x;
     const size_t TB = (size_t)a.TB;
@@ -188,7 +176,7 @@ __global__ void finalize_kernel(uint8_t* status, int32_t* sweeps, const T* delta
 
 // K4: belief = normalize(pi .* lambda) (:151-158), written case-major [case][sum r].
 template <typename T, typename OUT>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(512)
 belief_kernel(const NodeMeta* nodes, int n_nodes, const T* pl_all, int PL, int TBi, int V,
               int64_t n_valid, OUT* out, const uint8_t* status, const int32_t* sweeps,
               int32_t* out_sweeps, uint8_t* out_conv)

@@ -15,9 +15,6 @@
 namespace bnbp {
 
 constexpr int BLOCK = 128;
-#ifndef BNBP_MINB
-#define BNBP_MINB 1
-#endif
 
 // ------------------------------------------------------------------------------------------------
 // Parent side of one node: pi_X and all lambda-messages X->U_j from ONE pass over the CPT.
@@ -120,56 +117,59 @@ __device__ __forceinline__ void parent_run(ParentCtx<T, VEC, RMAX>& c)
 template <typename T> __device__ __forceinline__ T recip(T s) { return T(1) / s; }
 
 // ------------------------------------------------------------------------------------------------
-// TMA (bulk-async) staging.  A STAGE is a group of consecutive nodes whose read set -- pi/lambda
-// rows, incoming pi-message rows, incoming lambda-message rows; three CONTIGUOUS row ranges of the
-// tile, by construction of the slot layout -- fits one shared-memory buffer.  One elected thread
-// issues three cp.async.bulk copies per stage onto the stage's mbarrier; the block computes stage
-// s from shared memory while the copies of stages s+1 .. s+NST-1 are in flight, so HBM latency is
-// hidden by the pipeline depth and not by occupancy (profiles/r01b: 57 % long-scoreboard stalls at
-// 12 warps/SM with plain loads).  Results go straight to global memory with vector stores.
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+template <typename T, int VEC, int RMAX, int KNET, bool FREEZE, bool CHECK>
+__global__ void __launch_bounds__(BLOCK)
+sweep_kernel(const SweepArgs<T> a)
+{
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    constexpr size_t TBC = (size_t)BLOCK * VEC;        // cases per tile = slot stride
+    const int tid = threadIdx.x;
+    const int tile = blockIdx.x;
+    const int chunk = blockIdx.y;
+    const int lane0 = tid * VEC;                       // first case (within the tile) of this thread
+    const size_t case0 = (size_t)tile * TBC + lane0;   // index into per-case arrays
 
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count)
-{
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes)
-{
-    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity)
-{
-    asm volatile(
-        "{\n"
-        ".reg .pred p;\n"
-        "WAIT_LOOP:\n"
-        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
-        "@p bra WAIT_DONE;\n"
-        "bra WAIT_LOOP;\n"
-        "WAIT_DONE:\n"
-        "}\n" ::"r"(smem_u32(bar)), "r"(parity) : "memory");
-}
-__device__ __forceinline__ void bulk_g2s(void* dst_smem, const void* src_gmem, uint32_t bytes, uint64_t* bar)
-{
-    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                 ::"r"(smem_u32(dst_smem)), "l"(src_gmem), "r"(bytes), "r"(smem_u32(bar)) : "memory");
-}
+    bool act[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) act[v] = true;
+    if constexpr (FREEZE) {
+        // device-side loop termination: once a sweep found no active case, later (speculatively
+        // enqueued) launches return at once -- no host round-trip per sweep.
+        if (a.sweep_index > 0 && *reinterpret_cast<volatile int32_t*>(a.last_active) < a.sweep_index - 1) return;
+        // a case that met delta < eps at the previous (tested) sweep is frozen from now on: the
+        // reference breaks right after the commit (:135-147), so its state is final.
+        bool any = false;
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) {
+            bool frozen = a.status[case0 + v] != 0;
+            if (!frozen && a.prev_tested && a.delta_prev[case0 + v] < a.eps) {
+                frozen = true;
+                if (chunk == 0) { a.status[case0 + v] = 1; a.sweeps[case0 + v] = a.sweep_index; }
+            }
+            act[v] = !frozen;
+            any |= act[v];
+        }
+        if (chunk == 0) {
+#pragma unroll
+            for (int v = 0; v < VEC; ++v) a.delta_next[case0 + v] = Lim<T>::floor_();
+        }
+        if (!any) return;
+        if (chunk == 0) {
+            // one lane per warp that still has an active case publishes the sweep index
+            const unsigned live = __activemask();
+            if ((tid & 31) == __ffs(live) - 1) *a.last_active = a.sweep_index;   // benign race: same value
+        }
+    }
 
-// Where a node reads its time-t inputs from: row r of region R lives at base_R + (r - row0_R)*TBC
-// (+ the thread's lane offset, already applied to the base).
-template <typename T> struct NodeSrc {
-    const T* pl; int pl_row0;
-    const T* pm; int pm_row0;
-    const T* lm; int lm_row0;
-};
+    T* const pl = a.pl + ((size_t)tile * a.PL) * TBC + lane0;
+    const T* const cur = a.msg_cur + ((size_t)tile * a.M) * TBC + lane0;
+    T* const nxt = a.msg_nxt + ((size_t)tile * a.M) * TBC + lane0;
+    const uint32_t* const evb = a.evbits + ((size_t)tile * a.W) * TBC + lane0;
+    T* const scr = reinterpret_cast<T*>(smem_raw) + tid;
 
-template <typename T, int VEC, int RMAX, int KNET, bool CHECK>
-__device__ __forceinline__ void process_node(const SweepArgs<T>& a, const NodeMeta& nd, const NodeSrc<T>& src,
-                                             T* const pl, const T* const cur, T* const nxt, T* const scr,
-                                             const bool (&upd)[VEC], T (&dmax)[VEC])
-{
-    constexpr size_t TBC = (size_t)BLOCK * VEC;
-    const int r = nd.card, k = nd.k, m = nd.m;
+    T dmax[VEC];
+#pragma unroll
+    for (int v = 0; v < VEC; ++v) dmax[v] = Lim<T>::floor_();
 
     // normalise a message (RMAX-padded register vector), damp / delta it against the time-t value
     // when CHECK, store it to the time-(t+1) buffer
@@ -205,7 +205,7 @@ __device__ __forceinline__ void process_node(const SweepArgs<T>& a, const NodeMe
             }
     };
     // normalise pi_X / lambda_X and store in place; evidence nodes and frozen cases keep the old row
-    auto emit_node = [&](T* dst, const T (&val)[RMAX][VEC], const T (&oldv)[RMAX][VEC], int rr) {
+    auto emit_node = [&](T* dst, const T (&val)[RMAX][VEC], const T (&oldv)[RMAX][VEC], const bool (&upd)[VEC], int rr) {
         T s[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) s[v] = T(0);
@@ -227,323 +227,214 @@ __device__ __forceinline__ void process_node(const SweepArgs<T>& a, const NodeMe
             }
     };
 
-    // ---- time-t pi_X and lambda_X ----------------------------------------------------------------
-    T* const pX = pl + (size_t)nd.pl_off * TBC;                 // global destinations (in place)
-    T* const lX = pX + (size_t)r * TBC;
-    const T* const spX = src.pl + (size_t)(nd.pl_off - src.pl_row0) * TBC;
-    const T* const slX = spX + (size_t)r * TBC;
-    T pi[RMAX][VEC];
-    ParentCtx<T, VEC, RMAX> pc;
-#pragma unroll
-    for (int x = 0; x < RMAX; ++x) {
-        if (x < r) {
-            const Pk<T, VEC> p = ldp<T, VEC>(spX + x * TBC);
-            const Pk<T, VEC> l = ldp<T, VEC>(slX + x * TBC);
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) { pi[x][v] = p.v[v]; pc.lam[x][v] = l.v[v]; }
-        } else {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) { pi[x][v] = T(0); pc.lam[x][v] = T(0); }
-        }
-    }
+    const int n0 = a.chunk_off[chunk], n1 = a.chunk_off[chunk + 1];
+    Pk<uint32_t, VEC> evw;
+    int evw_idx = -1;
 
-    // ---- child side: lambda_X (:220-238) and pi-messages X->children (:202-218) -----------------
-    {
-        const T* const Lb = src.lm + (size_t)(nd.lin_off - src.lm_row0) * TBC;
-        const int32_t* const outs = a.c_pi_out + nd.c0;
-        T ln[RMAX][VEC];
-        if (m == 0) {
+    for (int X = n0; X < n1; ++X) {
+        const NodeMeta nd = a.nodes[X];
+        const int r = nd.card, k = nd.k, m = nd.m;
+        if ((X >> 5) != evw_idx) { evw_idx = X >> 5; evw = ldp<uint32_t, VEC>(evb + (size_t)evw_idx * TBC); }
+        bool upd[VEC];                                  // may pi_X / lambda_X be rewritten?
 #pragma unroll
-            for (int x = 0; x < RMAX; ++x)
+        for (int v = 0; v < VEC; ++v) upd[v] = act[v] && !((evw.v[v] >> (X & 31)) & 1u);
+
+        // ---- time-t pi_X and lambda_X ------------------------------------------------------------
+        T* const pX = pl + (size_t)nd.pl_off * TBC;
+        T* const lX = pX + (size_t)r * TBC;
+        T pi[RMAX][VEC];
+        ParentCtx<T, VEC, RMAX> pc;
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
-        } else if (m == 1) {
+        for (int x = 0; x < RMAX; ++x) {
+            if (x < r) {
+                const Pk<T, VEC> p = ldp<T, VEC>(pX + x * TBC);
+                const Pk<T, VEC> l = ldp<T, VEC>(lX + x * TBC);
 #pragma unroll
-            for (int x = 0; x < RMAX; ++x) {
-                if (x < r) {
-                    const Pk<T, VEC> L = ldp<T, VEC>(Lb + x * TBC);
+                for (int v = 0; v < VEC; ++v) { pi[x][v] = p.v[v]; pc.lam[x][v] = l.v[v]; }
+            } else {
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) ln[x][v] = L.v[v];
-                }
+                for (int v = 0; v < VEC; ++v) { pi[x][v] = T(0); pc.lam[x][v] = T(0); }
             }
-            emit_msg(outs[0], pi, r);                       // no other child: N(pi_X)
-        } else if (m == 2) {
-            T L1[RMAX][VEC], pv[RMAX][VEC];
-            const T* const Lb1 = Lb + (size_t)r * TBC;
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x) {
-                if (x < r) {
-                    const Pk<T, VEC> A = ldp<T, VEC>(Lb + x * TBC);
-                    const Pk<T, VEC> B = ldp<T, VEC>(Lb1 + x * TBC);
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) { ln[x][v] = A.v[v]; L1[x][v] = B.v[v]; }
-                } else {
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) { ln[x][v] = T(0); L1[x][v] = T(0); }
-                }
-            }
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v] * L1[x][v];
-            emit_msg(outs[0], pv, r);
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) { pv[x][v] = pi[x][v] * ln[x][v]; ln[x][v] *= L1[x][v]; }
-            emit_msg(outs[1], pv, r);
-        } else {
-#pragma unroll
-            for (int x = 0; x < RMAX; ++x)
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
-            for (int c = 0; c < m; ++c) {
-                const T* const Lc = Lb + (size_t)(c * r) * TBC;
-#pragma unroll
-                for (int x = 0; x < RMAX; ++x) {
-                    if (x < r) {
-                        const Pk<T, VEC> L = ldp<T, VEC>(Lc + x * TBC);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) ln[x][v] *= L.v[v];
-                    }
-                }
-            }
-            for (int c = 0; c < m; ++c) {
-                T pv[RMAX][VEC];
+        }
+
+        // ---- child side: lambda_X (:220-238) and pi-messages X->children (:202-218) -------------
+        {
+            const T* const Lb = cur + (size_t)nd.lin_off * TBC;
+            const int32_t* const outs = a.c_pi_out + nd.c0;
+            T ln[RMAX][VEC];
+            if (m == 0) {
 #pragma unroll
                 for (int x = 0; x < RMAX; ++x)
 #pragma unroll
-                    for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v];
-                for (int c2 = 0; c2 < m; ++c2) {
-                    if (c2 == c) continue;
-                    const T* const Lc = Lb + (size_t)(c2 * r) * TBC;
+                    for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
+            } else if (m == 1) {
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x) {
+                    if (x < r) {
+                        const Pk<T, VEC> L = ldp<T, VEC>(Lb + x * TBC);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) ln[x][v] = L.v[v];
+                    }
+                }
+                emit_msg(outs[0], pi, r);                       // no other child: N(pi_X)
+            } else if (m == 2) {
+                T L1[RMAX][VEC], pv[RMAX][VEC];
+                const T* const Lb1 = Lb + (size_t)r * TBC;
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x) {
+                    if (x < r) {
+                        const Pk<T, VEC> A = ldp<T, VEC>(Lb + x * TBC);
+                        const Pk<T, VEC> B = ldp<T, VEC>(Lb1 + x * TBC);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { ln[x][v] = A.v[v]; L1[x][v] = B.v[v]; }
+                    } else {
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) { ln[x][v] = T(0); L1[x][v] = T(0); }
+                    }
+                }
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v] * L1[x][v];
+                emit_msg(outs[0], pv, r);
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) { pv[x][v] = pi[x][v] * ln[x][v]; ln[x][v] *= L1[x][v]; }
+                emit_msg(outs[1], pv, r);
+            } else {
+#pragma unroll
+                for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) ln[x][v] = T(1);
+                for (int c = 0; c < m; ++c) {
+                    const T* const Lc = Lb + (size_t)(c * r) * TBC;
 #pragma unroll
                     for (int x = 0; x < RMAX; ++x) {
                         if (x < r) {
                             const Pk<T, VEC> L = ldp<T, VEC>(Lc + x * TBC);
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) pv[x][v] *= L.v[v];
+                            for (int v = 0; v < VEC; ++v) ln[x][v] *= L.v[v];
                         }
                     }
                 }
-                emit_msg(outs[c], pv, r);
+                for (int c = 0; c < m; ++c) {
+                    T pv[RMAX][VEC];
+#pragma unroll
+                    for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) pv[x][v] = pi[x][v];
+                    for (int c2 = 0; c2 < m; ++c2) {
+                        if (c2 == c) continue;
+                        const T* const Lc = Lb + (size_t)(c2 * r) * TBC;
+#pragma unroll
+                        for (int x = 0; x < RMAX; ++x) {
+                            if (x < r) {
+                                const Pk<T, VEC> L = ldp<T, VEC>(Lc + x * TBC);
+#pragma unroll
+                                for (int v = 0; v < VEC; ++v) pv[x][v] *= L.v[v];
+                            }
+                        }
+                    }
+                    emit_msg(outs[c], pv, r);
+                }
             }
+            emit_node(lX, ln, pc.lam, upd, r);
         }
-        emit_node(lX, ln, pc.lam, r);
-    }
 
-    // ---- parent side: pi_X (:174-200) and lambda-messages X->parents (:240-266) -------------------
-    pc.cpt = a.cpt + nd.cpt_off;
-    pc.r = r;
-    pc.scr = scr;
-#pragma unroll
-    for (int x = 0; x < RMAX; ++x)
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) { pc.pacc[x][v] = T(0); pc.lacck[x][v] = T(0); pc.mk[x][v] = T(0); }
-    if (k == 0) {
-        // root: all_combination_pattern calls the body once with the empty condition (:280-283)
+        // ---- parent side: pi_X (:174-200) and lambda-messages X->parents (:240-266) ---------------
+        pc.cpt = a.cpt + nd.cpt_off;
+        pc.r = r;
+        pc.scr = scr;
 #pragma unroll
         for (int x = 0; x < RMAX; ++x)
-            if (x < r) {
-                const T p = __ldg(pc.cpt + x);
 #pragma unroll
-                for (int v = 0; v < VEC; ++v) pc.pacc[x][v] = p;
-            }
-    } else {
-        const int32_t* const ecard = a.e_card + nd.e0;
-        const int32_t* const louts = a.e_lam_out + nd.e0;
-        // stage the outer parents' messages in scratch, the last parent's in registers
-        int so = 0;
-        const T* mp = src.pm + (size_t)(nd.pin_off - src.pm_row0) * TBC;
-        if (k > 1) {
+            for (int v = 0; v < VEC; ++v) { pc.pacc[x][v] = T(0); pc.lacck[x][v] = T(0); pc.mk[x][v] = T(0); }
+        if (k == 0) {
+            // root: all_combination_pattern calls the body once with the empty condition (:280-283)
 #pragma unroll
-            for (int j = 0; j < KNET - 1; ++j) {
-                if (j < k - 1) {
-                    const int rjj = ecard[j];
-                    pc.rj[j] = rjj;
-                    pc.soff[j] = so;
-                    for (int u = 0; u < rjj; ++u) {
-                        const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
+            for (int x = 0; x < RMAX; ++x)
+                if (x < r) {
+                    const T p = __ldg(pc.cpt + x);
 #pragma unroll
-                        for (int v = 0; v < VEC; ++v) {
-                            scr[((so + u) * VEC + v) * BLOCK] = mm.v[v];
-                            scr[((nd.scr_half + so + u) * VEC + v) * BLOCK] = T(0);
+                    for (int v = 0; v < VEC; ++v) pc.pacc[x][v] = p;
+                }
+        } else {
+            const int32_t* const ecard = a.e_card + nd.e0;
+            const int32_t* const louts = a.e_lam_out + nd.e0;
+            // stage the outer parents' messages in scratch, the last parent's in registers
+            int so = 0, slot = nd.pin_off;
+            if (k > 1) {
+#pragma unroll
+                for (int j = 0; j < KNET - 1; ++j) {
+                    if (j < k - 1) {
+                        const int rjj = ecard[j];
+                        pc.rj[j] = rjj;
+                        pc.soff[j] = so;
+                        const T* const mp = cur + (size_t)slot * TBC;
+                        for (int u = 0; u < rjj; ++u) {
+                            const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) {
+                                scr[((so + u) * VEC + v) * BLOCK] = mm.v[v];
+                                scr[((nd.scr_half + so + u) * VEC + v) * BLOCK] = T(0);
+                            }
                         }
+                        so += rjj;
+                        slot += rjj;
                     }
-                    so += rjj;
-                    mp += (size_t)rjj * TBC;
                 }
             }
-        }
-        pc.sacc_base = nd.scr_half;
-        const int rk = ecard[k - 1];
-        pc.rk = rk;
-#pragma unroll
-        for (int u = 0; u < RMAX; ++u)
-            if (u < rk) {
-                const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
-            }
-        if (k == 1) parent_run<1, T, VEC, RMAX>(pc);
-        else if (k == 2) parent_run<2, T, VEC, RMAX>(pc);
-        else if constexpr (KNET > 2) {
-            if (k == 3) parent_run<3, T, VEC, RMAX>(pc);
-            else if (k == 4) parent_run<4, T, VEC, RMAX>(pc);
-            else if constexpr (KNET > 4) {
-                if (k == 5) parent_run<5, T, VEC, RMAX>(pc);
-                else if (k == 6) parent_run<6, T, VEC, RMAX>(pc);
-                else if (k == 7) parent_run<7, T, VEC, RMAX>(pc);
-                else parent_run<8, T, VEC, RMAX>(pc);
-            }
-        }
-        // lambda-messages to the outer parents (accumulated in scratch) ...
-        int so2 = 0;
-        for (int j = 0; j < k - 1; ++j) {
-            const int rjj = ecard[j];
-            T val[RMAX][VEC];
-            if constexpr (RMAX <= 8) {
+            pc.sacc_base = nd.scr_half;
+            const int rk = ecard[k - 1];
+            pc.rk = rk;
+            {
+                const T* const mp = cur + (size_t)slot * TBC;
 #pragma unroll
                 for (int u = 0; u < RMAX; ++u)
-                    if (u < rjj) {
+                    if (u < rk) {
+                        const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
+#pragma unroll
+                        for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
+                    }
+            }
+            if (k == 1) parent_run<1, T, VEC, RMAX>(pc);
+            else if (k == 2) parent_run<2, T, VEC, RMAX>(pc);
+            else if constexpr (KNET > 2) {
+                if (k == 3) parent_run<3, T, VEC, RMAX>(pc);
+                else if (k == 4) parent_run<4, T, VEC, RMAX>(pc);
+                else if constexpr (KNET > 4) {
+                    if (k == 5) parent_run<5, T, VEC, RMAX>(pc);
+                    else if (k == 6) parent_run<6, T, VEC, RMAX>(pc);
+                    else if (k == 7) parent_run<7, T, VEC, RMAX>(pc);
+                    else parent_run<8, T, VEC, RMAX>(pc);
+                }
+            }
+            // lambda-messages to the outer parents (accumulated in scratch) ...
+            int so2 = 0;
+            for (int j = 0; j < k - 1; ++j) {
+                const int rjj = ecard[j];
+                T val[RMAX][VEC];
+                if constexpr (RMAX <= 8) {
+#pragma unroll
+                    for (int u = 0; u < RMAX; ++u)
+                        if (u < rjj) {
+#pragma unroll
+                            for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
+                        }
+                } else {
+                    for (int u = 0; u < rjj; ++u)
 #pragma unroll
                         for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
-                    }
-            } else {
-                for (int u = 0; u < rjj; ++u)
-#pragma unroll
-                    for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
+                }
+                emit_msg(louts[j], val, rjj);
+                so2 += rjj;
             }
-            emit_msg(louts[j], val, rjj);
-            so2 += rjj;
+            // ... and to the last parent (accumulated in registers)
+            emit_msg(louts[k - 1], pc.lacck, rk);
         }
-        // ... and to the last parent (accumulated in registers)
-        emit_msg(louts[k - 1], pc.lacck, rk);
-    }
-    // pi_X = normalize(acc) unless X is evidence (:177) or the case is frozen
-    emit_node(pX, pc.pacc, pi, r);
-}
-
-// ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int RMAX, int KNET, bool FREEZE, bool CHECK>
-__global__ void __launch_bounds__(BLOCK, BNBP_MINB)
-sweep_kernel(const SweepArgs<T> a)
-{
-    extern __shared__ __align__(128) unsigned char smem_raw[];
-    constexpr size_t TBC = (size_t)BLOCK * VEC;        // cases per tile = slot stride
-    constexpr size_t ROWB = TBC * sizeof(T);           // bytes of one slot row of a tile
-    const int tid = threadIdx.x;
-    const int tile = blockIdx.x;
-    const int chunk = blockIdx.y;
-    const int lane0 = tid * VEC;                       // first case (within the tile) of this thread
-    const size_t case0 = (size_t)tile * TBC + lane0;   // index into per-case arrays
-
-    // shared memory: [mbarriers | NST stage buffers of stage_rows rows | recursion scratch]
-    uint64_t* const bars = reinterpret_cast<uint64_t*>(smem_raw);
-    unsigned char* const stage0 = smem_raw + 128;
-    const int NST = a.n_stage_bufs;
-    const size_t stage_bytes = (size_t)a.stage_rows * ROWB;
-    T* const scr = reinterpret_cast<T*>(stage0 + (size_t)NST * stage_bytes) + tid;
-
-    bool act[VEC];
-    bool any = true;
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) act[v] = true;
-    if constexpr (FREEZE) {
-        // device-side loop termination: once a sweep found no active case, later (speculatively
-        // enqueued) launches return at once -- no host round-trip per sweep.
-        if (a.sweep_index > 0 && *reinterpret_cast<volatile int32_t*>(a.last_active) < a.sweep_index - 1) return;
-        // a case that met delta < eps at the previous (tested) sweep is frozen from now on: the
-        // reference breaks right after the commit (:135-147), so its state is final.
-        any = false;
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) {
-            bool frozen = a.status[case0 + v] != 0;
-            if (!frozen && a.prev_tested && a.delta_prev[case0 + v] < a.eps) {
-                frozen = true;
-                if (chunk == 0) { a.status[case0 + v] = 1; a.sweeps[case0 + v] = a.sweep_index; }
-            }
-            act[v] = !frozen;
-            any |= act[v];
-        }
-        if (chunk == 0) {
-#pragma unroll
-            for (int v = 0; v < VEC; ++v) a.delta_next[case0 + v] = Lim<T>::floor_();
-        }
-        // the whole tile is frozen: the block leaves together (no barrier is pending yet)
-        if (!__syncthreads_or(any ? 1 : 0)) return;
-        if (chunk == 0 && tid == 0) *a.last_active = a.sweep_index;   // benign race: same value
-    }
-
-    T* const pl_tile = a.pl + ((size_t)tile * a.PL) * TBC;
-    const T* const cur_tile = a.msg_cur + ((size_t)tile * a.M) * TBC;
-    T* const pl = pl_tile + lane0;
-    const T* const cur = cur_tile + lane0;
-    T* const nxt = a.msg_nxt + ((size_t)tile * a.M) * TBC + lane0;
-    const uint32_t* const evb = a.evbits + ((size_t)tile * a.W) * TBC + lane0;
-
-    const int s0 = a.chunk_off[chunk], s1 = a.chunk_off[chunk + 1];
-
-    // one elected thread feeds the pipeline
-    auto issue = [&](int s) {
-        const StageMeta st = a.stages[s];
-        if (!st.staged) return;
-        const int b = (s - s0) % NST;
-        unsigned char* buf = stage0 + (size_t)b * stage_bytes;
-        const uint32_t bytes = (uint32_t)((st.pl_rows + st.pm_rows + st.lm_rows) * ROWB);
-        mbar_expect_tx(&bars[b], bytes);
-        if (st.pl_rows) bulk_g2s(buf, pl_tile + (size_t)st.pl_row0 * TBC, (uint32_t)(st.pl_rows * ROWB), &bars[b]);
-        buf += (size_t)st.pl_rows * ROWB;
-        if (st.pm_rows) bulk_g2s(buf, cur_tile + (size_t)st.pm_row0 * TBC, (uint32_t)(st.pm_rows * ROWB), &bars[b]);
-        buf += (size_t)st.pm_rows * ROWB;
-        if (st.lm_rows) bulk_g2s(buf, cur_tile + (size_t)st.lm_row0 * TBC, (uint32_t)(st.lm_rows * ROWB), &bars[b]);
-    };
-    if (tid == 0) {
-        for (int b = 0; b < NST; ++b) mbar_init(&bars[b], 1);
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        for (int s = s0; s < s1 && s < s0 + NST; ++s) issue(s);
-    }
-    __syncthreads();
-
-    T dmax[VEC];
-#pragma unroll
-    for (int v = 0; v < VEC; ++v) dmax[v] = Lim<T>::floor_();
-    Pk<uint32_t, VEC> evw;
-    int evw_idx = -1;
-    uint32_t phases = 0;                               // bit b = parity of the next fill of buffer b
-
-    for (int s = s0; s < s1; ++s) {
-        const StageMeta st = a.stages[s];
-        const int b = (s - s0) % NST;
-        NodeSrc<T> src;
-        if (st.staged) {
-            // (unstaged stages never arm their barrier, so the parity is counted per actual fill)
-            mbar_wait(&bars[b], (phases >> b) & 1u);
-            phases ^= 1u << b;
-            const T* buf = reinterpret_cast<const T*>(stage0 + (size_t)b * stage_bytes) + lane0;
-            src.pl = buf;                                       src.pl_row0 = st.pl_row0;
-            src.pm = buf + (size_t)st.pl_rows * TBC;            src.pm_row0 = st.pm_row0;
-            src.lm = src.pm + (size_t)st.pm_rows * TBC;         src.lm_row0 = st.lm_row0;
-        } else {
-            // a node whose read set exceeds a stage buffer (hub with many children): plain loads
-            src.pl = pl;  src.pl_row0 = 0;
-            src.pm = cur; src.pm_row0 = 0;
-            src.lm = cur; src.lm_row0 = 0;
-        }
-        if (any) {
-            for (int X = st.g0; X < st.g1; ++X) {
-                const NodeMeta nd = a.nodes[X];
-                if ((X >> 5) != evw_idx) { evw_idx = X >> 5; evw = ldp<uint32_t, VEC>(evb + (size_t)evw_idx * TBC); }
-                bool upd[VEC];                                  // may pi_X / lambda_X be rewritten?
-#pragma unroll
-                for (int v = 0; v < VEC; ++v) upd[v] = act[v] && !((evw.v[v] >> (X & 31)) & 1u);
-                process_node<T, VEC, RMAX, KNET, CHECK>(a, nd, src, pl, cur, nxt, scr, upd, dmax);
-            }
-        }
-        // everyone is done reading buffer b: refill it with stage s + NST
-        __syncthreads();
-        if (tid == 0 && s + NST < s1) issue(s + NST);
+        // pi_X = normalize(acc) unless X is evidence (:177) or the case is frozen
+        emit_node(pX, pc.pacc, pi, upd, r);
     }
 
     if constexpr (CHECK) {

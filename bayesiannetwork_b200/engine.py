@@ -16,6 +16,31 @@ from ._capi import BnbpError  # noqa: F401
 from .flat import EvidenceBatch, FlatNetwork
 
 FP64, FP32 = 0, 1
+SPECIALIZE = {"auto": 0, "always": 1, "never": 2}
+
+
+def _net_c(net: FlatNetwork):
+    return _capi.FlatNetworkC(net.n_nodes, _vp(net.card), _vp(net.parent_off), _vp(net.parents),
+                              _vp(net.cpt_off), _vp(net.cpt))
+
+
+def precompile(net: FlatNetwork, precision: str = "fp64", variants: int = 0b111) -> None:
+    """Run the network compiler without a GPU: generate the specialised sweep kernels of ``net``
+    and leave their cubins in the cache (``bnbp_precompile``)."""
+    lib = _capi.load()
+    opt = _capi.OptionsC({"fp64": FP64, "fp32": FP32}[precision], -1, 0, 0)
+    _capi.check(lib.bnbp_precompile(C.byref(_net_c(net)), C.byref(opt), variants))
+
+
+def spec_source(net: FlatNetwork, precision: str = "fp64", variant: int = 0) -> str:
+    """CUDA source the network compiler generates for ``net`` (``bnbp_spec_source``)."""
+    lib = _capi.load()
+    opt = _capi.OptionsC({"fp64": FP64, "fp32": FP32}[precision], -1, 0, 0)
+    need = C.c_int64(0)
+    _capi.check(lib.bnbp_spec_source(C.byref(_net_c(net)), C.byref(opt), variant, None, 0, C.byref(need)))
+    buf = C.create_string_buffer(need.value)
+    _capi.check(lib.bnbp_spec_source(C.byref(_net_c(net)), C.byref(opt), variant, buf, need.value, C.byref(need)))
+    return buf.value.decode()
 
 
 @dataclass
@@ -38,15 +63,14 @@ class BeliefPropagation:
     (belief_propagation.hpp:24,31) with a batch in place of one evidence map."""
 
     def __init__(self, net: FlatNetwork, precision: str = "fp64", device: int = -1,
-                 max_resident_cases: int = 0):
+                 max_resident_cases: int = 0, specialize: str = "auto"):
         self.net = net
         self.precision = {"fp64": FP64, "fp32": FP32, "f64": FP64, "f32": FP32}[precision]
         lib = _capi.load()
         self._lib = lib
         self._h = C.c_void_p()
-        fn = _capi.FlatNetworkC(net.n_nodes, _vp(net.card), _vp(net.parent_off), _vp(net.parents),
-                                _vp(net.cpt_off), _vp(net.cpt))
-        opt = _capi.OptionsC(self.precision, device, max_resident_cases)
+        fn = _net_c(net)
+        opt = _capi.OptionsC(self.precision, device, max_resident_cases, SPECIALIZE[specialize])
         _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
 
     def close(self):

@@ -194,6 +194,8 @@ def main():
     ap.add_argument("--cases", type=int, default=0, help="cases per GPU (default: the workload's)")
     ap.add_argument("--sweeps", type=int, default=0, help="fixed sweeps per step (default: the workload's)")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
+    ap.add_argument("--specialize", default="auto", choices=["auto", "always", "never"],
+                    help="sweep-kernel family: network-specialised (NVRTC) or generic")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -226,7 +228,7 @@ def main():
     n, V = ev.n_cases, net.belief_values
     tdtype = torch.float64 if args.precision == "fp64" else torch.float32
     tsize = 8 if args.precision == "fp64" else 4
-    bp = BeliefPropagation(net, args.precision, device=local_rank)
+    bp = BeliefPropagation(net, args.precision, device=local_rank, specialize=args.specialize)
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
@@ -294,7 +296,8 @@ def main():
         except Exception:
             traffic = None
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "sweep_kernel", "peak_source": peak_src,
+                "traffic": traffic, "kernel": "bnbp_spec_sweep" if st["last_specialised"] else "sweep_kernel",
+                "peak_source": peak_src,
                 "algorithmic_bytes_per_case_sweep": 2 * S * tsize, "ms_per_launch": sweep_ms_per_launch}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory both ways) ----------------------
@@ -347,6 +350,8 @@ def main():
                        "max_card": int(net.card.max()), "cases_per_gpu": n, "sweeps": sweeps,
                        "state_values_per_case": S, "schedule": "synchronous, fixed sweeps, no damping",
                        "sharding": f"cases x{world}", "gather": bool(gathered is not None),
+                       "kernel_family": "network-specialised (NVRTC sm_100a)" if st["last_specialised"] else "generic",
+                       "cases_per_tile": int(st["cases_per_tile"]),
                        "l2": f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
                              f"of per-case state per GPU vs 126 MB"},
             "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,

@@ -16,6 +16,9 @@
  *   bnbp_run_batch_device  same, evidence / marginals already resident in device memory
  *   bnbp_destroy       <- belief_propagation::~belief_propagation()   :21
  *   bnbp_last_error    <- (the reference has no error channel; UB / NaN / endless loop)
+ *   bnbp_refresh_cpt   <- the reference reads vertex_t::cpt at call time (graph.hpp:157-161), so
+ *                         CPT edits between calls are visible; here they need this call
+ *   bnbp_precompile / bnbp_spec_source  (new: the network compiler, see BNBP_SPEC_* below)
  *
  * Semantics reproduced exactly (belief_propagation.hpp:75-148): synchronous (Jacobi)
  * schedule, no damping unless asked, evidence vector written into both pi and lambda of the
@@ -45,6 +48,14 @@ enum {
 
 enum { BNBP_FP64 = 0, BNBP_FP32 = 1 };
 
+/* Sweep-kernel family.  The reference walks hash maps on every sweep; libbnbp has two GPU kernels:
+ * a generic one that interprets the flat network (any network), and one COMPILED FOR THE NETWORK
+ * at run time (NVRTC, sm_100a; cubins cached on disk) in which cardinalities, slot offsets and the
+ * CPT arena are compile-time constants.  AUTO specialises eligible networks (small enough to
+ * unroll, CPT arena <= 60 KB of constant bank) once a batch has >= 4096 cases.  Both are GPU
+ * paths with identical semantics; neither is a CPU fallback. */
+enum { BNBP_SPEC_AUTO = 0, BNBP_SPEC_ALWAYS = 1, BNBP_SPEC_NEVER = 2 };
+
 /* Flat (CSR) description of a discrete Bayesian network.
  *   node i      = i-th entry of graph_t::vertex_list()                (graph.hpp:214)
  *   card[i]     = vertex_t::selectable_num                            (graph.hpp:159)
@@ -66,7 +77,8 @@ typedef struct bnbp_options {
     int32_t precision;          /* BNBP_FP64 (default, the reference's arithmetic) or BNBP_FP32 */
     int32_t device;             /* CUDA device ordinal; -1 = current device                     */
     int64_t max_resident_cases; /* cases kept in HBM at once (0 = pick from free memory)         */
-    int32_t reserved[8];
+    int32_t specialize;         /* BNBP_SPEC_AUTO (default) / ALWAYS (error if impossible) / NEVER */
+    int32_t reserved[7];
 } bnbp_options;
 
 /* Evidence for a batch, CSR over cases.  Entry e of case c (ev_off[c] <= e < ev_off[c+1])
@@ -106,7 +118,10 @@ typedef struct bnbp_stats {
     double  last_sweep_ms;           /* device time of the sweep launches (CUDA events)         */
     double  last_total_ms;           /* device time init..beliefs of the last run               */
     int64_t resident_cases;          /* cases per HBM-resident chunk                            */
-    int64_t reserved[8];
+    int64_t last_specialised;        /* 1 if the last run used the network-specialised sweep kernel */
+    int64_t cases_per_tile;          /* 128 x cases per thread of the kernel family of the last run */
+    double  spec_compile_ms;         /* NVRTC time spent by this handle (0 when served by the cache) */
+    int64_t reserved[5];
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;
@@ -136,6 +151,18 @@ int  bnbp_get_stats(const bnbp_handle* h, bnbp_stats* out);
 
 /* Re-upload CPT values after the host network changed them (topology must be unchanged). */
 int  bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values);
+
+/* Network compiler without a GPU (build machines, tests): generate the specialised sweep kernel of
+ * `net` for opt->precision and compile it into the cubin cache ($BNBP_CACHE_DIR, default
+ * <dir of libbnbp.so>/jitcache), so that bnbp_create/run on the GPU box finds it there.
+ * variant_mask: bit 0 plain (fixed sweeps), bit 1 freeze, bit 2 freeze+check (epsilon mode, damping).
+ * Returns BNBP_ERR_INVALID with the reason if the network is not eligible. */
+int  bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant_mask);
+
+/* The generated CUDA source of one variant (0, 1, 2), for inspection and tests.  Writes at most
+ * cap bytes including the terminating NUL and returns the full length via *needed. */
+int  bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant,
+                      char* buf, int64_t cap, int64_t* needed);
 
 #ifdef __cplusplus
 }

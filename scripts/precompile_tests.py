@@ -1,0 +1,42 @@
+"""Fill the in-tree cubin cache with the specialised kernels the GPU tests will ask for, so the
+GPU box spends its minutes on running them (NVRTC works without a GPU).  Purely an optimisation:
+a missing cache entry is compiled on the box on first use."""
+import os
+import sys
+from concurrent.futures import ProcessPoolExecutor
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, ROOT)
+sys.path.insert(0, os.path.join(ROOT, "tests"))
+
+
+def jobs():
+    import numpy as np
+    import test_gpu_spec as t
+    from helpers import load_fixture
+    out = []
+    for name, net, evkw, eps, cap in t._cases():
+        for prec in ("fp64", "fp32"):
+            if prec == "fp32" and eps > 0:
+                continue
+            out.append((net, prec, 0b100 if eps > 0 else 0b001))
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz"), allow_pickle=False)
+    for name in ["pearl_tests", "pearl_nan_fixed6", "resume_tests"]:
+        f = load_fixture(fx, name)
+        out.append((f["net"], "fp64", 0b101))
+    from bayesiannetwork_b200 import synth
+    out.append((synth.grid(5, seed=8), "fp64", 0b111))
+    return out
+
+
+def one(job):
+    from bayesiannetwork_b200 import engine
+    net, prec, mask = job
+    engine.precompile(net, prec, mask)
+    return net.name, prec, mask
+
+
+if __name__ == "__main__":
+    with ProcessPoolExecutor(8) as ex:
+        for r in ex.map(one, jobs()):
+            print(r, flush=True)

@@ -1,0 +1,99 @@
+"""Parity of the NETWORK-SPECIALISED sweep kernels (bnbp_spec.cuh, compiled by NVRTC on the box)
+with the oracle and with the generic kernel -- needs a B200 (-m gpu).
+
+Same bar as test_gpu_parity.py: fp64 1e-9 / 1e-12 with equal sweep counts in eps mode, fp32
+1e-5 / 1e-7 at fixed sweep counts.  ``specialize="always"`` makes a missing / failing network
+compiler an error instead of a silent switch to the generic kernel."""
+import numpy as np
+import pytest
+
+from bayesiannetwork_b200 import synth
+from bayesiannetwork_b200.flat import EvidenceBatch
+from helpers import assert_close, load_fixture
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp64": dict(rtol=1e-9, atol=1e-12), "fp32": dict(rtol=1e-5, atol=1e-7)}
+
+
+@pytest.fixture(scope="module")
+def BP():
+    from bayesiannetwork_b200.engine import BeliefPropagation
+    return BeliefPropagation
+
+
+def _hub():
+    card = [3] + [2 + (i % 3) for i in range(12)] + [2, 4]
+    parents = [[]] + [[0] for _ in range(12)] + [[], [5, 9]]
+    return synth._assemble(card, parents, 77, "hub12")
+
+
+def _cases():
+    yield "alarm37_eps", synth.alarm37(), dict(exact_k=4), 1e-6, 200
+    yield "alarm37_fixed", synth.alarm37(), dict(exact_k=4), 0.0, 20
+    yield "alarm37_soft", synth.alarm37(), dict(exact_k=4, soft=True), 0.0, 15
+    yield "polytree40", synth.random_polytree(40, card_hi=4, seed=21), dict(p=0.15), 1e-8, 300
+    yield "grid6_loopy", synth.grid(6, seed=4), dict(p=0.1), 1e-7, 400
+    yield "dag45_k4", synth.random_dag(45, 4, 2, 3, seed=7), dict(p=0.1), 0.0, 12
+    yield "hub12_isolated", _hub(), dict(p=0.3), 1e-9, 200
+
+
+@pytest.mark.parametrize("name,net,evkw,eps,cap", list(_cases()), ids=[c[0] for c in _cases()])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_specialised_vs_oracle(BP, oracle_mod, name, net, evkw, eps, cap, precision):
+    if precision == "fp32" and eps > 0:
+        pytest.skip("fp32 parity is asserted at fixed sweep counts")
+    ev = synth.make_evidence(net, 777, seed=17, **evkw)          # ragged: not a multiple of any tile
+    om, osw, ocv = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap, threads=0)
+    bp = BP(net, precision, specialize="always")
+    res = bp(ev, eps, max_sweeps=cap)
+    assert bp.stats()["last_specialised"] == 1
+    assert np.array_equal(res.sweeps, osw), (name, np.nonzero(res.sweeps != osw)[0][:5])
+    assert np.array_equal(res.converged, ocv), name
+    assert_close(res.marginals, om, what=name, **TOL[precision])
+
+
+@pytest.mark.parametrize("name", ["pearl_tests", "pearl_nan", "pearl_nan_fixed6", "resume_tests", "resume_soft"])
+def test_specialised_reference_fixtures(BP, ref_fixtures, name):
+    """The reference's own graphs incl. the impossible-evidence (NaN) case, from reference output."""
+    f = load_fixture(ref_fixtures, name)
+    bp = BP(f["net"], "fp64", specialize="always")
+    res = bp(f["ev"], f["eps"], max_sweeps=f["max_sweeps"])
+    assert bp.stats()["last_specialised"] == 1
+    assert np.array_equal(res.sweeps, f["sweeps"]) and np.array_equal(res.converged, f["converged"])
+    assert_close(res.marginals, f["marginals"], what=name, **TOL["fp64"])
+
+
+def test_specialised_extensions_and_refresh(BP, oracle_mod):
+    """damping / check_interval (variants 1 and 2) and bnbp_refresh_cpt into the constant bank."""
+    net = synth.grid(5, seed=8)
+    ev = synth.make_evidence(net, 300, p=0.15, seed=5)
+    bp = BP(net, specialize="always")
+    for kw in (dict(damping=0.25), dict(check_interval=4), dict(damping=0.1, check_interval=3)):
+        om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-8, max_sweeps=500, threads=0, **kw)
+        res = bp(ev, 1e-8, max_sweeps=500, **kw)
+        assert bp.stats()["last_specialised"] == 1
+        assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv), kw
+        assert_close(res.marginals, om, what=str(kw), **TOL["fp64"])
+    net2 = synth.grid(5, seed=9)                                  # same topology, other CPTs
+    bp.refresh_cpt(net2.cpt)
+    om, _, _ = oracle_mod.run_port(net2, ev, eps=0.0, max_sweeps=9)
+    assert_close(bp(ev, 0.0, max_sweeps=9).marginals, om, what="refresh", **TOL["fp64"])
+
+
+def test_specialised_equals_generic_bitwise_shape(BP):
+    """Both kernel families implement the same schedule: fixed sweeps, same sweep counts, results
+    within a few ulp of each other (they differ only in the order of some products)."""
+    net = synth.alarm37()
+    ev = synth.make_evidence(net, 5000, exact_k=4)
+    a = BP(net, specialize="always")(ev, 0.0, max_sweeps=20)
+    b = BP(net, specialize="never")(ev, 0.0, max_sweeps=20)
+    assert_close(a.marginals, b.marginals, rtol=1e-12, atol=1e-15, what="spec vs generic")
+
+
+def test_ineligible_network_is_refused_when_forced(BP):
+    from bayesiannetwork_b200.engine import BnbpError
+    net = synth.high_card(6, card=32, n_parents=2, seed=10)       # cardinality 32: not specialisable
+    bp = BP(net, specialize="always")
+    with pytest.raises(BnbpError):
+        bp(EvidenceBatch.empty(4), 0.0, max_sweeps=2)
+    assert BP(net, specialize="auto")(EvidenceBatch.empty(4), 0.0, max_sweeps=2).marginals.shape[0] == 4

@@ -1,0 +1,59 @@
+"""Host logic of the network compiler (bnbp_jit.cu): runs WITHOUT a GPU -- source generation and
+the NVRTC compile to an sm_100a cubin are pure host work; no kernel is launched here."""
+import os
+import re
+import subprocess
+
+import pytest
+
+from bayesiannetwork_b200 import synth
+
+
+@pytest.fixture(scope="module")
+def engine():
+    from bayesiannetwork_b200 import _build, engine
+    _build.build()
+    return engine
+
+
+def test_generated_source_describes_the_network(engine):
+    net = synth.pearl_network()
+    src = engine.spec_source(net, "fp64", 2)
+    assert "#define BNBP_T double" in src and "#define BNBP_VARIANT 2" in src
+    assert "#define BNBP_NCPT 16" in src
+    assert len(re.findall(r"^struct N\d+ ", src, flags=re.M)) == 4
+    # H has parents R, S (cards 2, 2) and no children (libs/bayesian/test/belief_propagation.cpp:9-62)
+    n3 = [l for l in src.splitlines() if l.startswith("struct N3 ")][0]
+    assert "R=2,K=2,M=0" in n3 and "RU[2]={2,2}" in n3
+    # software pipeline: every node is declared, loaded and computed exactly once, loads first
+    walk = [l for l in src.splitlines() if l.startswith("#define BNBP_WALK")][0]
+    for i in range(4):
+        assert walk.count(f"BNBP_DECL(N{i})") == 1 and walk.count(f"BNBP_COMP(N{i})") == 1
+        assert walk.index(f"BNBP_LOAD(N{i})") < walk.index(f"BNBP_COMP(N{i})")
+    assert "extern \"C\" __global__" in src                      # the hand-written body follows
+    assert engine.spec_source(net, "fp32", 0).count("#define BNBP_T float") == 1
+
+
+def test_precompile_pearl_into_cache(engine, tmp_path, monkeypatch):
+    """NVRTC -> cubin -> cache file, no GPU involved; the cubin is sm_100a and holds the kernel."""
+    monkeypatch.setenv("BNBP_CACHE_DIR", str(tmp_path))
+    engine.precompile(synth.pearl_network(), "fp64", 0b001)
+    files = [f for f in os.listdir(tmp_path) if f.endswith(".cubin")]
+    assert len(files) == 1
+    engine.precompile(synth.pearl_network(), "fp64", 0b001)      # served by the cache
+    assert len([f for f in os.listdir(tmp_path) if f.endswith(".cubin")]) == 1
+    cuobjdump = "/usr/local/cuda/bin/cuobjdump"
+    if os.path.exists(cuobjdump):
+        out = subprocess.run([cuobjdump, "-elf", str(tmp_path / files[0])], capture_output=True, text=True).stdout
+        assert "bnbp_spec_sweep" in out and "bnbp_cpt" in out
+        sass = subprocess.run([cuobjdump, "-sass", str(tmp_path / files[0])], capture_output=True, text=True).stdout
+        assert "sm_100" in sass
+        assert "c[0x3]" in sass                                   # CPT entries are constant-bank operands
+
+
+def test_ineligible_networks_are_reported(engine):
+    from bayesiannetwork_b200.engine import BnbpError
+    with pytest.raises(BnbpError, match="not eligible"):
+        engine.precompile(synth.high_card(6, card=32, n_parents=2, seed=10), "fp64", 1)
+    with pytest.raises(BnbpError, match="not eligible"):
+        engine.spec_source(synth.grid(40), "fp64", 0)             # 1600 nodes
