@@ -11,6 +11,7 @@
 #include <cmath>
 #include <cstdio>
 #include <cstring>
+#include <map>
 #include <memory>
 #include <string>
 #include <vector>
@@ -94,8 +95,13 @@ struct bnbp_handle {
     // device state for the resident chunk
     int64_t cap = 0;
     DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
-    // staging for the host API
-    DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out, s_out_sweeps, s_out_conv;
+    // staging for the host API (outputs double-buffered: D2H of chunk i overlaps the sweeps of chunk i+1)
+    DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out[2], s_out_sweeps[2], s_out_conv[2];
+    cudaStream_t copy_stream = nullptr;
+    cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    // column groups of the tiled belief kernel, per (tile width, output element size)
+    struct BeliefPlan { DevBuf groups; int n_groups = 0; int stride = 0; size_t smem = 0; bool ok = false; };
+    std::map<int, BeliefPlan> belief_plans;
     int32_t* pinned_poll = nullptr;    // [4]
     cudaStream_t stream = nullptr;
     cudaEvent_t ev_total[2] = {nullptr, nullptr};
@@ -255,6 +261,42 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm)
     return BNBP_OK;
 }
 
+// Column groups for belief_tiled_kernel: consecutive nodes whose marginals fit one shared-memory
+// tile of [tb cases][width] output elements (<= 96 KB, so two blocks share an SM).
+int belief_plan(bnbp_handle* h, int tb, int out_size, bnbp_handle::BeliefPlan** out)
+{
+    const int key = tb * 16 + out_size;
+    bnbp_handle::BeliefPlan& p = h->belief_plans[key];
+    *out = &p;
+    if (p.n_groups) return BNBP_OK;
+    const int width = (int)std::min<size_t>((size_t)h->V, (size_t)(96 * 1024) / ((size_t)tb * out_size) - 1);
+    int maxcard = 1;
+    for (int x = 0; x < h->N; ++x) maxcard = std::max(maxcard, (int)h->nodes[x].card);
+    std::vector<BeliefGroup> groups;
+    if (width >= maxcard) {
+        int x = 0;
+        while (x < h->N) {
+            BeliefGroup g;
+            g.n0 = x; g.j0 = h->nodes[x].bel_off;
+            int w = 0;
+            while (x < h->N && w + h->nodes[x].card <= width) { w += h->nodes[x].card; ++x; }
+            g.n1 = x; g.j1 = g.j0 + w;
+            groups.push_back(g);
+        }
+        p.ok = true;
+    } else {
+        groups.push_back(BeliefGroup{0, 0, 0, 0});      // marker: use the untiled kernel
+        p.ok = false;
+    }
+    p.n_groups = (int)groups.size();
+    p.stride = width | 1;                                // odd row stride: conflict-free phase 1
+    p.smem = (size_t)tb * p.stride * out_size;
+    int rc = p.groups.ensure(groups.size() * sizeof(BeliefGroup));
+    if (rc) return rc;
+    CU_TRY(cudaMemcpy(p.groups.p, groups.data(), groups.size() * sizeof(BeliefGroup), cudaMemcpyHostToDevice));
+    return BNBP_OK;
+}
+
 struct DevEvidence {       // device pointers, offsets absolute with the given bases
     const int64_t* ev_off; int64_t ev_base;
     const int32_t* ev_node; const int32_t* ev_state;
@@ -399,11 +441,25 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         h->last_kernel_launches++;
     }
 
-    belief_kernel<T, OUT><<<tiles, h->tb, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, h->tb,
-                                                h->V, n, d_out, (const uint8_t*)h->d_status.p,
-                                                (const int32_t*)h->d_sweeps.p, d_out_sweeps, d_out_conv);
-    CU_TRY(cudaGetLastError());
-    h->last_kernel_launches++;
+    {
+        bnbp_handle::BeliefPlan* plan = nullptr;
+        int rc = belief_plan(h, h->tb, (int)sizeof(OUT), &plan);
+        if (rc) return rc;
+        if (plan->ok) {
+            if (plan->smem > 48 * 1024)
+                CU_TRY(cudaFuncSetAttribute(belief_tiled_kernel<T, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+            belief_tiled_kernel<T, OUT><<<tiles, h->tb, plan->smem, st>>>(
+                (const NodeMeta*)h->d_nodes.p, (const BeliefGroup*)plan->groups.p, plan->n_groups, (const T*)h->d_pl.p, h->PL,
+                h->tb, h->V, plan->stride, n, d_out, (const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
+                d_out_sweeps, d_out_conv);
+        } else {
+            belief_kernel<T, OUT><<<tiles, h->tb, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, h->tb,
+                                                        h->V, n, d_out, (const uint8_t*)h->d_status.p,
+                                                        (const int32_t*)h->d_sweeps.p, d_out_sweeps, d_out_conv);
+        }
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+    }
     if (planned_sweeps) *planned_sweeps = eps_mode ? -1 : (int64_t)total_sweeps * n;
     return BNBP_OK;
 }
@@ -605,7 +661,10 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     {
         SpecLayout L = spec_layout(h);
         h->spec_eligible_ = spec_eligible(L, h->precision == BNBP_FP32, &h->spec_why);
-        h->spec_vec = h->precision == BNBP_FP32 ? 2 : 1;
+        // measured on B200 (profiles/r01c): one case per thread beats 2/4 in both precisions -- the
+        // kernel is HBM-latency bound, so resident warps (registers per thread) matter more than
+        // wider accesses; fp64 1.147 ms/sweep at (1,3,1), fp32 0.620 ms at (1,4,1) for 1M alarm37 cases
+        h->spec_vec = 1;
         h->spec_minb = h->precision == BNBP_FP32 ? 4 : 3;
         h->spec_ahead = 1;
         if (const char* ev = getenv("BNBP_SPEC_VEC")) {
@@ -674,6 +733,11 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     if ((rc = h->d_misc.ensure(64))) return rc;
     CU_TRY(cudaMemset(h->d_misc.p, 0, 64));
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
+    CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+        CU_TRY(cudaEventCreateWithFlags(&h->ev_computed[i], cudaEventDisableTiming));
+        CU_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
+    }
     for (int i = 0; i < 2; ++i) {
         CU_TRY(cudaEventCreate(&h->ev_total[i]));
         CU_TRY(cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
@@ -695,9 +759,15 @@ void bnbp_destroy(bnbp_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
-                      &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out,
-                      &h->s_out_sweeps, &h->s_out_conv})
+                      &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1],
+                      &h->s_out_sweeps[0], &h->s_out_sweeps[1], &h->s_out_conv[0], &h->s_out_conv[1]})
         b->release();
+    for (auto& kv : h->belief_plans) kv.second.groups.release();
+    for (int i = 0; i < 2; ++i) {
+        if (h->ev_computed[i]) cudaEventDestroy(h->ev_computed[i]);
+        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
+    }
+    if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int v = 0; v < 3; ++v) spec_unload(&h->spec[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -831,17 +901,37 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->ev_sweep_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
-    if ((rc = ensure_state(h, ev->n_cases))) return rc;
-    const int64_t cap = h->cap;
-    if ((rc = h->s_out.ensure((size_t)cap * h->V * 8))) return rc;
-    if ((rc = h->s_out_sweeps.ensure((size_t)cap * 4))) return rc;
-    if ((rc = h->s_out_conv.ensure((size_t)cap))) return rc;
+    // Chunk pipeline: a large batch is cut into ~8 chunks; the device->host copy of chunk i (on
+    // copy_stream, out of staging buffer i&1) overlaps init/sweeps/beliefs of chunk i+1.  Marginals
+    // are 8*V bytes per case, so on PCIe the copy, not the kernels, bounds the host-buffer call.
+    int64_t chunk = ev->n_cases;
+    if (ev->n_cases >= 131072) chunk = std::max<int64_t>(65536, ((ev->n_cases + 7) / 8 + 511) / 512 * 512);
+    if ((rc = ensure_state(h, chunk))) return rc;
+    chunk = std::min(chunk, h->cap);
+    for (int i = 0; i < 2; ++i) {
+        if ((rc = h->s_out[i].ensure((size_t)chunk * h->V * 8))) return rc;
+        if ((rc = h->s_out_sweeps[i].ensure((size_t)chunk * 4))) return rc;
+        if ((rc = h->s_out_conv[i].ensure((size_t)chunk))) return rc;
+    }
+    cudaStream_t cs = h->copy_stream;
+    struct Drain {                       // no path leaves this call with copies to host memory in flight
+        cudaStream_t a, b;
+        ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); }
+    } drain{st, cs};
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
-    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += cap) {
-        const int64_t n = std::min<int64_t>(cap, ev->n_cases - c0);
+    int idx = 0;
+    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += chunk, ++idx) {
+        const int sb = idx & 1;
+        const int64_t n = std::min<int64_t>(chunk, ev->n_cases - c0);
         const int64_t a = ev->ev_off[c0], b = ev->ev_off[c0 + n];
-        if ((rc = h->s_ev_off.ensure((size_t)(n + 1) * 8))) return rc;
+        if ((rc = h->s_ev_off.ensure((size_t)(chunk + 1) * 8))) return rc;
+        // evidence staging may have to grow: wait for the chunk that still reads the old buffers
+        if (h->s_ev_node.bytes < (size_t)(b - a) * 4 || h->s_ev_state.bytes < (size_t)(b - a) * 4 ||
+            (soft && (h->s_ev_val_off.bytes < (size_t)(b - a + 1) * 8 ||
+                      h->s_ev_values.bytes < (size_t)(ev->ev_val_off[b] - ev->ev_val_off[a]) * 8)))
+            CU_TRY(cudaStreamSynchronize(st));
         if ((rc = h->s_ev_node.ensure(std::max<size_t>(16, (size_t)(b - a) * 4)))) return rc;
+        if (idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[sb], 0));   // staging buffer sb is free again
         CU_TRY(cudaMemcpyAsync(h->s_ev_off.p, ev->ev_off + c0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
         if (b > a) CU_TRY(cudaMemcpyAsync(h->s_ev_node.p, ev->ev_node + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
         DevEvidence de{(const int64_t*)h->s_ev_off.p, a, (const int32_t*)h->s_ev_node.p, nullptr, nullptr, nullptr, 0};
@@ -860,19 +950,22 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
             de.ev_state = (const int32_t*)h->s_ev_state.p;
         }
         if (h->precision == BNBP_FP32)
-            rc = run_chunk<float, double>(h, n, de, *prm, (double*)h->s_out.p, (int32_t*)h->s_out_sweeps.p,
-                                          (uint8_t*)h->s_out_conv.p, st, nullptr);
+            rc = run_chunk<float, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps[sb].p,
+                                          (uint8_t*)h->s_out_conv[sb].p, st, nullptr);
         else
-            rc = run_chunk<double, double>(h, n, de, *prm, (double*)h->s_out.p, (int32_t*)h->s_out_sweeps.p,
-                                           (uint8_t*)h->s_out_conv.p, st, nullptr);
+            rc = run_chunk<double, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps[sb].p,
+                                           (uint8_t*)h->s_out_conv[sb].p, st, nullptr);
         if (rc) return rc;
-        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, h->s_out.p, (size_t)n * h->V * 8, cudaMemcpyDeviceToHost, st));
-        std::vector<int32_t> sw;
-        if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps + c0, h->s_out_sweeps.p, (size_t)n * 4, cudaMemcpyDeviceToHost, st));
-        if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged + c0, h->s_out_conv.p, (size_t)n, cudaMemcpyDeviceToHost, st));
-        // staging buffers are reused by the next chunk
-        CU_TRY(cudaStreamSynchronize(st));
+        CU_TRY(cudaEventRecord(h->ev_computed[sb], st));
+        CU_TRY(cudaStreamWaitEvent(cs, h->ev_computed[sb], 0));
+        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, h->s_out[sb].p, (size_t)n * h->V * 8, cudaMemcpyDeviceToHost, cs));
+        if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps + c0, h->s_out_sweeps[sb].p, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+        if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged + c0, h->s_out_conv[sb].p, (size_t)n, cudaMemcpyDeviceToHost, cs));
+        CU_TRY(cudaEventRecord(h->ev_copied[sb], cs));
     }
+    // the call returns with every result on the host
+    CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[(idx - 1) & 1], 0));
+    if (idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[idx & 1], 0));
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
     if ((rc = check_error_flag(h, st))) return rc;

@@ -200,4 +200,58 @@ belief_kernel(const NodeMeta* nodes, int n_nodes, const T* pl_all, int PL, int T
     if (out_conv) out_conv[c] = status[c];
 }
 
+// K4, tiled: the same belief (:151-158), but the case-major rows leave through shared memory so that
+// global stores are coalesced.  belief_kernel above lets every thread write its own 8*V-byte row
+// (32 rows per warp store = 32 sectors with 8 valid bytes each); here a block first fills a
+// [case][column] tile for a group of consecutive nodes (phase 1, conflict-free: odd row stride),
+// then each warp streams whole row segments to HBM (phase 2).  For V <= the tile width the segment
+// is the full row and the block's output is one contiguous region of TB*V values.
+struct BeliefGroup { int32_t n0, n1, j0, j1; };   // nodes [n0, n1) = columns [j0, j1) of a marginal row
+
+template <typename T, typename OUT>
+__global__ void __launch_bounds__(512)
+belief_tiled_kernel(const NodeMeta* __restrict__ nodes, const BeliefGroup* __restrict__ groups, int n_groups,
+                    const T* __restrict__ pl_all, int PL, int TBi, int V, int stride, int64_t n_valid,
+                    OUT* __restrict__ out, const uint8_t* __restrict__ status, const int32_t* __restrict__ sweeps,
+                    int32_t* __restrict__ out_sweeps, uint8_t* __restrict__ out_conv)
+{
+    extern __shared__ __align__(16) unsigned char belief_smem[];
+    OUT* const tile_buf = reinterpret_cast<OUT*>(belief_smem);
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const size_t TB = (size_t)TBi;
+    const int64_t c0 = (int64_t)tile * TBi;
+    const int64_t c = c0 + lane;
+    const int rows = (int)((n_valid - c0) < (int64_t)TBi ? (n_valid - c0) : (int64_t)TBi);
+    const T* const pl = pl_all + ((size_t)tile * PL) * TB + lane;
+    const int warp = lane >> 5, wl = lane & 31, n_warps = TBi >> 5;
+    for (int g = 0; g < n_groups; ++g) {
+        const BeliefGroup gr = groups[g];
+        if (c < n_valid) {
+            OUT* const mine = tile_buf + (size_t)lane * stride;
+            for (int X = gr.n0; X < gr.n1; ++X) {
+                const NodeMeta nd = nodes[X];
+                const int r = nd.card;
+                T s = T(0);
+                for (int x = 0; x < r; ++x)
+                    s += pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB];
+                for (int x = 0; x < r; ++x)
+                    mine[nd.bel_off - gr.j0 + x] =
+                        (OUT)((pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB]) / s);
+            }
+        }
+        __syncthreads();
+        const int w = gr.j1 - gr.j0;
+        for (int row = warp; row < rows; row += n_warps) {
+            OUT* const dst = out + (size_t)(c0 + row) * V + gr.j0;
+            const OUT* const src = tile_buf + (size_t)row * stride;
+            for (int j = wl; j < w; j += 32) dst[j] = src[j];
+        }
+        __syncthreads();
+    }
+    if (c < n_valid) {
+        if (out_sweeps) out_sweeps[c] = sweeps[c];
+        if (out_conv) out_conv[c] = status[c];
+    }
+}
+
 } // namespace bnbp

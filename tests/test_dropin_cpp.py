@@ -1,0 +1,61 @@
+"""The C++ drop-in boundary: the reference's OWN test sources (libs/bayesian/test/*.cpp), compiled
+unmodified against include/bayesian/*.hpp + libbnbp (oracle/Makefile `dropin`, binaries under
+oracle/_ref/), and the repo's own C++ tests (tests/cpp).  The container builds the binaries
+(/root/reference exists there); the GPU box runs the prebuilt ones."""
+import os
+import subprocess
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+REF_BIN = os.path.join(ROOT, "oracle", "_ref")
+OWN_BIN = os.path.join(ROOT, "tests", "cpp", "_build")
+
+
+def _run(path):
+    if not os.path.exists(path):
+        pytest.skip(f"{os.path.relpath(path, ROOT)} not built (run __graft_entry__.build() where /root/reference exists)")
+    r = subprocess.run([path], capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "No errors detected" in r.stdout, r.stdout[-3000:] + r.stderr[-1000:]
+    return r.stdout
+
+
+@pytest.fixture(scope="module", autouse=True)
+def built():
+    """Build here when the sources are around; never fails the test run by itself."""
+    if os.path.isdir("/root/reference"):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "oracle"), "dropin"], capture_output=True)
+    if os.path.exists(os.path.join(ROOT, "bayesiannetwork_b200", "lib", "libbnbp.so")):
+        subprocess.run(["make", "-C", os.path.join(ROOT, "tests", "cpp")], capture_output=True)
+
+
+@pytest.mark.parametrize("name", ["cpt", "graph", "matrix"])
+def test_reference_container_tests_pass_on_the_new_headers(name):
+    """cpt.cpp / graph.cpp / matrix.cpp of the reference: pure host code, no GPU needed."""
+    out = _run(os.path.join(REF_BIN, f"dropin_{name}"))
+    assert "FAILED" not in out
+
+
+def test_headers_compile_with_plain_gxx_in_cxx11_and_cxx17(tmp_path):
+    """The headers must not need nvcc: host code reaches the GPU only through the C ABI."""
+    src = tmp_path / "t.cpp"
+    src.write_text('#include "bayesian/inference/belief_propagation.hpp"\n'
+                   'int probe() { bn::graph_t g; bn::inference::loopy_belief_propagation bp(g); (void)bp; return 0; }\n')
+    for std in ("c++11", "c++17"):
+        r = subprocess.run(["g++", f"-std={std}", "-Wall", "-Wextra", "-Werror", "-fsyntax-only",
+                            "-I" + os.path.join(ROOT, "include"), str(src)], capture_output=True, text=True)
+        assert r.returncode == 0, r.stderr
+
+
+@pytest.mark.gpu
+def test_reference_bp_tests_pass_on_the_gpu_backend():
+    """libs/bayesian/test/belief_propagation.cpp, unmodified: 7 test cases, BOOST_CHECK_CLOSE bars of
+    the reference (0.01 % - 3 %), computed by the CUDA kernels."""
+    out = _run(os.path.join(REF_BIN, "dropin_belief_propagation"))
+    assert out.count("[  ok  ]") == 7, out
+
+
+@pytest.mark.gpu
+def test_own_cpp_tests_on_the_gpu_backend():
+    out = _run(os.path.join(OWN_BIN, "test_dropin_batch"))
+    assert out.count("[  ok  ]") == 8, out
