@@ -85,8 +85,8 @@ struct bnbp_handle {
     bool spec_eligible_ = false;
     std::string spec_why;              // why the network is not specialised
     int spec_vec = 1, spec_minb = 1, spec_ahead = 1;
-    SpecKernel spec[3];
-    int spec_state[3] = {0, 0, 0};     // 0 untried, 1 loaded, -1 failed
+    SpecKernel spec[5];                // + 3 plain-first (no message loads), 4 plain-last (no message stores)
+    int spec_state[5] = {0, 0, 0, 0, 0};   // 0 untried, 1 loaded, -1 failed
     bool run_spec = false;             // kernel family of the current run
     int last_specialised = 0;
     double spec_compile_ms = 0.0;
@@ -248,10 +248,13 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm)
             return fail(BNBP_ERR_INVALID, "specialize=ALWAYS but the network is not eligible: " + h->spec_why);
         const bool eps_mode = prm.epsilon > 0.0;
         const int interval = prm.check_interval > 0 ? prm.check_interval : 1;
-        bool need[3] = {!eps_mode && prm.damping == 0.0, eps_mode && interval > 1 && prm.damping == 0.0,
-                        eps_mode || prm.damping != 0.0};
+        const bool plain = !eps_mode && prm.damping == 0.0;
+        // fixed sweep count: the first sweep knows every message is 1 (:44-55) and the last sweep's
+        // messages are never read, so neither is moved through HBM (variants 3 and 4)
+        bool need[5] = {plain && prm.max_sweeps != 2, eps_mode && interval > 1 && prm.damping == 0.0,
+                        eps_mode || prm.damping != 0.0, plain && prm.max_sweeps >= 2, plain && prm.max_sweeps >= 2};
         bool ok = true;
-        for (int v = 0; v < 3 && ok; ++v)
+        for (int v = 0; v < 5 && ok; ++v)
             if (need[v] && ensure_spec(h, v) != BNBP_OK) ok = false;
         if (!ok && h->specialize == BNBP_SPEC_ALWAYS) return BNBP_ERR_CUDA;   // message already set
         h->run_spec = ok;
@@ -261,36 +264,29 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm)
     return BNBP_OK;
 }
 
-// Column groups for belief_tiled_kernel: consecutive nodes whose marginals fit one shared-memory
-// tile of [tb cases][width] output elements (<= 96 KB, so two blocks share an SM).
+// Column groups for belief_tiled_kernel: consecutive nodes whose marginals fit one per-warp
+// shared-memory tile of [32 cases][width] output elements (32 columns: 8.4 KB per warp in fp64).
 int belief_plan(bnbp_handle* h, int tb, int out_size, bnbp_handle::BeliefPlan** out)
 {
     const int key = tb * 16 + out_size;
     bnbp_handle::BeliefPlan& p = h->belief_plans[key];
     *out = &p;
     if (p.n_groups) return BNBP_OK;
-    const int width = (int)std::min<size_t>((size_t)h->V, (size_t)(96 * 1024) / ((size_t)tb * out_size) - 1);
-    int maxcard = 1;
-    for (int x = 0; x < h->N; ++x) maxcard = std::max(maxcard, (int)h->nodes[x].card);
+    int width = 32;                                      // every node fits a group: width >= max cardinality
+    for (int x = 0; x < h->N; ++x) width = std::max(width, (int)h->nodes[x].card);
     std::vector<BeliefGroup> groups;
-    if (width >= maxcard) {
-        int x = 0;
-        while (x < h->N) {
-            BeliefGroup g;
-            g.n0 = x; g.j0 = h->nodes[x].bel_off;
-            int w = 0;
-            while (x < h->N && w + h->nodes[x].card <= width) { w += h->nodes[x].card; ++x; }
-            g.n1 = x; g.j1 = g.j0 + w;
-            groups.push_back(g);
-        }
-        p.ok = true;
-    } else {
-        groups.push_back(BeliefGroup{0, 0, 0, 0});      // marker: use the untiled kernel
-        p.ok = false;
+    for (int x = 0; x < h->N;) {
+        BeliefGroup g;
+        g.n0 = x; g.j0 = h->nodes[x].bel_off;
+        int w = 0;
+        while (x < h->N && w + h->nodes[x].card <= width) { w += h->nodes[x].card; ++x; }
+        g.n1 = x; g.j1 = g.j0 + w;
+        groups.push_back(g);
     }
+    p.ok = true;
     p.n_groups = (int)groups.size();
     p.stride = width | 1;                                // odd row stride: conflict-free phase 1
-    p.smem = (size_t)tb * p.stride * out_size;
+    p.smem = (size_t)tb * p.stride * out_size;           // tb/32 warps x [32][stride]
     int rc = p.groups.ensure(groups.size() * sizeof(BeliefGroup));
     if (rc) return rc;
     CU_TRY(cudaMemcpy(p.groups.p, groups.data(), groups.size() * sizeof(BeliefGroup), cudaMemcpyHostToDevice));
@@ -330,6 +326,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         ia.delta = (T*)h->d_delta.p; ia.cap = h->cap;
         ia.status = (uint8_t*)h->d_status.p; ia.sweeps = (int32_t*)h->d_sweeps.p;
         ia.error_flag = d_error;
+        // the specialised first sweep (variant 3) does not read the time-0 messages
+        ia.write_msgs = (h->run_spec && !eps_mode && prm.damping == 0.0 && max_sweeps >= 2) ? 0 : 1;
         init_kernel<T><<<tiles, h->tb, 0, st>>>(ia);
         CU_TRY(cudaGetLastError());
         h->last_kernel_launches++;
@@ -389,7 +387,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             sa.prev_tested = prev_tested ? 1 : 0;
             if (h->run_spec) {
                 // network-specialised kernel: variant 0 plain, 1 freeze, 2 freeze + check
-                const int variant = check ? 2 : (eps_mode ? 1 : 0);
+                int variant = check ? 2 : (eps_mode ? 1 : 0);
+                if (variant == 0 && max_sweeps >= 2) variant = t == 0 ? 3 : (t == max_sweeps - 1 ? 4 : 0);
                 SpecAux<T> ax;
                 ax.delta_prev = sa.delta_prev; ax.delta_cur = sa.delta_cur; ax.delta_next = sa.delta_next;
                 ax.status = sa.status; ax.sweeps = sa.sweeps; ax.last_active = sa.last_active;
@@ -768,7 +767,7 @@ void bnbp_destroy(bnbp_handle* h)
         if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
     }
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
-    for (int v = 0; v < 3; ++v) spec_unload(&h->spec[v]);
+    for (int v = 0; v < 5; ++v) spec_unload(&h->spec[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_total[i]) cudaEventDestroy(h->ev_total[i]);
@@ -786,7 +785,7 @@ int bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values)
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaDeviceSynchronize());          // runs may have been enqueued on caller streams
     h->cpt_host.assign(cpt, cpt + n_values);
-    for (int v = 0; v < 3; ++v) {             // constant banks of the loaded specialised kernels
+    for (int v = 0; v < 5; ++v) {             // constant banks of the loaded specialised kernels
         if (h->spec_state[v] != 1) continue;
         std::string err;
         bool ok;
@@ -807,7 +806,7 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
     int rc = build_layout(net, opt, &h);
     if (rc) return rc;
     if (!h.spec_eligible_) return fail(BNBP_ERR_INVALID, "network is not eligible for specialisation: " + h.spec_why);
-    for (int v = 0; v < 3; ++v) {
+    for (int v = 0; v < 5; ++v) {
         if (!(variant_mask & (1 << v))) continue;
         SpecConfig cfg;
         cfg.fp32 = h.precision == BNBP_FP32;
@@ -822,7 +821,7 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
 int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant, char* buf, int64_t cap,
                      int64_t* needed)
 {
-    if (variant < 0 || variant > 2) return fail(BNBP_ERR_INVALID, "variant must be 0, 1 or 2");
+    if (variant < 0 || variant > 4) return fail(BNBP_ERR_INVALID, "variant must be 0..4");
     bnbp_handle h;
     int rc = build_layout(net, opt, &h);
     if (rc) return rc;

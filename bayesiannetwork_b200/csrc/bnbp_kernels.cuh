@@ -115,6 +115,7 @@ template <typename T> struct InitArgs {
     T* delta; int64_t cap;      // delta[3][cap]
     uint8_t* status; int32_t* sweeps;
     int32_t* error_flag;
+    int32_t write_msgs;         // 0: the first sweep will not read the time-0 messages (all ones)
 };
 
 template <typename T>
@@ -127,7 +128,8 @@ __global__ void __launch_bounds__(512) init_kernel(const InitArgs<T> a)
     T* msg = a.msg0 + ((size_t)tile * a.M) * TB + lane;
     uint32_t* evb = a.evbits + ((size_t)tile * a.W) * TB + lane;
     for (int s = 0; s < a.PL; ++s) pl[(size_t)s * TB] = __ldg(a.pl_init + s);
-    for (int s = 0; s < a.M; ++s) msg[(size_t)s * TB] = T(1);
+    if (a.write_msgs)
+        for (int s = 0; s < a.M; ++s) msg[(size_t)s * TB] = T(1);
     for (int w = 0; w < a.W; ++w) evb[(size_t)w * TB] = 0u;
     for (int i = 0; i < 3; ++i) a.delta[(size_t)i * a.cap + c] = Lim<T>::floor_();
     a.sweeps[c] = 0;
@@ -202,10 +204,11 @@ belief_kernel(const NodeMeta* nodes, int n_nodes, const T* pl_all, int PL, int T
 
 // K4, tiled: the same belief (:151-158), but the case-major rows leave through shared memory so that
 // global stores are coalesced.  belief_kernel above lets every thread write its own 8*V-byte row
-// (32 rows per warp store = 32 sectors with 8 valid bytes each); here a block first fills a
-// [case][column] tile for a group of consecutive nodes (phase 1, conflict-free: odd row stride),
-// then each warp streams whole row segments to HBM (phase 2).  For V <= the tile width the segment
-// is the full row and the block's output is one contiguous region of TB*V values.
+// (32 rows per warp store = 32 sectors with 8 valid bytes each).  Here every WARP owns 32 cases and
+// a private [32][W+1] tile: for a group of consecutive nodes (<= W columns of the marginal row) each
+// lane normalises its case into its tile row (conflict-free: odd row stride), then the warp streams
+// the 32 row segments to HBM, one 8*W-byte contiguous segment per store instruction.  Warps never
+// wait for each other (no block barrier) and the tile is small enough for 24 resident warps per SM.
 struct BeliefGroup { int32_t n0, n1, j0, j1; };   // nodes [n0, n1) = columns [j0, j1) of a marginal row
 
 template <typename T, typename OUT>
@@ -216,37 +219,37 @@ belief_tiled_kernel(const NodeMeta* __restrict__ nodes, const BeliefGroup* __res
                     int32_t* __restrict__ out_sweeps, uint8_t* __restrict__ out_conv)
 {
     extern __shared__ __align__(16) unsigned char belief_smem[];
-    OUT* const tile_buf = reinterpret_cast<OUT*>(belief_smem);
     const int tile = blockIdx.x, lane = threadIdx.x;
+    const int warp = lane >> 5, wl = lane & 31;
+    OUT* const tile_buf = reinterpret_cast<OUT*>(belief_smem) + (size_t)warp * 32 * stride;
     const size_t TB = (size_t)TBi;
-    const int64_t c0 = (int64_t)tile * TBi;
-    const int64_t c = c0 + lane;
-    const int rows = (int)((n_valid - c0) < (int64_t)TBi ? (n_valid - c0) : (int64_t)TBi);
+    const int64_t w0 = (int64_t)tile * TBi + warp * 32;     // first case of this warp
+    const int64_t c = w0 + wl;
+    if (w0 >= n_valid) return;                               // whole warp beyond the batch
+    const int rows = (int)((n_valid - w0) < 32 ? (n_valid - w0) : 32);
     const T* const pl = pl_all + ((size_t)tile * PL) * TB + lane;
-    const int warp = lane >> 5, wl = lane & 31, n_warps = TBi >> 5;
+    OUT* const mine = tile_buf + (size_t)wl * stride;
     for (int g = 0; g < n_groups; ++g) {
         const BeliefGroup gr = groups[g];
         if (c < n_valid) {
-            OUT* const mine = tile_buf + (size_t)lane * stride;
             for (int X = gr.n0; X < gr.n1; ++X) {
                 const NodeMeta nd = nodes[X];
                 const int r = nd.card;
+                const T* const p = pl + (size_t)nd.pl_off * TB;
                 T s = T(0);
+                for (int x = 0; x < r; ++x) s += p[(size_t)x * TB] * p[(size_t)(r + x) * TB];
                 for (int x = 0; x < r; ++x)
-                    s += pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB];
-                for (int x = 0; x < r; ++x)
-                    mine[nd.bel_off - gr.j0 + x] =
-                        (OUT)((pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB]) / s);
+                    mine[nd.bel_off - gr.j0 + x] = (OUT)((p[(size_t)x * TB] * p[(size_t)(r + x) * TB]) / s);
             }
         }
-        __syncthreads();
+        __syncwarp();
         const int w = gr.j1 - gr.j0;
-        for (int row = warp; row < rows; row += n_warps) {
-            OUT* const dst = out + (size_t)(c0 + row) * V + gr.j0;
+        for (int row = 0; row < rows; ++row) {
+            OUT* const dst = out + (size_t)(w0 + row) * V + gr.j0;
             const OUT* const src = tile_buf + (size_t)row * stride;
             for (int j = wl; j < w; j += 32) dst[j] = src[j];
         }
-        __syncthreads();
+        __syncwarp();
     }
     if (c < n_valid) {
         if (out_sweeps) out_sweeps[c] = sweeps[c];

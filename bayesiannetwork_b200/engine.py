@@ -24,7 +24,7 @@ def _net_c(net: FlatNetwork):
                               _vp(net.cpt_off), _vp(net.cpt))
 
 
-def precompile(net: FlatNetwork, precision: str = "fp64", variants: int = 0b111) -> None:
+def precompile(net: FlatNetwork, precision: str = "fp64", variants: int = 0b11111) -> None:
     """Run the network compiler without a GPU: generate the specialised sweep kernels of ``net``
     and leave their cubins in the cache (``bnbp_precompile``)."""
     lib = _capi.load()

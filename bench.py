@@ -323,9 +323,21 @@ def main():
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
             dt = float(t[0])
+        # context for the number: what the host link moves when it does nothing else (the marginals
+        # are 8*V bytes per case; on PCIe this copy, not the kernels, bounds the host-buffer call)
+        probe = torch.empty(n * V, dtype=torch.float64, device=dev)
+        p_out.view(-1).copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        p_out.view(-1).copy_(probe, non_blocking=True)
+        torch.cuda.synchronize()
+        d2h_gbs = n * V * 8 / (time.perf_counter() - t0) / 1e9
+        del probe
         e2e = {"value": world * n * sweeps * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(ev.nbytes()), "d2h_bytes_per_step": int(n * V * 8 + n * 5),
-               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps}
+               "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
+               "d2h_link_gbs_measured": d2h_gbs, "d2h_floor_ms_per_step": 1e3 * n * V * 8 / (d2h_gbs * 1e9),
+               "pipeline": "8 chunks, D2H of chunk i overlaps init/sweeps/beliefs of chunk i+1"}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle port on all host cores ---------------
     cpu = None

@@ -155,11 +155,13 @@ int  bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values);
 /* Network compiler without a GPU (build machines, tests): generate the specialised sweep kernel of
  * `net` for opt->precision and compile it into the cubin cache ($BNBP_CACHE_DIR, default
  * <dir of libbnbp.so>/jitcache), so that bnbp_create/run on the GPU box finds it there.
- * variant_mask: bit 0 plain (fixed sweeps), bit 1 freeze, bit 2 freeze+check (epsilon mode, damping).
+ * variant_mask: bit 0 plain (fixed sweeps), bit 1 freeze, bit 2 freeze+check (epsilon mode, damping),
+ *               bit 3 plain-first (time-0 messages are all 1: not loaded), bit 4 plain-last (messages
+ *               of the last sweep are never read: not stored).
  * Returns BNBP_ERR_INVALID with the reason if the network is not eligible. */
 int  bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant_mask);
 
-/* The generated CUDA source of one variant (0, 1, 2), for inspection and tests.  Writes at most
+/* The generated CUDA source of one variant (0..4), for inspection and tests.  Writes at most
  * cap bytes including the terminating NUL and returns the full length via *needed. */
 int  bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant,
                       char* buf, int64_t cap, int64_t* needed);

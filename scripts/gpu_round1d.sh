@@ -9,4 +9,4 @@ timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > gpurun_out/r
 timeout 600 ncu --metrics gpu__time_duration.sum,dram__bytes_read.sum,dram__bytes_write.sum --clock-control none -s 30 -c 30 --csv --log-file gpurun_out/r01d_launches.csv python bench.py --no-cpu --no-e2e --steps 1 --warmup 3 > gpurun_out/r01d_launches.log 2>&1
 # full-size capture of the specialised kernel for the traffic figure
 timeout 600 ncu --set full --clock-control none --import-source on -k regex:bnbp_spec_sweep -s 10 -c 1 -o gpurun_out/r01d_spec_fp64_1m python bench.py --no-cpu --no-e2e --steps 1 --warmup 3 > gpurun_out/r01d_ncu.log 2>&1; tail -2 gpurun_out/r01d_ncu.log
-for w in grid100 dag2000; do timeout 600 python bench.py --workload $w --no-cpu --steps 3 > gpurun_out/r01d_bench_$w.json 2> gpurun_out/r01d_bench_$w.err; cut -c1-300 gpurun_out/r01d_bench_$w.json; tail -2 gpurun_out/r01d_bench_$w.err; done
+for w in grid100 dag2000; do timeout 600 python bench.py --workload $w --no-cpu --no-e2e --cases 16384 --steps 2 > gpurun_out/r01d_bench_$w.json 2> gpurun_out/r01d_bench_$w.err; cut -c1-300 gpurun_out/r01d_bench_$w.json; tail -2 gpurun_out/r01d_bench_$w.err; done

@@ -24,7 +24,7 @@ def precompile():
     def one(job):
         prec, (vec, minb, ahead) = job
         code = (f"import sys; sys.path.insert(0, {ROOT!r}); from bayesiannetwork_b200 import engine, synth; "
-                f"engine.precompile(synth.alarm37(), {prec!r}, 1)")
+                f"engine.precompile(synth.alarm37(), {prec!r}, 0b11001)")
         r = subprocess.run([sys.executable, "-c", code], env=env_for(vec, minb, ahead), capture_output=True, text=True)
         return job, r.returncode, r.stderr[-300:]
     jobs = [(p, c) for p, cs in COMBOS.items() for c in cs]

@@ -80,6 +80,18 @@ def test_specialised_extensions_and_refresh(BP, oracle_mod):
     assert_close(bp(ev, 0.0, max_sweeps=9).marginals, om, what="refresh", **TOL["fp64"])
 
 
+@pytest.mark.parametrize("cap", [1, 2, 3])
+def test_specialised_short_fixed_runs(BP, oracle_mod, cap):
+    """1, 2 and 3 fixed sweeps: the first sweep (no message loads) and the last sweep (no message
+    stores) are separate kernel variants; 1 sweep uses the plain variant alone."""
+    net = synth.grid(5, seed=8)
+    ev = synth.make_evidence(net, 300, p=0.15, seed=5)
+    om, osw, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=cap)
+    res = BP(net, specialize="always")(ev, 0.0, max_sweeps=cap)
+    assert np.array_equal(res.sweeps, osw)
+    assert_close(res.marginals, om, what=f"{cap} sweeps", **TOL["fp64"])
+
+
 def test_specialised_equals_generic_bitwise_shape(BP):
     """Both kernel families implement the same schedule: fixed sweeps, same sweep counts, results
     within a few ulp of each other (they differ only in the order of some products)."""
