@@ -196,6 +196,9 @@ def main():
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
     ap.add_argument("--specialize", default="auto", choices=["auto", "always", "never"],
                     help="sweep-kernel family: network-specialised (NVRTC) or generic")
+    ap.add_argument("--epsilon", type=float, default=0.0,
+                    help="> 0: time-to-solution mode (reference stopping rule, delta < epsilon per case, "
+                         "--sweeps = cap, default 200); value counts the sweeps actually executed")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -224,7 +227,7 @@ def main():
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
     net, ev, sweeps = build_workload(args.workload, args.cases or None, rank)
-    sweeps = args.sweeps or sweeps
+    sweeps = args.sweeps or (200 if args.epsilon > 0 else sweeps)
     n, V = ev.n_cases, net.belief_values
     tdtype = torch.float64 if args.precision == "fp64" else torch.float32
     tsize = 8 if args.precision == "fp64" else 4
@@ -245,7 +248,7 @@ def main():
     stream = tstream.cuda_stream
 
     def step():
-        bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=0.0, max_sweeps=sweeps,
+        bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=args.epsilon, max_sweeps=sweeps,
                       out_sweeps=d_sw, out_converged=d_cv, stream=stream)
         if world > 1:
             # the only collectives of the path: global sweep count + all-converged flag (and,
@@ -279,12 +282,30 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, sweep_ms_per_launch = float(t[0]), float(t[1])
     clocks = sampler.stop() if sampler else None
-    value = world * n * sweeps * args.steps / (ms * 1e-3)
+    eps_info = None
+    if args.epsilon > 0:
+        # time-to-solution mode: count the sweeps each case actually executed (same every step)
+        tot = torch.stack([d_sw.sum(dtype=torch.int64), (d_cv != 0).sum(dtype=torch.int64),
+                           d_sw.max().to(torch.int64)])
+        if world > 1:
+            mx = tot[2:].clone()
+            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
+            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            tot[2] = mx[0]
+        case_sweeps, n_conv, max_sw = (int(x) for x in tot.tolist())
+        value = case_sweeps * args.steps / (ms * 1e-3)
+        eps_info = {"epsilon": args.epsilon, "max_sweeps": sweeps, "case_sweeps_per_step": case_sweeps,
+                    "mean_sweeps_per_case": case_sweeps / (world * n), "max_sweeps_seen": max_sw,
+                    "converged_fraction": n_conv / (world * n), "sweep_launches_per_step": int(st["last_sweep_launches"])}
+    else:
+        value = world * n * sweeps * args.steps / (ms * 1e-3)
 
     # ---- roofline of the dominant kernel (sweep_kernel) ----------------------------------------------
     S = net.state_values
     peak, peak_src = measured_peaks()
     bytes_per_launch = 2.0 * S * tsize * n           # every state value read once and written once
+    if eps_info:                                     # frozen cases move no data: average over the launches
+        bytes_per_launch = 2.0 * S * tsize * eps_info["case_sweeps_per_step"] / world / max(1, st["last_sweep_launches"])
     achieved = bytes_per_launch / (sweep_ms_per_launch * 1e-3) / 1e9
     traffic = None
     tpath = os.path.join(ROOT, "profiles", "traffic.json")
@@ -312,11 +333,11 @@ def main():
         ev_pinned = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
         out_np = p_out.numpy()
         e2e_steps = max(1, min(args.steps, 5))
-        bp(ev_pinned, 0.0, max_sweeps=sweeps, out=out_np)      # warm-up (staging buffers)
+        bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)      # warm-up (staging buffers)
         barrier()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
-            bp(ev_pinned, 0.0, max_sweeps=sweeps, out=out_np)
+            bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         if world > 1:
@@ -333,7 +354,8 @@ def main():
         torch.cuda.synchronize()
         d2h_gbs = n * V * 8 / (time.perf_counter() - t0) / 1e9
         del probe
-        e2e = {"value": world * n * sweeps * e2e_steps / dt, "unit": UNIT,
+        units_per_step = eps_info["case_sweeps_per_step"] if eps_info else world * n * sweeps
+        e2e = {"value": units_per_step * e2e_steps / dt, "unit": UNIT,
                "h2d_bytes_per_step": int(ev.nbytes()), "d2h_bytes_per_step": int(n * V * 8 + n * 5),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "d2h_link_gbs_measured": d2h_gbs, "d2h_floor_ms_per_step": 1e3 * n * V * 8 / (d2h_gbs * 1e9),
@@ -341,7 +363,7 @@ def main():
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle port on all host cores ---------------
     cpu = None
-    if rank == 0 and world == 1 and not args.no_cpu:
+    if rank == 0 and world == 1 and not args.no_cpu and not eps_info:
         cores = cpu_cores()
         sample_cases = 256
         rate, dt = time_port(net, ev.slice(0, sample_cases), sweeps, cores)
@@ -360,7 +382,9 @@ def main():
             "data": "synthetic",
             "config": {"workload": args.workload, "nodes": net.n_nodes, "edges": net.n_edges,
                        "max_card": int(net.card.max()), "cases_per_gpu": n, "sweeps": sweeps,
-                       "state_values_per_case": S, "schedule": "synchronous, fixed sweeps, no damping",
+                       "state_values_per_case": S,
+                       "schedule": ("synchronous, stop per case at delta < epsilon (reference rule)" if eps_info
+                                    else "synchronous, fixed sweeps, no damping"), "eps_mode": eps_info,
                        "sharding": f"cases x{world}", "gather": bool(gathered is not None),
                        "kernel_family": "network-specialised (NVRTC sm_100a)" if st["last_specialised"] else "generic",
                        "cases_per_tile": int(st["cases_per_tile"]),

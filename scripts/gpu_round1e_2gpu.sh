@@ -1,0 +1,6 @@
+set -x
+mkdir -p gpurun_out
+nvidia-smi -L > gpurun_out/r01e_2gpu_devices.txt
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu > gpurun_out/r01e_bench_2gpu.json 2> gpurun_out/r01e_bench_2gpu.err; cut -c1-300 gpurun_out/r01e_bench_2gpu.json; tail -3 gpurun_out/r01e_bench_2gpu.err
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus 2 --steps 10 --warmup 3 --no-cpu --no-e2e --gather > gpurun_out/r01e_bench_2gpu_gather.json 2> gpurun_out/r01e_bench_2gpu_gather.err; cut -c1-300 gpurun_out/r01e_bench_2gpu_gather.json
+timeout 300 python bench.py --impl reference --gpus 2 --steps 2 --warmup 1 > gpurun_out/r01e_bench_reference_n2.json 2>&1

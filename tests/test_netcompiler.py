@@ -57,3 +57,18 @@ def test_ineligible_networks_are_reported(engine):
         engine.precompile(synth.high_card(6, card=32, n_parents=2, seed=10), "fp64", 1)
     with pytest.raises(BnbpError, match="not eligible"):
         engine.spec_source(synth.grid(40), "fp64", 0)             # 1600 nodes
+
+
+def test_cmake_project_configures(tmp_path):
+    """CMakeLists.txt (the CUDA / C-ABI build wiring the north star asks for) configures with the
+    image's cmake + nvcc; the full build is exercised by hand (takes a minute), not here."""
+    import shutil
+    cmake = shutil.which("cmake")
+    if not cmake or not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("cmake / nvcc not available")
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = {k: v for k, v in os.environ.items() if k not in ("CC", "CXX")}
+    r = subprocess.run([cmake, "-S", root, "-B", str(tmp_path / "b"), "-DCMAKE_CUDA_COMPILER=/usr/local/cuda/bin/nvcc"],
+                       capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+    assert (tmp_path / "b" / "gen" / "bnbp_spec_embed.inc").exists()
