@@ -10,6 +10,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <chrono>
 #include <cstring>
 #include <map>
 #include <memory>
@@ -96,7 +97,7 @@ struct bnbp_handle {
     int64_t cap = 0;
     DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
     // staging for the host API (outputs double-buffered: D2H of chunk i overlaps the sweeps of chunk i+1)
-    DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out[2], s_out_sweeps[2], s_out_conv[2];
+    DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out[2], s_out_sweeps, s_out_conv;   // sweeps/conv: whole batch
     cudaStream_t copy_stream = nullptr;
     cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
     // column groups of the tiled belief kernel, per (tile width, output element size)
@@ -648,7 +649,7 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     h->vec = (h->rmax <= 4) ? 2 : 1;
     if (const char* ev = getenv("BNBP_VEC")) {           // tuning knob: cases per thread
         const int v = atoi(ev);
-        if ((v == 1 || v == 2) && h->rmax <= 4) h->vec = v;
+        if ((v == 1 || v == 2) && h->rmax <= 8) h->vec = v;
     }
     h->tb = BLOCK_THREADS * h->vec;
     h->cpt_values = net->cpt_off[N];
@@ -759,7 +760,7 @@ void bnbp_destroy(bnbp_handle* h)
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
                       &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1],
-                      &h->s_out_sweeps[0], &h->s_out_sweeps[1], &h->s_out_conv[0], &h->s_out_conv[1]})
+                      &h->s_out_sweeps, &h->s_out_conv})
         b->release();
     for (auto& kv : h->belief_plans) kv.second.groups.release();
     for (int i = 0; i < 2; ++i) {
@@ -900,28 +901,62 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->ev_sweep_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
-    // Chunk pipeline: a large batch is cut into ~8 chunks; the device->host copy of chunk i (on
-    // copy_stream, out of staging buffer i&1) overlaps init/sweeps/beliefs of chunk i+1.  Marginals
-    // are 8*V bytes per case, so on PCIe the copy, not the kernels, bounds the host-buffer call.
-    int64_t chunk = ev->n_cases;
-    if (ev->n_cases >= 131072) chunk = std::max<int64_t>(65536, ((ev->n_cases + 7) / 8 + 511) / 512 * 512);
-    if ((rc = ensure_state(h, chunk))) return rc;
-    chunk = std::min(chunk, h->cap);
-    for (int i = 0; i < 2; ++i) {
-        if ((rc = h->s_out[i].ensure((size_t)chunk * h->V * 8))) return rc;
-        if ((rc = h->s_out_sweeps[i].ensure((size_t)chunk * 4))) return rc;
-        if ((rc = h->s_out_conv[i].ensure((size_t)chunk))) return rc;
+    // Chunk pipeline: the device->host copy of chunk i (on copy_stream, out of staging buffer i&1)
+    // overlaps init/sweeps/beliefs of chunk i+1.  Marginals are 8*V bytes per case, so the copy is
+    // of the same order as the kernels.  Schedule 3/8, 3/8, 1/8, 1/8 of the batch: big chunks keep
+    // the sweep grids many waves deep (a 128K-case grid is 2.3 waves: +20 % per sweep, r01g trace),
+    // the small last chunk keeps the exposed tail copy short.
+    std::vector<int64_t> plan;
+    {
+        const int64_t n = ev->n_cases;
+        auto up = [](int64_t v) { return (v + 511) / 512 * 512; };
+        if (n >= 262144) {
+            const int64_t big = up(n * 3 / 8), small = up(n / 8);
+            plan = {big, big, small, n};                  // the last entry takes what is left
+        } else if (n >= 32768) {
+            const int64_t q = up((n + 3) / 4);
+            plan = {q, q, q, n};
+        } else {
+            plan = {n};
+        }
     }
+    int64_t chunk = *std::max_element(plan.begin(), plan.end() - (plan.size() > 1 ? 1 : 0));
+    if ((rc = ensure_state(h, chunk))) return rc;
+    if (h->cap < chunk) {                                 // HBM cannot hold the planned chunk: equal resident chunks
+        chunk = h->cap;
+        plan.assign(1, chunk);
+    }
+    for (int i = 0; i < 2; ++i)
+        if ((rc = h->s_out[i].ensure((size_t)chunk * h->V * 8))) return rc;
+    // per-case sweep counts / flags stay on the device until the end: the caller's arrays are usually
+    // pageable, and a pageable D2H per chunk would block the host and serialise the pipeline
+    if ((rc = h->s_out_sweeps.ensure((size_t)ev->n_cases * 4))) return rc;
+    if ((rc = h->s_out_conv.ensure((size_t)ev->n_cases))) return rc;
+    const bool trace = getenv("BNBP_TRACE") != nullptr;
+    const auto t_begin = std::chrono::steady_clock::now();
+    auto stamp = [&](const char* what, int i) {
+        if (trace)
+            fprintf(stderr, "[bnbp] %8.3f ms  %s %d\n",
+                    std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, i);
+    };
     cudaStream_t cs = h->copy_stream;
     struct Drain {                       // no path leaves this call with copies to host memory in flight
         cudaStream_t a, b;
         ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); }
     } drain{st, cs};
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
+    std::vector<cudaEvent_t> tev;                     // BNBP_TRACE: device timeline of the pipeline
+    auto mark = [&](cudaStream_t s) {
+        if (!trace) return;
+        cudaEvent_t e;
+        cudaEventCreate(&e);
+        cudaEventRecord(e, s);
+        tev.push_back(e);
+    };
     int idx = 0;
-    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += chunk, ++idx) {
+    for (int64_t c0 = 0, n = 0; c0 < ev->n_cases; c0 += n, ++idx) {
         const int sb = idx & 1;
-        const int64_t n = std::min<int64_t>(chunk, ev->n_cases - c0);
+        n = std::min<int64_t>(std::min<int64_t>(plan[std::min<size_t>((size_t)idx, plan.size() - 1)], chunk), ev->n_cases - c0);
         const int64_t a = ev->ev_off[c0], b = ev->ev_off[c0 + n];
         if ((rc = h->s_ev_off.ensure((size_t)(chunk + 1) * 8))) return rc;
         // evidence staging may have to grow: wait for the chunk that still reads the old buffers
@@ -948,26 +983,46 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
             if (b > a) CU_TRY(cudaMemcpyAsync(h->s_ev_state.p, ev->ev_state + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
             de.ev_state = (const int32_t*)h->s_ev_state.p;
         }
+        stamp("enqueue chunk", idx);
+        mark(st);
         if (h->precision == BNBP_FP32)
-            rc = run_chunk<float, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps[sb].p,
-                                          (uint8_t*)h->s_out_conv[sb].p, st, nullptr);
+            rc = run_chunk<float, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps.p + c0,
+                                          (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         else
-            rc = run_chunk<double, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps[sb].p,
-                                           (uint8_t*)h->s_out_conv[sb].p, st, nullptr);
+            rc = run_chunk<double, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps.p + c0,
+                                           (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         if (rc) return rc;
+        mark(st);
         CU_TRY(cudaEventRecord(h->ev_computed[sb], st));
         CU_TRY(cudaStreamWaitEvent(cs, h->ev_computed[sb], 0));
+        mark(cs);
         CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, h->s_out[sb].p, (size_t)n * h->V * 8, cudaMemcpyDeviceToHost, cs));
-        if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps + c0, h->s_out_sweeps[sb].p, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
-        if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged + c0, h->s_out_conv[sb].p, (size_t)n, cudaMemcpyDeviceToHost, cs));
+        mark(cs);
         CU_TRY(cudaEventRecord(h->ev_copied[sb], cs));
+        stamp("enqueued copy", idx);
     }
+    CU_TRY(cudaStreamWaitEvent(cs, h->ev_computed[(idx - 1) & 1], 0));
+    if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps, h->s_out_sweeps.p, (size_t)ev->n_cases * 4, cudaMemcpyDeviceToHost, cs));
+    if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged, h->s_out_conv.p, (size_t)ev->n_cases, cudaMemcpyDeviceToHost, cs));
+    CU_TRY(cudaEventRecord(h->ev_copied[(idx - 1) & 1], cs));
+    stamp("all enqueued", idx);
     // the call returns with every result on the host
     CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[(idx - 1) & 1], 0));
     if (idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[idx & 1], 0));
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
     if ((rc = check_error_flag(h, st))) return rc;
+    CU_TRY(cudaStreamSynchronize(cs));
+    stamp("done", idx);
+    for (size_t i = 0; i + 3 < tev.size(); i += 4) {
+        float a = 0, b = 0, c = 0, d = 0;
+        cudaEventElapsedTime(&a, tev[0], tev[i]);
+        cudaEventElapsedTime(&b, tev[0], tev[i + 1]);
+        cudaEventElapsedTime(&c, tev[0], tev[i + 2]);
+        cudaEventElapsedTime(&d, tev[0], tev[i + 3]);
+        fprintf(stderr, "[bnbp] chunk %zu: compute %.3f..%.3f ms, copy %.3f..%.3f ms (device timeline)\n", i / 4, a, b, c, d);
+    }
+    for (cudaEvent_t e : tev) cudaEventDestroy(e);
     if (out_sweeps) {
         int64_t s = 0;
         for (int64_t c = 0; c < ev->n_cases; ++c) s += out_sweeps[c];
