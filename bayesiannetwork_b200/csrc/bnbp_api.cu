@@ -6,6 +6,7 @@
 #include "bnbp_kernels.cuh"
 #include "bnbp_variants.h"
 #include "bnbp_jit.h"
+#include "bnbp_dense.h"
 
 #include <algorithm>
 #include <cmath>
@@ -91,6 +92,22 @@ struct bnbp_handle {
     bool run_spec = false;             // kernel family of the current run
     int last_specialised = 0;
     double spec_compile_ms = 0.0;
+    // dense contraction path (bnbp_dense.h): nodes whose CPT has >= dense_min entries
+    int64_t dense_min = 4096;          // < 0: never
+    int TS = 0;                        // per-case slots of the contraction scratch (T1 / T2 tables)
+    int dense_nodes = 0;
+    double dense_flops_per_case = 0.0; // 4 * sum |CPT| over the dense nodes, per sweep
+    std::vector<DenseJob> djobs;       // sorted by factor count
+    struct DenseGroup { int nf, n_y, ytab0, max_rows; };
+    std::vector<DenseGroup> dgroups;   // one launch each
+    std::vector<int32_t> dytab;
+    std::vector<unsigned long long> ddig;
+    std::vector<int64_t> dense_pt_off; // per node: offset of the transposed CPT copy in arena 1 (-1: not dense)
+    int64_t cpt_t_values = 0;
+    DevBuf d_djobs, d_dytab, d_ddig, d_cpt_t, d_tscr;
+    std::vector<cudaEvent_t> ev_dense; // pairs around the dense launches of a sweep
+    int ev_dense_used = 0;
+    int64_t last_dense_launches = 0;
     // device network
     DevBuf d_nodes, d_e_card, d_e_lam_out, d_c_pi_out, d_cpt, d_pl_init;
     // device state for the resident chunk
@@ -163,12 +180,12 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
 {
     const int64_t TBMAX = 512;          // every kernel family's tile width divides this
     int64_t want = (n_cases + TBMAX - 1) / TBMAX * TBMAX;
-    const size_t per_case = (size_t)(h->PL + 2 * (size_t)h->M) * h->tsize + (size_t)h->W * 4 + 3 * h->tsize + 8;
+    const size_t per_case = (size_t)(h->PL + 2 * (size_t)h->M + (size_t)h->TS) * h->tsize + (size_t)h->W * 4 + 3 * h->tsize + 8;
     int64_t limit = h->max_resident;
     if (limit <= 0) {
         size_t free_b = 0, total_b = 0;
         CU_TRY(cudaMemGetInfo(&free_b, &total_b));
-        size_t held = h->d_pl.bytes + h->d_msg[0].bytes + h->d_msg[1].bytes + h->d_evbits.bytes;
+        size_t held = h->d_pl.bytes + h->d_msg[0].bytes + h->d_msg[1].bytes + h->d_evbits.bytes + h->d_tscr.bytes;
         // leave room for output staging (V doubles per case) and the caller's own buffers
         double usable = 0.80 * (double)(free_b + held);
         limit = (int64_t)(usable / (double)(per_case + (size_t)h->V * 8));
@@ -177,7 +194,7 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
     want = std::min(want, limit);
     if (want <= h->cap) return BNBP_OK;
     // grow: release first so the new allocation can reuse the space
-    h->d_pl.release(); h->d_msg[0].release(); h->d_msg[1].release(); h->d_evbits.release();
+    h->d_pl.release(); h->d_msg[0].release(); h->d_msg[1].release(); h->d_evbits.release(); h->d_tscr.release();
     h->d_delta.release(); h->d_status.release(); h->d_sweeps.release();
     h->cap = 0;
     int rc;
@@ -185,6 +202,7 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
     if ((rc = h->d_msg[0].ensure(std::max<size_t>(16, (size_t)want * h->M * h->tsize)))) return rc;
     if ((rc = h->d_msg[1].ensure(std::max<size_t>(16, (size_t)want * h->M * h->tsize)))) return rc;
     if ((rc = h->d_evbits.ensure((size_t)want * h->W * 4))) return rc;
+    if (h->TS > 0 && (rc = h->d_tscr.ensure((size_t)want * h->TS * h->tsize))) return rc;
     if ((rc = h->d_delta.ensure((size_t)want * 3 * h->tsize))) return rc;
     if ((rc = h->d_status.ensure((size_t)want))) return rc;
     if ((rc = h->d_sweeps.ensure((size_t)want * 4))) return rc;
@@ -343,7 +361,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.cpt = (const T*)h->d_cpt.p;
     sa.pl = (T*)h->d_pl.p;
     sa.evbits = (const uint32_t*)h->d_evbits.p;
-    sa.PL = h->PL; sa.M = h->M; sa.W = h->W;
+    sa.PL = h->PL; sa.M = h->M; sa.W = h->W; sa.TS = h->TS;
+    sa.tscr = (const T*)h->d_tscr.p;
     // enough threads to fill 148 SMs a few times over: split the node walk when the batch is small
     const int64_t threads_per_row = (int64_t)tiles * BLOCK_THREADS;
     int n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, h->N / 8)),
@@ -386,6 +405,43 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             sa.delta_next = delta + (size_t)((t + 1) % 3) * h->cap;
             sa.sweep_index = t;
             sa.prev_tested = prev_tested ? 1 : 0;
+            if (h->TS > 0) {
+                // dense nodes: this sweep's CPT x batch products (time-t messages and lambda_X), before
+                // the sweep kernel overwrites lambda_X in place
+                const bool timed = h->ev_dense_used < 512;
+                if (timed) {
+                    if ((int)h->ev_dense.size() < 2 * (h->ev_dense_used + 1)) {
+                        cudaEvent_t e0, e1;
+                        CU_TRY(cudaEventCreate(&e0));
+                        CU_TRY(cudaEventCreate(&e1));
+                        h->ev_dense.push_back(e0);
+                        h->ev_dense.push_back(e1);
+                    }
+                    CU_TRY(cudaEventRecord(h->ev_dense[2 * h->ev_dense_used], st));
+                }
+                DenseArgs<T> da;
+                da.jobs = (const DenseJob*)h->d_djobs.p;
+                da.dig = (const unsigned long long*)h->d_ddig.p;
+                da.arena0 = (const T*)h->d_cpt.p;
+                da.arena1 = (const T*)h->d_cpt_t.p;
+                da.pl = (const T*)h->d_pl.p;
+                da.msg_cur = sa.msg_cur;
+                da.tscr = (T*)h->d_tscr.p;
+                da.PL = h->PL; da.M = h->M; da.TS = h->TS; da.TBC = h->tb;
+                da.status = eps_mode ? (const uint8_t*)h->d_status.p : nullptr;
+                for (const bnbp_handle::DenseGroup& g : h->dgroups) {
+                    da.ytab = (const int32_t*)h->d_dytab.p + g.ytab0;
+                    cudaError_t e = launch_dense<T>(da, g.nf, dim3((unsigned)((int64_t)tiles * h->tb / DT_M), (unsigned)g.n_y),
+                                                    dense_smem_bytes(g.max_rows, sizeof(T)), st);
+                    if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("dense launch: ") + cudaGetErrorString(e));
+                    h->last_dense_launches++;
+                    h->last_kernel_launches++;
+                }
+                if (timed) {
+                    CU_TRY(cudaEventRecord(h->ev_dense[2 * h->ev_dense_used + 1], st));
+                    h->ev_dense_used++;
+                }
+            }
             if (h->run_spec) {
                 // network-specialised kernel: variant 0 plain, 1 freeze, 2 freeze + check
                 int variant = check ? 2 : (eps_mode ? 1 : 0);
@@ -505,6 +561,121 @@ int upload_cpt(bnbp_handle* h, const double* cpt, int64_t n)
     rc = h->d_pl_init.ensure(init.size() * sizeof(T));
     if (rc) return rc;
     CU_TRY(cudaMemcpy(h->d_pl_init.p, init.data(), init.size() * sizeof(T), cudaMemcpyHostToDevice));
+    if (h->cpt_t_values > 0) {
+        // arena 1: P^T [(uB,x)][uA] of every dense node, the B operand of GEMM 2 (bnbp_dense.h)
+        std::vector<T> pt((size_t)h->cpt_t_values);
+        for (int x = 0; x < h->N; ++x) {
+            if (h->dense_pt_off[x] < 0) continue;
+            const NodeMeta& nd = h->nodes[x];
+            int64_t QA = 1;
+            for (int j = 0; j < nd.dense_s; ++j) QA *= h->e_card[nd.e0 + j];
+            const int64_t cptn = (x + 1 < h->N ? h->nodes[x + 1].cpt_off : n) - nd.cpt_off;
+            const int64_t QBr = cptn / QA;
+            const double* P = cpt + nd.cpt_off;
+            T* out = pt.data() + h->dense_pt_off[x];
+            for (int64_t ua = 0; ua < QA; ++ua)
+                for (int64_t c = 0; c < QBr; ++c) out[c * QA + ua] = (T)P[ua * QBr + c];
+        }
+        rc = h->d_cpt_t.ensure(pt.size() * sizeof(T));
+        if (rc) return rc;
+        CU_TRY(cudaMemcpy(h->d_cpt_t.p, pt.data(), pt.size() * sizeof(T), cudaMemcpyHostToDevice));
+    }
+    return BNBP_OK;
+}
+
+// Dense contraction plan (bnbp_dense.h): which nodes meet the batch as matrix products, where their
+// parents are split, the GEMM job list (sorted by factor count = one launch per count), the digit
+// table that maps an operand row to its factor rows, and the slots of the per-case result tables.
+int plan_dense(bnbp_handle* h, const bnbp_flat_network* net, const std::vector<int32_t>& e_pin)
+{
+    h->djobs.clear(); h->dgroups.clear(); h->dytab.clear(); h->ddig.clear();
+    h->dense_pt_off.assign(h->N, -1);
+    h->TS = 0; h->dense_nodes = 0; h->dense_flops_per_case = 0.0; h->cpt_t_values = 0;
+    if (h->dense_min < 0) return BNBP_OK;
+    int64_t ts = 0;
+    std::vector<DenseJob> jobs;
+    std::vector<std::vector<unsigned long long>> digs;
+    auto make_digits = [&](const DenseJob& jb) {
+        const int kpad = (jb.K + DT_K - 1) / DT_K * DT_K + DT_K;       // the kernel prefetches one stage past the end
+        std::vector<unsigned long long> d((size_t)kpad);
+        std::vector<int> stride(jb.nf), base(jb.nf);
+        int st = 1, rows = 0;
+        for (int f = jb.nf - 1; f >= 0; --f) { stride[f] = st; st *= jb.f_card[f]; }
+        for (int f = 0; f < jb.nf; ++f) { base[f] = rows; rows += jb.f_card[f]; }
+        for (int kk = 0; kk < kpad; ++kk) {
+            unsigned long long v = 0;
+            for (int f = 0; f < jb.nf; ++f) {
+                const int row = kk < jb.K ? base[f] + (kk / stride[f]) % jb.f_card[f] : rows;   // rows = the zero row
+                v |= (unsigned long long)row << (8 * f);
+            }
+            d[(size_t)kk] = v;
+        }
+        return d;
+    };
+    for (int x = 0; x < h->N; ++x) {
+        NodeMeta& nd = h->nodes[x];
+        const int k = nd.k, r = nd.card;
+        const int64_t cptn = net->cpt_off[x + 1] - net->cpt_off[x];
+        if (k == 0 || cptn < h->dense_min || cptn > (int64_t)1 << 30) continue;
+        int best_s = -1;
+        int64_t best_cost = 0;
+        int64_t QA = 1;
+        int rowsA = 0, rows_all = r;
+        for (int j = 0; j < k; ++j) rows_all += h->e_card[nd.e0 + j];
+        for (int s = 1; s <= k; ++s) {
+            QA *= h->e_card[nd.e0 + s - 1];
+            rowsA += h->e_card[nd.e0 + s - 1];
+            const int rowsB = rows_all - rowsA;
+            if (s > DENSE_MAXF || k - s + 1 > DENSE_MAXF || rowsA > DENSE_MAXROWS || rowsB > DENSE_MAXROWS) continue;
+            const int64_t cost = QA + cptn / QA;              // per-case result slots: QA + QB*r
+            if (best_s < 0 || cost < best_cost) { best_s = s; best_cost = cost; }
+        }
+        if (best_s < 0 || ts + best_cost > (int64_t)1 << 30) continue;
+        const int s = best_s;
+        QA = 1;
+        for (int j = 0; j < s; ++j) QA *= h->e_card[nd.e0 + j];
+        const int64_t QBr = cptn / QA;
+        nd.dense_s = s;
+        nd.t1_off = (int32_t)ts; ts += QBr;
+        nd.t2_off = (int32_t)ts; ts += QA;
+        h->dense_pt_off[x] = h->cpt_t_values;
+        DenseJob g1;                                          // T1 = WA x P
+        memset(&g1, 0, sizeof g1);
+        g1.arena = 0; g1.b_off = nd.cpt_off; g1.K = (int32_t)QA; g1.N = (int32_t)QBr; g1.t_off = nd.t1_off; g1.nf = s;
+        for (int j = 0; j < s; ++j) { g1.f_slot[j] = e_pin[nd.e0 + j]; g1.f_card[j] = h->e_card[nd.e0 + j]; g1.n_rows += g1.f_card[j]; }
+        DenseJob g2;                                          // T2 = WB x P^T
+        memset(&g2, 0, sizeof g2);
+        g2.arena = 1; g2.b_off = h->cpt_t_values; g2.K = (int32_t)QBr; g2.N = (int32_t)QA; g2.t_off = nd.t2_off; g2.nf = k - s + 1;
+        for (int j = s; j < k; ++j) { g2.f_slot[j - s] = e_pin[nd.e0 + j]; g2.f_card[j - s] = h->e_card[nd.e0 + j]; g2.n_rows += g2.f_card[j - s]; }
+        g2.f_slot[k - s] = -(nd.pl_off + r + 1);              // lambda_X, fastest digit (x)
+        g2.f_card[k - s] = r;
+        g2.n_rows += r;
+        jobs.push_back(g1); digs.push_back(make_digits(g1));
+        jobs.push_back(g2); digs.push_back(make_digits(g2));
+        h->cpt_t_values += cptn;
+        h->dense_flops_per_case += 4.0 * (double)cptn;
+        h->dense_nodes++;
+    }
+    h->TS = (int)ts;
+    if (jobs.empty()) return BNBP_OK;
+    // one launch per factor count (and per 65535 grid rows)
+    std::vector<int> order(jobs.size());
+    for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].nf < jobs[b].nf; });
+    for (int idx : order) {
+        DenseJob jb = jobs[(size_t)idx];
+        const int ny = (jb.N + DT_N - 1) / DT_N;
+        if (h->dgroups.empty() || h->dgroups.back().nf != jb.nf || h->dgroups.back().n_y + ny > 65535)
+            h->dgroups.push_back({jb.nf, 0, (int)h->dytab.size(), 0});
+        bnbp_handle::DenseGroup& g = h->dgroups.back();
+        jb.y0 = g.n_y;
+        jb.dig_off = (int64_t)h->ddig.size();
+        h->ddig.insert(h->ddig.end(), digs[(size_t)idx].begin(), digs[(size_t)idx].end());
+        for (int y = 0; y < ny; ++y) h->dytab.push_back((int32_t)h->djobs.size());
+        g.n_y += ny;
+        g.max_rows = std::max(g.max_rows, (int)jb.n_rows);
+        h->djobs.push_back(jb);
+    }
     return BNBP_OK;
 }
 
@@ -533,6 +704,8 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         else if (!strcmp(ev, "never")) h->specialize = BNBP_SPEC_NEVER;
         else if (!strcmp(ev, "auto")) h->specialize = BNBP_SPEC_AUTO;
     }
+    h->dense_min = (opt && opt->dense_min_cpt != 0) ? opt->dense_min_cpt : 4096;
+    if (const char* ev = getenv("BNBP_DENSE_MIN")) h->dense_min = atoll(ev);   // tuning / test knob (< 0: never)
     if (h->specialize < BNBP_SPEC_AUTO || h->specialize > BNBP_SPEC_NEVER)
         return fail(BNBP_ERR_INVALID, "bnbp_options.specialize out of range");
     h->N = N;
@@ -627,6 +800,11 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
                 c_pi_out[h->nodes[u].c0 + ci] = e_pin[e];                 // U writes pi-msg here, X reads it
             }
     }
+    for (int x = 0; x < N; ++x) { h->nodes[x].dense_s = 0; h->nodes[x].t1_off = h->nodes[x].t2_off = 0; h->nodes[x].pad_ = 0; }
+    {
+        int rc = plan_dense(h, net, e_pin);
+        if (rc) return rc;
+    }
     // scratch: outer parents' messages + accumulators
     int so_max = 0;
     h->cost_prefix.assign(N + 1, 0.0);
@@ -636,7 +814,14 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         for (int j = 0; j < nd.k; ++j) { sin += e_card[nd.e0 + j]; if (j < nd.k - 1) so += e_card[nd.e0 + j]; }
         so_max = std::max(so_max, so);
         const double cptn = (double)(net->cpt_off[x + 1] - net->cpt_off[x]);
-        h->cost_prefix[x + 1] = h->cost_prefix[x] + 2.0 * (2 * nd.card + sin + nd.m * nd.card) + 0.5 * cptn +
+        // a dense node reads its per-case tables (QA + QB*r coalesced loads) instead of walking the CPT
+        double table = 0.5 * cptn;
+        if (nd.dense_s) {
+            double QA = 1.0;
+            for (int j = 0; j < nd.dense_s; ++j) QA *= e_card[nd.e0 + j];
+            table = 2.0 * (QA + cptn / QA);
+        }
+        h->cost_prefix[x + 1] = h->cost_prefix[x] + 2.0 * (2 * nd.card + sin + nd.m * nd.card) + table +
                                 (double)nd.m * nd.m * nd.card;
     }
     h->scratch_vals = 2 * so_max;
@@ -661,6 +846,10 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     {
         SpecLayout L = spec_layout(h);
         h->spec_eligible_ = spec_eligible(L, h->precision == BNBP_FP32, &h->spec_why);
+        if (h->spec_eligible_ && h->TS > 0) {
+            h->spec_eligible_ = false;
+            h->spec_why = "the dense contraction path is active for this network";
+        }
         // measured on B200 (profiles/r01c): one case per thread beats 2/4 in both precisions -- the
         // kernel is HBM-latency bound, so resident warps (registers per thread) matter more than
         // wider accesses; fp64 1.147 ms/sweep at (1,3,1), fp32 0.620 ms at (1,4,1) for 1M alarm37 cases
@@ -730,6 +919,19 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     rc = h->precision == BNBP_FP32 ? upload_cpt<float>(h.get(), net->cpt, net->cpt_off[N])
                                    : upload_cpt<double>(h.get(), net->cpt, net->cpt_off[N]);
     if (rc) return rc;
+    if (h->TS > 0) {
+        if ((rc = h->d_djobs.ensure(h->djobs.size() * sizeof(DenseJob))) || (rc = h->d_dytab.ensure(h->dytab.size() * 4)) ||
+            (rc = h->d_ddig.ensure(h->ddig.size() * 8)))
+            return rc;
+        CU_TRY(cudaMemcpy(h->d_djobs.p, h->djobs.data(), h->djobs.size() * sizeof(DenseJob), cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(h->d_dytab.p, h->dytab.data(), h->dytab.size() * 4, cudaMemcpyHostToDevice));
+        CU_TRY(cudaMemcpy(h->d_ddig.p, h->ddig.data(), h->ddig.size() * 8, cudaMemcpyHostToDevice));
+        int max_rows = 0;
+        for (const bnbp_handle::DenseGroup& g : h->dgroups) max_rows = std::max(max_rows, g.max_rows);
+        const int bytes = (int)dense_smem_bytes(max_rows, h->tsize);
+        cudaError_t e = h->precision == BNBP_FP32 ? set_dense_smem<float>(bytes) : set_dense_smem<double>(bytes);
+        if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("dense shared-memory opt-in: ") + cudaGetErrorString(e));
+    }
     if ((rc = h->d_misc.ensure(64))) return rc;
     CU_TRY(cudaMemset(h->d_misc.p, 0, 64));
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
@@ -759,6 +961,7 @@ void bnbp_destroy(bnbp_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
+                      &h->d_djobs, &h->d_dytab, &h->d_ddig, &h->d_cpt_t, &h->d_tscr,
                       &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1],
                       &h->s_out_sweeps, &h->s_out_conv})
         b->release();
@@ -770,6 +973,7 @@ void bnbp_destroy(bnbp_handle* h)
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     for (int v = 0; v < 5; ++v) spec_unload(&h->spec[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
+    for (cudaEvent_t e : h->ev_dense) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
         if (h->ev_total[i]) cudaEventDestroy(h->ev_total[i]);
         if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
@@ -850,9 +1054,10 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     if (ev->n_cases > 0 && !ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    h->last_sweep_launches = h->last_kernel_launches = 0;
+    h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = 0;
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
+    h->ev_dense_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
     if ((rc = ensure_state(h, ev->n_cases))) return rc;
@@ -896,9 +1101,10 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         if (ev->ev_off[c + 1] < ev->ev_off[c]) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    h->last_sweep_launches = h->last_kernel_launches = 0;
+    h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = 0;
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
+    h->ev_dense_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
     // Chunk pipeline: the device->host copy of chunk i (on copy_stream, out of staging buffer i&1)
@@ -1050,6 +1256,11 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->last_specialised = h->last_specialised;
     out->cases_per_tile = h->tb;
     out->spec_compile_ms = h->spec_compile_ms;
+    out->dense_nodes = h->dense_nodes;
+    out->dense_values_per_case = h->TS;
+    out->dense_flops_per_case_sweep = h->dense_flops_per_case;
+    out->last_dense_launches = h->last_dense_launches;
+    out->last_dense_ms = -1.0;
     out->last_sweep_ms = -1.0;
     out->last_total_ms = -1.0;
     if (h->total_recorded) {
@@ -1064,6 +1275,13 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
                 else ok = false;
             }
             if (ok) out->last_sweep_ms = sw;
+            double dn = 0;
+            ok = h->ev_dense_used > 0;
+            for (int i = 0; i < h->ev_dense_used; ++i) {
+                if (cudaEventElapsedTime(&ms, h->ev_dense[2 * i], h->ev_dense[2 * i + 1]) == cudaSuccess) dn += ms;
+                else ok = false;
+            }
+            if (ok) out->last_dense_ms = dn;
         }
         cudaGetLastError();
     }

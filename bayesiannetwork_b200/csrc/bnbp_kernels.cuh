@@ -25,7 +25,7 @@ namespace bnbp {
 constexpr int KMAX = 8;        // max in-degree handled by the templated recursion
 constexpr int MAX_CHUNKS = 192;
 
-struct NodeMeta {              // 48 bytes, warp-uniform
+struct NodeMeta {              // 64 bytes, warp-uniform
     int32_t card;              // r_X
     int32_t k;                 // number of parents
     int32_t m;                 // number of children
@@ -37,6 +37,12 @@ struct NodeMeta {              // 48 bytes, warp-uniform
     int64_t cpt_off;           // offset into the device CPT arena
     int32_t bel_off;           // offset of X in a row of marginals
     int32_t scr_half;          // scratch values reserved for the outer parents' messages (accumulators follow)
+    // dense contraction path (bnbp_dense.cuh): dense_s = 0 for ordinary nodes, else the split point s
+    // (parents [0,s) form group A, [s,k) group B) and the slots of the per-case tables T1 / T2
+    int32_t dense_s;
+    int32_t t1_off;            // T1[(uB,x)], QB*r slots
+    int32_t t2_off;            // T2[uA], QA slots
+    int32_t pad_;
 };
 
 template <typename T> struct SweepArgs {
@@ -49,7 +55,8 @@ template <typename T> struct SweepArgs {
     const T*        msg_cur;    // [tiles][M][TB]
     T*              msg_nxt;
     const uint32_t* evbits;     // [tiles][W][TB]
-    int32_t PL, M, W;
+    const T*        tscr;       // [tiles][TS][TB] per-case tables of the dense nodes (this sweep's GEMMs)
+    int32_t PL, M, W, TS;
     int32_t n_chunks;
     int32_t chunk_off[MAX_CHUNKS + 1];
     // convergence bookkeeping (only touched when FREEZE / CHECK)

@@ -37,26 +37,50 @@ template <typename T, int VEC, int RMAX> struct ParentCtx {
     T lam[RMAX][VEC], pacc[RMAX][VEC], mk[RMAX][VEC], lacck[RMAX][VEC];
 };
 
-template <typename T, int VEC, int RMAX>
+// SRC selects where the table comes from:
+//   SRC_CPT    the node's CPT in the device arena (warp-uniform broadcast loads)
+//   SRC_T1     a PER-CASE table T1[(uB,x)] produced by the dense contraction (bnbp_dense.cuh, GEMM 1):
+//              same recursion over the parents of group B, one coalesced load per entry
+//   SRC_T2     the per-case table T2[uA] of GEMM 2: r = 1 and lambda = 1, only lambda-messages come out
+enum { SRC_CPT = 0, SRC_T1 = 1, SRC_T2 = 2 };
+
+template <int SRC, typename T, int VEC, int RMAX>
 __device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T (&P)[VEC], int q, T (&ret)[VEC])
 {
-    const T* blk = c.cpt + (size_t)q * (size_t)(c.rk * c.r);
+    constexpr size_t STR = SRC == SRC_CPT ? 1 : (size_t)BLOCK * VEC;   // per-case tables are batch-minor
+    const int rr = SRC == SRC_T2 ? 1 : c.r;
+    const T* blk = c.cpt + (size_t)q * (size_t)(c.rk * rr) * STR;
 #pragma unroll
     for (int v = 0; v < VEC; ++v) ret[v] = T(0);
     auto body = [&](int b) {
-        const T* row = blk + b * c.r;
+        const T* row = blk + (size_t)(b * rr) * STR;
         T w[VEC], pm[VEC];
 #pragma unroll
         for (int v = 0; v < VEC; ++v) { w[v] = T(0); pm[v] = P[v] * c.mk[b][v]; }
         auto inner = [&](int x) {
-            const T p = __ldg(row + x);
+            T p[VEC];
+            if constexpr (SRC == SRC_CPT) {
+                const T pu = __ldg(row + x);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) p[v] = pu;
+            } else {
+                const Pk<T, VEC> pk = ldp<T, VEC>(row + (size_t)x * STR);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) p[v] = pk.v[v];
+            }
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
-                w[v] = fma(c.lam[x][v], p, w[v]);
-                c.pacc[x][v] = fma(p, pm[v], c.pacc[x][v]);
+                if constexpr (SRC == SRC_T2) {
+                    w[v] = p[v];
+                } else {
+                    w[v] = fma(c.lam[x][v], p[v], w[v]);
+                    c.pacc[x][v] = fma(p[v], pm[v], c.pacc[x][v]);
+                }
             }
         };
-        if constexpr (RMAX <= 8) {
+        if constexpr (SRC == SRC_T2) {
+            inner(0);
+        } else if constexpr (RMAX <= 8) {
 #pragma unroll
             for (int x = 0; x < RMAX; ++x)
                 if (x < c.r) inner(x);
@@ -78,11 +102,11 @@ __device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T 
     }
 }
 
-template <int LEVEL, int K, typename T, int VEC, int RMAX>
+template <int LEVEL, int K, int SRC, typename T, int VEC, int RMAX>
 __device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX>& c, const T (&P)[VEC], int q, T (&ret)[VEC])
 {
     if constexpr (LEVEL == K - 1) {
-        parent_leaf<T, VEC, RMAX>(c, P, q, ret);
+        parent_leaf<SRC, T, VEC, RMAX>(c, P, q, ret);
     } else {
         const int rl = c.rj[LEVEL];
 #pragma unroll
@@ -94,7 +118,7 @@ __device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX>& c, const T (
                 mv[v] = c.scr[((c.soff[LEVEL] + a) * VEC + v) * BLOCK];
                 P2[v] = P[v] * mv[v];
             }
-            parent_rec<LEVEL + 1, K, T, VEC, RMAX>(c, P2, q * rl + a, R);
+            parent_rec<LEVEL + 1, K, SRC, T, VEC, RMAX>(c, P2, q * rl + a, R);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 T* acc = &c.scr[((c.sacc_base + c.soff[LEVEL] + a) * VEC + v) * BLOCK];
@@ -105,13 +129,101 @@ __device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX>& c, const T (
     }
 }
 
-template <int K, typename T, int VEC, int RMAX>
+template <int K, int SRC, typename T, int VEC, int RMAX>
 __device__ __forceinline__ void parent_run(ParentCtx<T, VEC, RMAX>& c)
 {
     T one[VEC], ret[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) one[v] = T(1);
-    parent_rec<0, K, T, VEC, RMAX>(c, one, 0, ret);
+    parent_rec<0, K, SRC, T, VEC, RMAX>(c, one, 0, ret);
+}
+
+// One group of consecutive parents [j0, j0+kk) of a node against one table: stages their
+// pi-messages (outer ones in the scratch column, the last one in registers), runs the recursion and
+// emits the lambda-messages to exactly these parents.  An ordinary node is one group over its CPT;
+// a dense node is group A over T2 followed by group B over T1.
+template <int SRC, int KNET, typename T, int VEC, int RMAX, typename EmitMsg>
+__device__ __forceinline__ void parent_group(ParentCtx<T, VEC, RMAX>& pc, const T* table, const int32_t* ecard,
+                                             const int32_t* louts, const T* cur, T* scr, int scr_half, int kk,
+                                             int slot, EmitMsg& emit_msg)
+{
+    constexpr size_t TBC = (size_t)BLOCK * VEC;
+    pc.cpt = table;
+    pc.scr = scr;
+#pragma unroll
+    for (int x = 0; x < RMAX; ++x)
+#pragma unroll
+        for (int v = 0; v < VEC; ++v) { pc.lacck[x][v] = T(0); pc.mk[x][v] = T(0); }
+    // stage the outer parents' messages in scratch, the last parent's in registers
+    int so = 0;
+    if (kk > 1) {
+#pragma unroll
+        for (int j = 0; j < KNET - 1; ++j) {
+            if (j < kk - 1) {
+                const int rjj = ecard[j];
+                pc.rj[j] = rjj;
+                pc.soff[j] = so;
+                const T* const mp = cur + (size_t)slot * TBC;
+                for (int u = 0; u < rjj; ++u) {
+                    const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) {
+                        scr[((so + u) * VEC + v) * BLOCK] = mm.v[v];
+                        scr[((scr_half + so + u) * VEC + v) * BLOCK] = T(0);
+                    }
+                }
+                so += rjj;
+                slot += rjj;
+            }
+        }
+    }
+    pc.sacc_base = scr_half;
+    const int rk = ecard[kk - 1];
+    pc.rk = rk;
+    {
+        const T* const mp = cur + (size_t)slot * TBC;
+#pragma unroll
+        for (int u = 0; u < RMAX; ++u)
+            if (u < rk) {
+                const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
+            }
+    }
+    if (kk == 1) parent_run<1, SRC, T, VEC, RMAX>(pc);
+    else if (kk == 2) parent_run<2, SRC, T, VEC, RMAX>(pc);
+    else if constexpr (KNET > 2) {
+        if (kk == 3) parent_run<3, SRC, T, VEC, RMAX>(pc);
+        else if (kk == 4) parent_run<4, SRC, T, VEC, RMAX>(pc);
+        else if constexpr (KNET > 4) {
+            if (kk == 5) parent_run<5, SRC, T, VEC, RMAX>(pc);
+            else if (kk == 6) parent_run<6, SRC, T, VEC, RMAX>(pc);
+            else if (kk == 7) parent_run<7, SRC, T, VEC, RMAX>(pc);
+            else parent_run<8, SRC, T, VEC, RMAX>(pc);
+        }
+    }
+    // lambda-messages to the outer parents (accumulated in scratch) ...
+    int so2 = 0;
+    for (int j = 0; j < kk - 1; ++j) {
+        const int rjj = ecard[j];
+        T val[RMAX][VEC];
+        if constexpr (RMAX <= 8) {
+#pragma unroll
+            for (int u = 0; u < RMAX; ++u)
+                if (u < rjj) {
+#pragma unroll
+                    for (int v = 0; v < VEC; ++v) val[u][v] = scr[((scr_half + so2 + u) * VEC + v) * BLOCK];
+                }
+        } else {
+            for (int u = 0; u < rjj; ++u)
+#pragma unroll
+                for (int v = 0; v < VEC; ++v) val[u][v] = scr[((scr_half + so2 + u) * VEC + v) * BLOCK];
+        }
+        emit_msg(louts[j], val, rjj);
+        so2 += rjj;
+    }
+    // ... and to the last parent (accumulated in registers)
+    emit_msg(louts[kk - 1], pc.lacck, rk);
 }
 
 template <typename T> __device__ __forceinline__ T recip(T s) { return T(1) / s; }
@@ -343,95 +455,48 @@ sweep_kernel(const SweepArgs<T> a)
         }
 
         // ---- parent side: pi_X (:174-200) and lambda-messages X->parents (:240-266) ---------------
-        pc.cpt = a.cpt + nd.cpt_off;
         pc.r = r;
-        pc.scr = scr;
 #pragma unroll
         for (int x = 0; x < RMAX; ++x)
 #pragma unroll
-            for (int v = 0; v < VEC; ++v) { pc.pacc[x][v] = T(0); pc.lacck[x][v] = T(0); pc.mk[x][v] = T(0); }
+            for (int v = 0; v < VEC; ++v) pc.pacc[x][v] = T(0);
         if (k == 0) {
             // root: all_combination_pattern calls the body once with the empty condition (:280-283)
+            const T* const prior = a.cpt + nd.cpt_off;
 #pragma unroll
             for (int x = 0; x < RMAX; ++x)
                 if (x < r) {
-                    const T p = __ldg(pc.cpt + x);
+                    const T p = __ldg(prior + x);
 #pragma unroll
                     for (int v = 0; v < VEC; ++v) pc.pacc[x][v] = p;
                 }
+        } else if (nd.dense_s == 0) {
+            parent_group<SRC_CPT, KNET>(pc, a.cpt + nd.cpt_off, a.e_card + nd.e0, a.e_lam_out + nd.e0, cur, scr,
+                                        nd.scr_half, k, nd.pin_off, emit_msg);
         } else {
+            // dense node: the CPT already met the batch in two matrix products (bnbp_dense.cuh).
+            // Group A = parents [0, s) against T2[uA]; group B = parents [s, k) against T1[(uB,x)].
+            const int s = nd.dense_s;
+            const T* const tsc = a.tscr + ((size_t)tile * a.TS) * TBC + lane0;
             const int32_t* const ecard = a.e_card + nd.e0;
-            const int32_t* const louts = a.e_lam_out + nd.e0;
-            // stage the outer parents' messages in scratch, the last parent's in registers
-            int so = 0, slot = nd.pin_off;
-            if (k > 1) {
+            parent_group<SRC_T2, KNET>(pc, tsc + (size_t)nd.t2_off * TBC, ecard, a.e_lam_out + nd.e0, cur, scr,
+                                       nd.scr_half, s, nd.pin_off, emit_msg);
+            const T* const t1 = tsc + (size_t)nd.t1_off * TBC;
+            if (s == k) {
+                // no parent left in group B: T1[x] is the unnormalised pi_X
 #pragma unroll
-                for (int j = 0; j < KNET - 1; ++j) {
-                    if (j < k - 1) {
-                        const int rjj = ecard[j];
-                        pc.rj[j] = rjj;
-                        pc.soff[j] = so;
-                        const T* const mp = cur + (size_t)slot * TBC;
-                        for (int u = 0; u < rjj; ++u) {
-                            const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
+                for (int x = 0; x < RMAX; ++x)
+                    if (x < r) {
+                        const Pk<T, VEC> pk = ldp<T, VEC>(t1 + (size_t)x * TBC);
 #pragma unroll
-                            for (int v = 0; v < VEC; ++v) {
-                                scr[((so + u) * VEC + v) * BLOCK] = mm.v[v];
-                                scr[((nd.scr_half + so + u) * VEC + v) * BLOCK] = T(0);
-                            }
-                        }
-                        so += rjj;
-                        slot += rjj;
+                        for (int v = 0; v < VEC; ++v) pc.pacc[x][v] = pk.v[v];
                     }
-                }
+            } else {
+                int slot = nd.pin_off;
+                for (int j = 0; j < s; ++j) slot += ecard[j];
+                parent_group<SRC_T1, KNET>(pc, t1, ecard + s, a.e_lam_out + nd.e0 + s, cur, scr, nd.scr_half, k - s,
+                                           slot, emit_msg);
             }
-            pc.sacc_base = nd.scr_half;
-            const int rk = ecard[k - 1];
-            pc.rk = rk;
-            {
-                const T* const mp = cur + (size_t)slot * TBC;
-#pragma unroll
-                for (int u = 0; u < RMAX; ++u)
-                    if (u < rk) {
-                        const Pk<T, VEC> mm = ldp<T, VEC>(mp + u * TBC);
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
-                    }
-            }
-            if (k == 1) parent_run<1, T, VEC, RMAX>(pc);
-            else if (k == 2) parent_run<2, T, VEC, RMAX>(pc);
-            else if constexpr (KNET > 2) {
-                if (k == 3) parent_run<3, T, VEC, RMAX>(pc);
-                else if (k == 4) parent_run<4, T, VEC, RMAX>(pc);
-                else if constexpr (KNET > 4) {
-                    if (k == 5) parent_run<5, T, VEC, RMAX>(pc);
-                    else if (k == 6) parent_run<6, T, VEC, RMAX>(pc);
-                    else if (k == 7) parent_run<7, T, VEC, RMAX>(pc);
-                    else parent_run<8, T, VEC, RMAX>(pc);
-                }
-            }
-            // lambda-messages to the outer parents (accumulated in scratch) ...
-            int so2 = 0;
-            for (int j = 0; j < k - 1; ++j) {
-                const int rjj = ecard[j];
-                T val[RMAX][VEC];
-                if constexpr (RMAX <= 8) {
-#pragma unroll
-                    for (int u = 0; u < RMAX; ++u)
-                        if (u < rjj) {
-#pragma unroll
-                            for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
-                        }
-                } else {
-                    for (int u = 0; u < rjj; ++u)
-#pragma unroll
-                        for (int v = 0; v < VEC; ++v) val[u][v] = scr[((nd.scr_half + so2 + u) * VEC + v) * BLOCK];
-                }
-                emit_msg(louts[j], val, rjj);
-                so2 += rjj;
-            }
-            // ... and to the last parent (accumulated in registers)
-            emit_msg(louts[k - 1], pc.lacck, rk);
         }
         // pi_X = normalize(acc) unless X is evidence (:177) or the case is frozen
         emit_node(pX, pc.pacc, pi, upd, r);

@@ -199,6 +199,8 @@ def main():
     ap.add_argument("--epsilon", type=float, default=0.0,
                     help="> 0: time-to-solution mode (reference stopping rule, delta < epsilon per case, "
                          "--sweeps = cap, default 200); value counts the sweeps actually executed")
+    ap.add_argument("--dense-min", type=int, default=0,
+                    help="CPT entries from which a node takes the dense contraction path (0 = library default, -1 = never)")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -231,7 +233,8 @@ def main():
     n, V = ev.n_cases, net.belief_values
     tdtype = torch.float64 if args.precision == "fp64" else torch.float32
     tsize = 8 if args.precision == "fp64" else 4
-    bp = BeliefPropagation(net, args.precision, device=local_rank, specialize=args.specialize)
+    bp = BeliefPropagation(net, args.precision, device=local_rank, specialize=args.specialize,
+                           dense_min_cpt=args.dense_min)
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
@@ -276,11 +279,15 @@ def main():
     ms = e0.elapsed_time(e1)
     st = bp.stats()
     launches_per_step = int(st["last_kernel_launches"])
-    sweep_ms_per_launch = st["last_sweep_ms"] / max(1, st["last_sweep_launches"])
+    # the library's own CUDA events: around all sweeps of the last step, and around the dense
+    # contraction launches inside them (nodes with large CPTs; 0 for the other workloads)
+    dense_ms = max(0.0, st["last_dense_ms"]) if st["dense_nodes"] else 0.0
+    sweep_ms_per_launch = (st["last_sweep_ms"] - dense_ms) / max(1, st["last_sweep_launches"])
+    dense_ms_per_sweep = dense_ms / max(1, st["last_sweep_launches"])
     if world > 1:
-        t = torch.tensor([ms, sweep_ms_per_launch], dtype=torch.float64, device=dev)
+        t = torch.tensor([ms, sweep_ms_per_launch, dense_ms_per_sweep], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, sweep_ms_per_launch = float(t[0]), float(t[1])
+        ms, sweep_ms_per_launch, dense_ms_per_sweep = float(t[0]), float(t[1]), float(t[2])
     clocks = sampler.stop() if sampler else None
     eps_info = None
     if args.epsilon > 0:
@@ -320,6 +327,20 @@ def main():
                 "traffic": traffic, "kernel": "bnbp_spec_sweep" if st["last_specialised"] else "sweep_kernel",
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_case_sweep": 2 * S * tsize, "ms_per_launch": sweep_ms_per_launch}
+
+    dense = None
+    if st["dense_nodes"] and dense_ms_per_sweep > 0 and not eps_info:
+        # CUDA-core contraction (fp64 parity needs fp64 products): nominal B200 vector peaks
+        # 2 x 148 SMs x 1.965 GHz x (64 fp64 | 128 fp32) lanes
+        pk = 37.2 if args.precision == "fp64" else 74.4
+        tf = st["dense_flops_per_case_sweep"] * n / (dense_ms_per_sweep * 1e-3) / 1e12
+        dense = {"kernel": "dense_gemm_kernel", "nodes": int(st["dense_nodes"]),
+                 "flops_per_case_sweep": st["dense_flops_per_case_sweep"], "ms_per_sweep": dense_ms_per_sweep,
+                 "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
+                 "peak_source": "nominal CUDA-core FMA peak at 1965 MHz (fp64 64, fp32 128 lanes per SM)",
+                 "table_values_per_case": int(st["dense_values_per_case"]),
+                 "launches_per_sweep": int(st["last_dense_launches"]) // max(1, int(st["last_sweep_launches"])),
+                 "share_of_sweep_time": dense_ms_per_sweep / (dense_ms_per_sweep + sweep_ms_per_launch)}
 
     # ---- end to end through the host-buffer C ABI (pinned host memory both ways) ----------------------
     e2e = None
@@ -390,7 +411,7 @@ def main():
                        "cases_per_tile": int(st["cases_per_tile"]),
                        "l2": f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
                              f"of per-case state per GPU vs 126 MB"},
-            "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e,
+            "roofline": roofline, "dense": dense, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
         }
         print(json.dumps(line), flush=True)

@@ -53,7 +53,13 @@ enum { BNBP_FP64 = 0, BNBP_FP32 = 1 };
  * at run time (NVRTC, sm_100a; cubins cached on disk) in which cardinalities, slot offsets and the
  * CPT arena are compile-time constants.  AUTO specialises eligible networks (small enough to
  * unroll, CPT arena <= 60 KB of constant bank) once a batch has >= 4096 cases.  Both are GPU
- * paths with identical semantics; neither is a CPU fallback. */
+ * paths with identical semantics; neither is a CPU fallback.
+ *
+ * Independently of the family, nodes with LARGE CPTs (>= bnbp_options.dense_min_cpt entries, e.g. the
+ * 32^4-entry tables of a card-32 node with 3 parents) take the dense contraction path: their CPT
+ * is multiplied with the whole batch as two matrix products per sweep (csrc/bnbp_dense.cuh) and the
+ * sweep kernel finishes from the per-case result tables.  Networks with such nodes are not
+ * specialised. */
 enum { BNBP_SPEC_AUTO = 0, BNBP_SPEC_ALWAYS = 1, BNBP_SPEC_NEVER = 2 };
 
 /* Flat (CSR) description of a discrete Bayesian network.
@@ -78,7 +84,9 @@ typedef struct bnbp_options {
     int32_t device;             /* CUDA device ordinal; -1 = current device                     */
     int64_t max_resident_cases; /* cases kept in HBM at once (0 = pick from free memory)         */
     int32_t specialize;         /* BNBP_SPEC_AUTO (default) / ALWAYS (error if impossible) / NEVER */
-    int32_t reserved[7];
+    int32_t dense_min_cpt;      /* nodes whose CPT has >= this many entries meet the batch as matrix
+                                   products (dense contraction path); 0 = default 4096, < 0 = never  */
+    int32_t reserved[6];
 } bnbp_options;
 
 /* Evidence for a batch, CSR over cases.  Entry e of case c (ev_off[c] <= e < ev_off[c+1])
@@ -121,7 +129,11 @@ typedef struct bnbp_stats {
     int64_t last_specialised;        /* 1 if the last run used the network-specialised sweep kernel */
     int64_t cases_per_tile;          /* 128 x cases per thread of the kernel family of the last run */
     double  spec_compile_ms;         /* NVRTC time spent by this handle (0 when served by the cache) */
-    int64_t reserved[5];
+    int64_t dense_nodes;             /* nodes on the dense contraction path                       */
+    int64_t dense_values_per_case;   /* per-case slots of their result tables T1/T2 (HBM scratch) */
+    double  dense_flops_per_case_sweep; /* 4 * sum |CPT| over the dense nodes                    */
+    int64_t last_dense_launches;     /* dense-contraction launches of the last run               */
+    double  last_dense_ms;           /* device time of (up to the first 512 sweeps') dense launches */
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;
