@@ -93,12 +93,13 @@ struct bnbp_handle {
     int last_specialised = 0;
     double spec_compile_ms = 0.0;
     // dense contraction path (bnbp_dense.h): nodes whose CPT has >= dense_min entries
-    int64_t dense_min = 4096;          // < 0: never
+    int64_t dense_min = 256;           // < 0: never
+    bool dense_mma = true;             // fp64: DMMA (tensor pipe) instead of DFMA for the products
     int TS = 0;                        // per-case slots of the contraction scratch (T1 / T2 tables)
     int dense_nodes = 0;
     double dense_flops_per_case = 0.0; // 4 * sum |CPT| over the dense nodes, per sweep
     std::vector<DenseJob> djobs;       // sorted by factor count
-    struct DenseGroup { int nf, n_y, ytab0, max_rows; };
+    struct DenseGroup { int nf, tnt, n_y, ytab0, max_rows; };
     std::vector<DenseGroup> dgroups;   // one launch each
     std::vector<int32_t> dytab;
     std::vector<unsigned long long> ddig;
@@ -431,8 +432,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 da.status = eps_mode ? (const uint8_t*)h->d_status.p : nullptr;
                 for (const bnbp_handle::DenseGroup& g : h->dgroups) {
                     da.ytab = (const int32_t*)h->d_dytab.p + g.ytab0;
-                    cudaError_t e = launch_dense<T>(da, g.nf, dim3((unsigned)((int64_t)tiles * h->tb / DT_M), (unsigned)g.n_y),
-                                                    dense_smem_bytes(g.max_rows, sizeof(T)), st);
+                    cudaError_t e = launch_dense<T>(da, g.nf, g.tnt, h->dense_mma, dim3((unsigned)((int64_t)tiles * h->tb / DT_M), (unsigned)g.n_y),
+                                                    dense_smem_bytes(g.max_rows, g.tnt, sizeof(T)), st);
                     if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("dense launch: ") + cudaGetErrorString(e));
                     h->last_dense_launches++;
                     h->last_kernel_launches++;
@@ -661,12 +662,16 @@ int plan_dense(bnbp_handle* h, const bnbp_flat_network* net, const std::vector<i
     // one launch per factor count (and per 65535 grid rows)
     std::vector<int> order(jobs.size());
     for (size_t i = 0; i < order.size(); ++i) order[i] = (int)i;
-    std::stable_sort(order.begin(), order.end(), [&](int a, int b) { return jobs[a].nf < jobs[b].nf; });
+    std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
+        return std::make_pair(jobs[a].nf, -dense_tnt(jobs[a].N)) < std::make_pair(jobs[b].nf, -dense_tnt(jobs[b].N));
+    });
     for (int idx : order) {
         DenseJob jb = jobs[(size_t)idx];
-        const int ny = (jb.N + DT_N - 1) / DT_N;
-        if (h->dgroups.empty() || h->dgroups.back().nf != jb.nf || h->dgroups.back().n_y + ny > 65535)
-            h->dgroups.push_back({jb.nf, 0, (int)h->dytab.size(), 0});
+        const int tnt = dense_tnt(jb.N);
+        const int ny = (jb.N + 16 * tnt - 1) / (16 * tnt);
+        if (h->dgroups.empty() || h->dgroups.back().nf != jb.nf || h->dgroups.back().tnt != tnt ||
+            h->dgroups.back().n_y + ny > 65535)
+            h->dgroups.push_back({jb.nf, tnt, 0, (int)h->dytab.size(), 0});
         bnbp_handle::DenseGroup& g = h->dgroups.back();
         jb.y0 = g.n_y;
         jb.dig_off = (int64_t)h->ddig.size();
@@ -704,7 +709,8 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         else if (!strcmp(ev, "never")) h->specialize = BNBP_SPEC_NEVER;
         else if (!strcmp(ev, "auto")) h->specialize = BNBP_SPEC_AUTO;
     }
-    h->dense_min = (opt && opt->dense_min_cpt != 0) ? opt->dense_min_cpt : 4096;
+    h->dense_min = (opt && opt->dense_min_cpt != 0) ? opt->dense_min_cpt : 256;
+    if (const char* ev = getenv("BNBP_DENSE_MMA")) h->dense_mma = atoi(ev) != 0;   // tuning knob: 0 = DFMA products
     if (const char* ev = getenv("BNBP_DENSE_MIN")) h->dense_min = atoll(ev);   // tuning / test knob (< 0: never)
     if (h->specialize < BNBP_SPEC_AUTO || h->specialize > BNBP_SPEC_NEVER)
         return fail(BNBP_ERR_INVALID, "bnbp_options.specialize out of range");
@@ -802,6 +808,15 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     }
     for (int x = 0; x < N; ++x) { h->nodes[x].dense_s = 0; h->nodes[x].t1_off = h->nodes[x].t2_off = 0; h->nodes[x].pad_ = 0; }
     {
+        // Small networks keep the network-specialised kernel (CPT in the constant bank, everything
+        // unrolled): the dense path only takes over by default where specialisation is impossible.
+        // An explicit threshold (option or BNBP_DENSE_MIN) is honoured as given.
+        h->cpt_values = net->cpt_off[N];
+        const bool explicit_dense = (opt && opt->dense_min_cpt != 0) || getenv("BNBP_DENSE_MIN") != nullptr;
+        std::string why;
+        if (!explicit_dense && h->specialize != BNBP_SPEC_NEVER &&
+            spec_eligible(spec_layout(h), h->precision == BNBP_FP32, &why))
+            h->dense_min = -1;
         int rc = plan_dense(h, net, e_pin);
         if (rc) return rc;
     }
@@ -928,7 +943,7 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
         CU_TRY(cudaMemcpy(h->d_ddig.p, h->ddig.data(), h->ddig.size() * 8, cudaMemcpyHostToDevice));
         int max_rows = 0;
         for (const bnbp_handle::DenseGroup& g : h->dgroups) max_rows = std::max(max_rows, g.max_rows);
-        const int bytes = (int)dense_smem_bytes(max_rows, h->tsize);
+        const int bytes = (int)dense_smem_bytes(max_rows, 8, h->tsize);
         cudaError_t e = h->precision == BNBP_FP32 ? set_dense_smem<float>(bytes) : set_dense_smem<double>(bytes);
         if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("dense shared-memory opt-in: ") + cudaGetErrorString(e));
     }

@@ -71,7 +71,7 @@ class BeliefPropagation:
         self._h = C.c_void_p()
         fn = _net_c(net)
         # dense_min_cpt: CPT size from which a node takes the dense contraction path (0 = default
-        # 4096 entries, < 0 = never); see include/bnbp.h
+        # 256 entries, < 0 = never); see include/bnbp.h
         opt = _capi.OptionsC(self.precision, device, max_resident_cases, SPECIALIZE[specialize], int(dense_min_cpt))
         _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
 

@@ -85,7 +85,7 @@ typedef struct bnbp_options {
     int64_t max_resident_cases; /* cases kept in HBM at once (0 = pick from free memory)         */
     int32_t specialize;         /* BNBP_SPEC_AUTO (default) / ALWAYS (error if impossible) / NEVER */
     int32_t dense_min_cpt;      /* nodes whose CPT has >= this many entries meet the batch as matrix
-                                   products (dense contraction path); 0 = default 4096, < 0 = never  */
+                                   products (dense contraction path); 0 = default 256, < 0 = never  */
     int32_t reserved[6];
 } bnbp_options;
 
