@@ -19,6 +19,7 @@ SPEC_EMBED = os.path.join(CSRC, "bnbp_spec_embed.inc")   # ... from this generat
 HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_sweep.cuh"),
            os.path.join(CSRC, "bnbp_variants.h"), os.path.join(CSRC, "bnbp_jit.h"), SPEC_SRC,
            os.path.join(CSRC, "bnbp_dense.h"), os.path.join(CSRC, "bnbp_dense.cuh"),
+           os.path.join(CSRC, "bnbp_dense_tc.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
 
 
@@ -61,7 +62,8 @@ def _env():
 def _units():
     units = [(os.path.join(CSRC, "bnbp_api.cu"), os.path.join(OBJDIR, "bnbp_api.o"), []),
              (os.path.join(CSRC, "bnbp_jit.cu"), os.path.join(OBJDIR, "bnbp_jit.o"), []),
-             (os.path.join(CSRC, "bnbp_dense_inst.cu"), os.path.join(OBJDIR, "bnbp_dense.o"), [])]
+             (os.path.join(CSRC, "bnbp_dense_inst.cu"), os.path.join(OBJDIR, "bnbp_dense.o"), []),
+             (os.path.join(CSRC, "bnbp_dense_tc_inst.cu"), os.path.join(OBJDIR, "bnbp_dense_tc.o"), [])]
     for t, v, r, k in sweep_variants():
         units.append((os.path.join(CSRC, "bnbp_sweep_inst.cu"),
                       os.path.join(OBJDIR, f"sweep_{t}_v{v}_r{r}_k{k}.o"),

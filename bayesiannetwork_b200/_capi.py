@@ -24,7 +24,8 @@ class FlatNetworkC(C.Structure):
 
 class OptionsC(C.Structure):
     _fields_ = [("precision", C.c_int32), ("device", C.c_int32), ("max_resident_cases", C.c_int64),
-                ("specialize", C.c_int32), ("dense_min_cpt", C.c_int32), ("reserved", C.c_int32 * 6)]
+                ("specialize", C.c_int32), ("dense_min_cpt", C.c_int32), ("dense_tensor", C.c_int32),
+                ("reserved", C.c_int32 * 5)]
 
 
 class EvidenceC(C.Structure):
@@ -46,7 +47,8 @@ class StatsC(C.Structure):
                 ("resident_cases", C.c_int64), ("last_specialised", C.c_int64), ("cases_per_tile", C.c_int64),
                 ("spec_compile_ms", C.c_double), ("dense_nodes", C.c_int64), ("dense_values_per_case", C.c_int64),
                 ("dense_flops_per_case_sweep", C.c_double), ("last_dense_launches", C.c_int64),
-                ("last_dense_ms", C.c_double)]
+                ("last_dense_ms", C.c_double), ("dense_tensor_jobs", C.c_int64),
+                ("dense_tensor_flops_per_case_sweep", C.c_double), ("last_dense_tensor_launches", C.c_int64)]
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",

@@ -7,6 +7,7 @@
 #include "bnbp_variants.h"
 #include "bnbp_jit.h"
 #include "bnbp_dense.h"
+#include "bnbp_dense_tc.cuh"
 
 #include <algorithm>
 #include <cmath>
@@ -106,6 +107,17 @@ struct bnbp_handle {
     std::vector<int64_t> dense_pt_off; // per node: offset of the transposed CPT copy in arena 1 (-1: not dense)
     int64_t cpt_t_values = 0;
     DevBuf d_djobs, d_dytab, d_ddig, d_cpt_t, d_tscr;
+    // tensor-core variant of the products (bnbp_dense_tc.cuh), fp32 handles
+    int dense_tc = 0;                  // bnbp_options.dense_tensor: 0 default thresholds, 1 every product, -1 never
+    struct TcGroup { int n_y, ytab0, max_rows, stages; };
+    std::vector<TcGroup> tcgroups;     // one launch each
+    struct TcPack { int64_t src_off, sk, sn, out_off; int K, N; };
+    std::vector<TcPack> tcpack;        // how each tensor-core job's B operand is cut out of the CPT arena
+    int64_t tc_values = 0;             // floats of the pre-tiled hi/lo arena
+    int dense_tc_jobs = 0;
+    double dense_tc_flops_per_case = 0.0;
+    int64_t last_dense_tc_launches = 0;
+    DevBuf d_cpt_tc;
     std::vector<cudaEvent_t> ev_dense; // pairs around the dense launches of a sweep
     int ev_dense_used = 0;
     int64_t last_dense_launches = 0;
@@ -438,6 +450,26 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                     h->last_dense_launches++;
                     h->last_kernel_launches++;
                 }
+                if constexpr (sizeof(T) == 4) {
+                    // tensor-core products (tcgen05, 3xTF32): 256 cases x 256 columns per CTA
+                    DenseTcArgs ta;
+                    ta.jobs = da.jobs; ta.dig = da.dig;
+                    ta.arena_tc = (const float*)h->d_cpt_tc.p;
+                    ta.pl = (const float*)da.pl; ta.msg_cur = (const float*)da.msg_cur; ta.tscr = (float*)da.tscr;
+                    ta.PL = da.PL; ta.M = da.M; ta.TS = da.TS; ta.TBC = da.TBC;
+                    ta.n_cases = (int64_t)tiles * h->tb;
+                    ta.status = da.status;
+                    for (const bnbp_handle::TcGroup& g : h->tcgroups) {
+                        ta.ytab = (const int32_t*)h->d_dytab.p + g.ytab0;
+                        ta.stages = g.stages;
+                        cudaError_t e = launch_dense_tc(ta, dim3((unsigned)((ta.n_cases + TC_M - 1) / TC_M), (unsigned)g.n_y),
+                                                        tc_smem_bytes(g.max_rows, g.stages), st);
+                        if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("tensor-core dense launch: ") + cudaGetErrorString(e));
+                        h->last_dense_launches++;
+                        h->last_dense_tc_launches++;
+                        h->last_kernel_launches++;
+                    }
+                }
                 if (timed) {
                     CU_TRY(cudaEventRecord(h->ev_dense[2 * h->ev_dense_used + 1], st));
                     h->ev_dense_used++;
@@ -581,6 +613,15 @@ int upload_cpt(bnbp_handle* h, const double* cpt, int64_t n)
         if (rc) return rc;
         CU_TRY(cudaMemcpy(h->d_cpt_t.p, pt.data(), pt.size() * sizeof(T), cudaMemcpyHostToDevice));
     }
+    if (h->tc_values > 0) {
+        // tensor-core jobs: B operands split hi/lo and pre-tiled into the MMA's shared-memory image
+        std::vector<float> tc((size_t)h->tc_values);
+        for (const bnbp_handle::TcPack& pk : h->tcpack)
+            tc_pack_job(tc.data() + pk.out_off, cpt + pk.src_off, pk.K, pk.N, pk.sk, pk.sn);
+        rc = h->d_cpt_tc.ensure(tc.size() * sizeof(float));
+        if (rc) return rc;
+        CU_TRY(cudaMemcpy(h->d_cpt_tc.p, tc.data(), tc.size() * sizeof(float), cudaMemcpyHostToDevice));
+    }
     return BNBP_OK;
 }
 
@@ -590,9 +631,24 @@ int upload_cpt(bnbp_handle* h, const double* cpt, int64_t n)
 int plan_dense(bnbp_handle* h, const bnbp_flat_network* net, const std::vector<int32_t>& e_pin)
 {
     h->djobs.clear(); h->dgroups.clear(); h->dytab.clear(); h->ddig.clear();
+    h->tcgroups.clear(); h->tcpack.clear();
+    h->tc_values = 0; h->dense_tc_jobs = 0; h->dense_tc_flops_per_case = 0.0;
     h->dense_pt_off.assign(h->N, -1);
     h->TS = 0; h->dense_nodes = 0; h->dense_flops_per_case = 0.0; h->cpt_t_values = 0;
     if (h->dense_min < 0) return BNBP_OK;
+    // which products run on the tensor cores (fp32 handles): worth a 256 x 256 CTA tile, factor rows
+    // fit next to >= 2 operand stages, pre-tiled arena within 16 GB
+    constexpr size_t TC_SMEM_LIMIT = 227 * 1024;                 // opt-in shared memory per CTA, sm_100
+    int tc_min_k = 32, tc_min_n = 128;
+    if (const char* ev = getenv("BNBP_TC_MIN_K")) tc_min_k = atoi(ev);
+    if (const char* ev = getenv("BNBP_TC_MIN_N")) tc_min_n = atoi(ev);
+    auto tc_ok = [&](const DenseJob& j) {
+        if (h->dense_tc < 0 || h->precision != BNBP_FP32) return false;
+        if (tc_stages_for(j.n_rows, TC_SMEM_LIMIT) < 2) return false;
+        if (h->tc_values + tc_job_floats(j.K, j.N) > ((int64_t)1 << 32)) return false;
+        return h->dense_tc > 0 || (j.K >= tc_min_k && j.N >= tc_min_n);
+    };
+    std::vector<int> tc_of;                                       // per job: index into tcpack or -1
     int64_t ts = 0;
     std::vector<DenseJob> jobs;
     std::vector<std::vector<unsigned long long>> digs;
@@ -639,21 +695,40 @@ int plan_dense(bnbp_handle* h, const bnbp_flat_network* net, const std::vector<i
         nd.dense_s = s;
         nd.t1_off = (int32_t)ts; ts += QBr;
         nd.t2_off = (int32_t)ts; ts += QA;
-        h->dense_pt_off[x] = h->cpt_t_values;
         DenseJob g1;                                          // T1 = WA x P
         memset(&g1, 0, sizeof g1);
         g1.arena = 0; g1.b_off = nd.cpt_off; g1.K = (int32_t)QA; g1.N = (int32_t)QBr; g1.t_off = nd.t1_off; g1.nf = s;
         for (int j = 0; j < s; ++j) { g1.f_slot[j] = e_pin[nd.e0 + j]; g1.f_card[j] = h->e_card[nd.e0 + j]; g1.n_rows += g1.f_card[j]; }
         DenseJob g2;                                          // T2 = WB x P^T
         memset(&g2, 0, sizeof g2);
-        g2.arena = 1; g2.b_off = h->cpt_t_values; g2.K = (int32_t)QBr; g2.N = (int32_t)QA; g2.t_off = nd.t2_off; g2.nf = k - s + 1;
+        g2.arena = 1; g2.b_off = 0; g2.K = (int32_t)QBr; g2.N = (int32_t)QA; g2.t_off = nd.t2_off; g2.nf = k - s + 1;
         for (int j = s; j < k; ++j) { g2.f_slot[j - s] = e_pin[nd.e0 + j]; g2.f_card[j - s] = h->e_card[nd.e0 + j]; g2.n_rows += g2.f_card[j - s]; }
         g2.f_slot[k - s] = -(nd.pl_off + r + 1);              // lambda_X, fastest digit (x)
         g2.f_card[k - s] = r;
         g2.n_rows += r;
-        jobs.push_back(g1); digs.push_back(make_digits(g1));
-        jobs.push_back(g2); digs.push_back(make_digits(g2));
-        h->cpt_t_values += cptn;
+        for (int which = 0; which < 2; ++which) {
+            DenseJob& g = which == 0 ? g1 : g2;
+            if (tc_ok(g)) {
+                // B[k][n]: GEMM 1 reads the reference layout P[uA][(uB,x)] as is, GEMM 2 reads it transposed
+                bnbp_handle::TcPack pk;
+                pk.src_off = nd.cpt_off; pk.K = g.K; pk.N = g.N; pk.out_off = h->tc_values;
+                pk.sk = which == 0 ? g.N : 1; pk.sn = which == 0 ? 1 : g.K;
+                g.arena = 2; g.b_off = h->tc_values;
+                h->tc_values += tc_job_floats(g.K, g.N);
+                tc_of.push_back((int)h->tcpack.size());
+                h->tcpack.push_back(pk);
+                h->dense_tc_jobs++;
+                h->dense_tc_flops_per_case += 2.0 * (double)g.K * (double)g.N;
+            } else {
+                tc_of.push_back(-1);
+                if (which == 1) {                             // CUDA-core GEMM 2 reads a transposed copy (arena 1)
+                    h->dense_pt_off[x] = h->cpt_t_values;
+                    g.b_off = h->cpt_t_values;
+                    h->cpt_t_values += cptn;
+                }
+            }
+            jobs.push_back(g); digs.push_back(make_digits(g));
+        }
         h->dense_flops_per_case += 4.0 * (double)cptn;
         h->dense_nodes++;
     }
@@ -665,7 +740,24 @@ int plan_dense(bnbp_handle* h, const bnbp_flat_network* net, const std::vector<i
     std::stable_sort(order.begin(), order.end(), [&](int a, int b) {
         return std::make_pair(jobs[a].nf, -dense_tnt(jobs[a].N)) < std::make_pair(jobs[b].nf, -dense_tnt(jobs[b].N));
     });
+    for (int idx : order) {                                   // tensor-core jobs: one launch (nf is a run-time loop there)
+        if (tc_of[(size_t)idx] < 0) continue;
+        DenseJob jb = jobs[(size_t)idx];
+        const int ny = (jb.N + TC_N - 1) / TC_N;
+        if (h->tcgroups.empty() || h->tcgroups.back().n_y + ny > 65535)
+            h->tcgroups.push_back({0, (int)h->dytab.size(), 0, 0});
+        bnbp_handle::TcGroup& g = h->tcgroups.back();
+        jb.y0 = g.n_y;
+        jb.dig_off = (int64_t)h->ddig.size();
+        h->ddig.insert(h->ddig.end(), digs[(size_t)idx].begin(), digs[(size_t)idx].end());
+        for (int y = 0; y < ny; ++y) h->dytab.push_back((int32_t)h->djobs.size());
+        g.n_y += ny;
+        g.max_rows = std::max(g.max_rows, (int)jb.n_rows);
+        g.stages = tc_stages_for(g.max_rows, TC_SMEM_LIMIT);
+        h->djobs.push_back(jb);
+    }
     for (int idx : order) {
+        if (tc_of[(size_t)idx] >= 0) continue;
         DenseJob jb = jobs[(size_t)idx];
         const int tnt = dense_tnt(jb.N);
         const int ny = (jb.N + 16 * tnt - 1) / (16 * tnt);
@@ -710,6 +802,8 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         else if (!strcmp(ev, "auto")) h->specialize = BNBP_SPEC_AUTO;
     }
     h->dense_min = (opt && opt->dense_min_cpt != 0) ? opt->dense_min_cpt : 256;
+    h->dense_tc = opt ? opt->dense_tensor : 0;
+    if (const char* ev = getenv("BNBP_DENSE_TC")) h->dense_tc = atoi(ev);      // tuning / test knob: -1 never, 1 every product
     if (const char* ev = getenv("BNBP_DENSE_MMA")) h->dense_mma = atoi(ev) != 0;   // tuning knob: 0 = DFMA products
     if (const char* ev = getenv("BNBP_DENSE_MIN")) h->dense_min = atoll(ev);   // tuning / test knob (< 0: never)
     if (h->specialize < BNBP_SPEC_AUTO || h->specialize > BNBP_SPEC_NEVER)
@@ -946,6 +1040,10 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
         const int bytes = (int)dense_smem_bytes(max_rows, 8, h->tsize);
         cudaError_t e = h->precision == BNBP_FP32 ? set_dense_smem<float>(bytes) : set_dense_smem<double>(bytes);
         if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("dense shared-memory opt-in: ") + cudaGetErrorString(e));
+        int tc_bytes = 0;
+        for (const bnbp_handle::TcGroup& g : h->tcgroups) tc_bytes = std::max(tc_bytes, (int)tc_smem_bytes(g.max_rows, g.stages));
+        if (tc_bytes > 0 && (e = set_dense_tc_smem(tc_bytes)) != cudaSuccess)
+            return fail(BNBP_ERR_CUDA, std::string("tensor-core dense shared-memory opt-in: ") + cudaGetErrorString(e));
     }
     if ((rc = h->d_misc.ensure(64))) return rc;
     CU_TRY(cudaMemset(h->d_misc.p, 0, 64));
@@ -1069,7 +1167,7 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     if (ev->n_cases > 0 && !ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
-    h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = 0;
+    h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = h->last_dense_tc_launches = 0;
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
     h->ev_dense_used = 0;
@@ -1116,7 +1214,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         if (ev->ev_off[c + 1] < ev->ev_off[c]) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
-    h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = 0;
+    h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = h->last_dense_tc_launches = 0;
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
     h->ev_dense_used = 0;
@@ -1275,6 +1373,9 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->dense_values_per_case = h->TS;
     out->dense_flops_per_case_sweep = h->dense_flops_per_case;
     out->last_dense_launches = h->last_dense_launches;
+    out->dense_tensor_jobs = h->dense_tc_jobs;
+    out->dense_tensor_flops_per_case_sweep = h->dense_tc_flops_per_case;
+    out->last_dense_tensor_launches = h->last_dense_tc_launches;
     out->last_dense_ms = -1.0;
     out->last_sweep_ms = -1.0;
     out->last_total_ms = -1.0;

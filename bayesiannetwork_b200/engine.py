@@ -63,7 +63,8 @@ class BeliefPropagation:
     (belief_propagation.hpp:24,31) with a batch in place of one evidence map."""
 
     def __init__(self, net: FlatNetwork, precision: str = "fp64", device: int = -1,
-                 max_resident_cases: int = 0, specialize: str = "auto", dense_min_cpt: int = 0):
+                 max_resident_cases: int = 0, specialize: str = "auto", dense_min_cpt: int = 0,
+                 dense_tensor: int = 0):
         self.net = net
         self.precision = {"fp64": FP64, "fp32": FP32, "f64": FP64, "f32": FP32}[precision]
         lib = _capi.load()
@@ -72,7 +73,10 @@ class BeliefPropagation:
         fn = _net_c(net)
         # dense_min_cpt: CPT size from which a node takes the dense contraction path (0 = default
         # 256 entries, < 0 = never); see include/bnbp.h
-        opt = _capi.OptionsC(self.precision, device, max_resident_cases, SPECIALIZE[specialize], int(dense_min_cpt))
+        # dense_tensor: fp32 handles run large dense products on the tensor cores (tcgen05, 3xTF32);
+        # 0 = default, 1 = every dense product, -1 = never
+        opt = _capi.OptionsC(self.precision, device, max_resident_cases, SPECIALIZE[specialize], int(dense_min_cpt),
+                             int(dense_tensor))
         _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
 
     def close(self):

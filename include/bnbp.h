@@ -86,7 +86,11 @@ typedef struct bnbp_options {
     int32_t specialize;         /* BNBP_SPEC_AUTO (default) / ALWAYS (error if impossible) / NEVER */
     int32_t dense_min_cpt;      /* nodes whose CPT has >= this many entries meet the batch as matrix
                                    products (dense contraction path); 0 = default 256, < 0 = never  */
-    int32_t reserved[6];
+    int32_t dense_tensor;       /* fp32 handles: large dense products run on the tensor cores (tcgen05, fp32
+                                   accumulators in TMEM, every operand split hi + lo into two tf32 values:
+                                   csrc/bnbp_dense_tc.cuh).  0 = default (products with K >= 32, N >= 128),
+                                   1 = every dense product, -1 = never (CUDA-core FMA products)             */
+    int32_t reserved[5];
 } bnbp_options;
 
 /* Evidence for a batch, CSR over cases.  Entry e of case c (ev_off[c] <= e < ev_off[c+1])
@@ -134,6 +138,9 @@ typedef struct bnbp_stats {
     double  dense_flops_per_case_sweep; /* 4 * sum |CPT| over the dense nodes                    */
     int64_t last_dense_launches;     /* dense-contraction launches of the last run               */
     double  last_dense_ms;           /* device time of (up to the first 512 sweeps') dense launches */
+    int64_t dense_tensor_jobs;       /* dense products (two per node) that run on the tensor cores */
+    double  dense_tensor_flops_per_case_sweep; /* their algorithmic flops, 2*K*N each (x3 issued: hi/lo split) */
+    int64_t last_dense_tensor_launches;
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;
