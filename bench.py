@@ -201,6 +201,8 @@ def main():
                          "--sweeps = cap, default 200); value counts the sweeps actually executed")
     ap.add_argument("--dense-min", type=int, default=0,
                     help="CPT entries from which a node takes the dense contraction path (0 = library default, -1 = never)")
+    ap.add_argument("--dense-tensor", type=int, default=0,
+                    help="fp32: dense products on the tensor cores (0 = library default, 1 = every product, -1 = never)")
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
@@ -234,7 +236,7 @@ def main():
     tdtype = torch.float64 if args.precision == "fp64" else torch.float32
     tsize = 8 if args.precision == "fp64" else 4
     bp = BeliefPropagation(net, args.precision, device=local_rank, specialize=args.specialize,
-                           dense_min_cpt=args.dense_min)
+                           dense_min_cpt=args.dense_min, dense_tensor=args.dense_tensor)
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
@@ -341,6 +343,25 @@ def main():
                  "table_values_per_case": int(st["dense_values_per_case"]),
                  "launches_per_sweep": int(st["last_dense_launches"]) // max(1, int(st["last_sweep_launches"])),
                  "share_of_sweep_time": dense_ms_per_sweep / (dense_ms_per_sweep + sweep_ms_per_launch)}
+        if st.get("dense_tensor_jobs", 0):
+            # tensor-core products (dense_tc_kernel, tcgen05 kind::tf32): every algorithmic multiply-add is
+            # issued three times (hi*hi + hi*lo + lo*hi); the tensor-pipe rate is measured against half the
+            # measured bf16 throughput (tf32 runs at half the bf16 rate), else the nominal 1.1 PFLOP/s
+            mp = {}
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            tpk = 0.5 * mp["bf16_tflops"] if mp.get("bf16_tflops") else 1100.0
+            ttf = 3.0 * st["dense_tensor_flops_per_case_sweep"] * n / (dense_ms_per_sweep * 1e-3) / 1e12
+            all_tc = int(st["dense_tensor_jobs"]) == 2 * int(st["dense_nodes"])
+            dense.update({"kernel": "dense_tc_kernel" if all_tc else "dense_tc_kernel + dense_gemm_kernel",
+                          "tensor_jobs": int(st["dense_tensor_jobs"]),
+                          "tensor": {"bound": "tensor", "achieved": ttf, "peak": tpk, "unit": "TFLOP/s", "frac": ttf / tpk,
+                                     "issued_flops_per_case_sweep": 3.0 * st["dense_tensor_flops_per_case_sweep"],
+                                     "note": "3xTF32: issued tf32 flops = 3 x algorithmic; time includes any CUDA-core products of the same sweep",
+                                     "peak_source": ("0.5 x measured bf16 (MEASURED_PEAKS.json bf16_tflops)"
+                                                     if mp.get("bf16_tflops") else "nominal tf32 dense 1.1 PFLOP/s")}})
 
     # ---- end to end through the host-buffer C ABI (pinned host memory both ways) ----------------------
     e2e = None

@@ -1,6 +1,8 @@
 """Shared helpers for the parity tests."""
 from __future__ import annotations
 
+import os
+
 import numpy as np
 
 from bayesiannetwork_b200.flat import EvidenceBatch, FlatNetwork
@@ -31,4 +33,9 @@ def assert_close(a, b, rtol, atol, what=""):
     err = np.abs(a[ok] - b[ok])
     bound = rtol * np.maximum(np.abs(a[ok]), np.abs(b[ok])) + atol
     bad = err > bound
+    log = os.environ.get("BNBP_MARGIN_LOG")          # how close to the bound: one line per comparison
+    if log and err.size:
+        with open(log, "a") as f:
+            f.write(f"{what}: max err/bound {float((err / bound).max()):.3f}, max err {float(err.max()):.3e} "
+                    f"(rtol {rtol:g}, atol {atol:g}, {err.size} entries)\n")
     assert not bad.any(), f"{what}: {int(bad.sum())} entries off, max err {err.max():.3e}"
