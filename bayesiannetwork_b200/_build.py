@@ -21,6 +21,13 @@ HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_swee
            os.path.join(CSRC, "bnbp_dense.h"), os.path.join(CSRC, "bnbp_dense.cuh"),
            os.path.join(CSRC, "bnbp_dense_tc.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
+INCLUDE = os.path.join(os.path.dirname(HERE), "include")
+# host-only units: rebuilt when the drop-in headers they wrap change
+HOST_HEADERS = {"bnbp_netfile.cpp": [os.path.join(INCLUDE, "bayesian", "graph.hpp"),
+                                     os.path.join(INCLUDE, "bayesian", "serializer", "bif.hpp"),
+                                     os.path.join(INCLUDE, "bayesian", "serializer", "dsc.hpp"),
+                                     os.path.join(INCLUDE, "bayesian", "serializer", "text_scanner.hpp"),
+                                     os.path.join(INCLUDE, "bnbp.h")]}
 
 
 def embed_spec_header() -> None:
@@ -42,7 +49,7 @@ def sweep_variants():
     return [(t, int(v), int(r), int(k)) for t in ("double", "float") for (v, r, k) in trip]
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
-              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
+              "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr", "-I", INCLUDE]
 
 
 def nvcc_path() -> str:
@@ -63,7 +70,8 @@ def _units():
     units = [(os.path.join(CSRC, "bnbp_api.cu"), os.path.join(OBJDIR, "bnbp_api.o"), []),
              (os.path.join(CSRC, "bnbp_jit.cu"), os.path.join(OBJDIR, "bnbp_jit.o"), []),
              (os.path.join(CSRC, "bnbp_dense_inst.cu"), os.path.join(OBJDIR, "bnbp_dense.o"), []),
-             (os.path.join(CSRC, "bnbp_dense_tc_inst.cu"), os.path.join(OBJDIR, "bnbp_dense_tc.o"), [])]
+             (os.path.join(CSRC, "bnbp_dense_tc_inst.cu"), os.path.join(OBJDIR, "bnbp_dense_tc.o"), []),
+             (os.path.join(CSRC, "bnbp_netfile.cpp"), os.path.join(OBJDIR, "bnbp_netfile.o"), [])]
     for t, v, r, k in sweep_variants():
         units.append((os.path.join(CSRC, "bnbp_sweep_inst.cu"),
                       os.path.join(OBJDIR, f"sweep_{t}_v{v}_r{r}_k{k}.o"),
@@ -75,7 +83,8 @@ def _stale(obj: str, src: str) -> bool:
     if not os.path.exists(obj):
         return True
     t = os.path.getmtime(obj)
-    return any(os.path.getmtime(f) > t for f in [src] + HEADERS)
+    deps = HOST_HEADERS.get(os.path.basename(src), HEADERS)
+    return any(os.path.getmtime(f) > t for f in [src] + deps)
 
 
 def build(force: bool = False, verbose: bool = False, extra=()) -> str:

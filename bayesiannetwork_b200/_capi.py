@@ -52,7 +52,9 @@ class StatsC(C.Structure):
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",
-           "bnbp_run_batch_device", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source"]
+           "bnbp_run_batch_device", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source",
+           "bnbp_netfile_parse", "bnbp_netfile_load", "bnbp_netfile_network", "bnbp_netfile_name",
+           "bnbp_netfile_node_name", "bnbp_netfile_state_name", "bnbp_netfile_free"]
 
 
 def lib_path() -> str:

@@ -31,6 +31,15 @@ int fail(int code, const std::string& msg)
     return code;
 }
 
+}  // namespace
+
+// the error channel for the other translation units of the library (bnbp_netfile.cpp)
+namespace bnbp {
+int set_error(int code, const std::string& msg) { return fail(code, msg); }
+}
+
+namespace {
+
 #define CU_TRY(expr)                                                                      \
     do {                                                                                  \
         cudaError_t e__ = (expr);                                                         \

@@ -95,7 +95,13 @@ class ClockSampler:
                 "samples": len(sm), "power_w_max": max(power)}
 
 
-def build_workload(name: str, n_cases: int | None, rank: int):
+def build_workload(name: str, n_cases: int | None, rank: int, network_file: str | None = None):
+    if network_file:
+        # a network file (BIF / DSC through bnbp_netfile_*): evidence on each node with p = 0.10, 20 sweeps
+        from bayesiannetwork_b200 import netfile
+        net = netfile.load(network_file).net
+        n = n_cases or (1 << 18)
+        return net, synth.make_evidence(net, n, case_offset=rank * n, p=0.10), 20
     factory, default_cases, evkw, sweeps = synth.WORKLOADS[name]
     net = factory()
     n = n_cases or default_cases
@@ -191,6 +197,7 @@ def main():
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="bnbp", choices=["bnbp", "reference"])
     ap.add_argument("--workload", default="alarm37", choices=sorted(synth.WORKLOADS))
+    ap.add_argument("--network", default="", help="a .bif / .dsc network file instead of a synthetic workload")
     ap.add_argument("--cases", type=int, default=0, help="cases per GPU (default: the workload's)")
     ap.add_argument("--sweeps", type=int, default=0, help="fixed sweeps per step (default: the workload's)")
     ap.add_argument("--precision", default="fp64", choices=["fp64", "fp32"])
@@ -230,7 +237,9 @@ def main():
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
 
-    net, ev, sweeps = build_workload(args.workload, args.cases or None, rank)
+    net, ev, sweeps = build_workload(args.workload, args.cases or None, rank, args.network or None)
+    if args.network:
+        args.workload = "file:" + os.path.basename(args.network)
     sweeps = args.sweeps or (200 if args.epsilon > 0 else sweeps)
     n, V = ev.n_cases, net.belief_values
     tdtype = torch.float64 if args.precision == "fp64" else torch.float32

@@ -19,6 +19,8 @@
  *   bnbp_refresh_cpt   <- the reference reads vertex_t::cpt at call time (graph.hpp:157-161), so
  *                         CPT edits between calls are visible; here they need this call
  *   bnbp_precompile / bnbp_spec_source  (new: the network compiler, see BNBP_SPEC_* below)
+ *   bnbp_netfile_*     <- serializer::bif::parse (serializer/bif.hpp:41-132) and serializer::dsc::parse
+ *                         (serializer/dsc.hpp:33-232): network files -> bnbp_flat_network
  *
  * Semantics reproduced exactly (belief_propagation.hpp:75-148): synchronous (Jacobi)
  * schedule, no damping unless asked, evidence vector written into both pi and lambda of the
@@ -184,6 +186,27 @@ int  bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int3
  * cap bytes including the terminating NUL and returns the full length via *needed. */
 int  bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant,
                       char* buf, int64_t cap, int64_t* needed);
+
+/* ---- network files (host only, no GPU needed) --------------------------------------------------------
+ * BIF / DSC text -> the flat network above.  Replaces the reference loaders
+ * bn::serializer::bif::parse (bayesian/serializer/bif.hpp:41-132, grammar :138-263, Boost.Spirit) and
+ * bn::serializer::dsc::parse (bayesian/serializer/dsc.hpp:33-232); the parsers are the drop-in headers
+ * include/bayesian/serializer/{bif,dsc}.hpp, this is their FFI face.  Node i of the flat network is
+ * the i-th `variable` / `node` section of the file (the reference's vertex_list() order); parents are
+ * listed in ascending node index and CPT rows in the layout of bnbp_flat_network whatever order the
+ * file used. */
+enum { BNBP_FORMAT_AUTO = 0, BNBP_FORMAT_BIF = 1, BNBP_FORMAT_DSC = 2 };
+
+typedef struct bnbp_network_file bnbp_network_file;
+
+int  bnbp_netfile_parse(const char* text, int64_t len, int32_t format, bnbp_network_file** out);
+int  bnbp_netfile_load(const char* path, int32_t format, bnbp_network_file** out);  /* AUTO: by extension, then content */
+/* the arrays stay owned by the file object and live until bnbp_netfile_free */
+const bnbp_flat_network* bnbp_netfile_network(const bnbp_network_file* nf);
+const char* bnbp_netfile_name(const bnbp_network_file* nf);
+const char* bnbp_netfile_node_name(const bnbp_network_file* nf, int32_t node);                  /* NULL if out of range */
+const char* bnbp_netfile_state_name(const bnbp_network_file* nf, int32_t node, int32_t state);  /* NULL if out of range */
+void bnbp_netfile_free(bnbp_network_file* nf);
 
 #ifdef __cplusplus
 }

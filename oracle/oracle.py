@@ -98,3 +98,30 @@ def run_reference(net, ev, eps=1e-3, max_sweeps=0, pure=False):
     if rc != 0:
         raise RuntimeError("bnref_run failed")
     return out, sweeps, conv, secs.value
+
+
+REF_DSC_SO = os.path.join(HERE, "_ref", "libbnref_dsc.so")
+
+
+def have_reference_dsc() -> bool:
+    return os.path.exists(REF_DSC_SO)
+
+
+def reference_dsc_flatten(text: str):
+    """The reference's own DSC loader (serializer/dsc.hpp) on `text`, read back through its graph
+    accessors.  Returns (card, parent_off, parents, cpt_off, cpt) in the layout of include/bnbp.h."""
+    if REF_DSC_SO not in _ref:
+        _ref[REF_DSC_SO] = C.CDLL(REF_DSC_SO)
+    lib = _ref[REF_DSC_SO]
+    lib.bnref_dsc_flatten.restype = C.c_int
+    raw = text.encode("utf-8")
+    n, e, v = C.c_int32(0), C.c_int32(0), C.c_int64(0)
+    lib.bnref_dsc_flatten(raw, C.byref(n), C.byref(e), C.byref(v), None, None, None, None, None)
+    card = np.zeros(n.value, dtype=np.int32)
+    poff = np.zeros(n.value + 1, dtype=np.int32)
+    par = np.zeros(max(e.value, 1), dtype=np.int32)
+    coff = np.zeros(n.value + 1, dtype=np.int64)
+    cpt = np.zeros(max(v.value, 1), dtype=np.float64)
+    lib.bnref_dsc_flatten(raw, C.byref(n), C.byref(e), C.byref(v), _ptr(card, C.c_int32), _ptr(poff, C.c_int32),
+                          _ptr(par, C.c_int32), _ptr(coff, C.c_int64), _ptr(cpt, C.c_double))
+    return card, poff, par[:e.value], coff, cpt[:v.value]

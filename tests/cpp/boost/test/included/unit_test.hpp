@@ -95,6 +95,13 @@ inline int run_all()
     ::boost_shim::report(::boost_shim::close_percent((a), (b), (tol)), __FILE__, __LINE__,       \
                          "|" #a " - " #b "| within " #tol " %")
 
+#define BOOST_CHECK_THROW(stmt, exception_type)                                                   \
+    do {                                                                                          \
+        bool caught__ = false;                                                                    \
+        try { (void)(stmt); } catch (exception_type const&) { caught__ = true; }                  \
+        ::boost_shim::report(caught__, __FILE__, __LINE__, #stmt " throws " #exception_type);     \
+    } while (0)
+
 #ifdef BOOST_TEST_MAIN
 int main()
 {

@@ -1,0 +1,41 @@
+"""The C-ABI library loads without a GPU and exports every entry point include/bnbp.h declares
+(no compute calls here)."""
+import os
+import re
+
+from bayesiannetwork_b200 import _capi
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared():
+    text = open(os.path.join(ROOT, "include", "bnbp.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)            # prose mentions names too
+    return sorted(set(re.findall(r"\b(bnbp_[a-z_]+)\s*\(", text)))
+
+
+def test_every_declared_symbol_is_exported():
+    lib = _capi.load()
+    names = declared()
+    assert len(names) >= 17, names
+    missing = [n for n in names if not hasattr(lib, n)]
+    assert not missing, missing
+    assert sorted(_capi.EXPORTS) == names
+
+
+def test_no_device_is_an_error_not_a_fallback():
+    """Without a usable GPU bnbp_create must fail loudly (BNBP_ERR_NO_DEVICE); on a GPU box the
+    count is simply positive."""
+    import numpy as np
+    from bayesiannetwork_b200 import synth
+    from bayesiannetwork_b200.engine import BeliefPropagation
+    lib = _capi.load()
+    if lib.bnbp_device_count() > 0:
+        return
+    try:
+        BeliefPropagation(synth.pearl_network())
+    except _capi.BnbpError as e:
+        assert e.code == 3, e
+    else:
+        raise AssertionError("bnbp_create succeeded without a device")
+    assert np.isfinite(1.0)

@@ -47,6 +47,12 @@ def test_headers_compile_with_plain_gxx_in_cxx11_and_cxx17(tmp_path):
         assert r.returncode == 0, r.stderr
 
 
+def test_serializer_headers():
+    """bn::serializer::bif / dsc used the way the reference's are (tests/cpp/test_serializer.cpp)."""
+    out = _run(os.path.join(OWN_BIN, "test_serializer"))
+    assert out.count("[  ok  ]") == 4, out
+
+
 @pytest.mark.gpu
 def test_reference_bp_tests_pass_on_the_gpu_backend():
     """libs/bayesian/test/belief_propagation.cpp, unmodified: 7 test cases, BOOST_CHECK_CLOSE bars of
