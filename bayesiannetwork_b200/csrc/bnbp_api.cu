@@ -137,8 +137,9 @@ struct bnbp_handle {
     DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
     // staging for the host API (outputs double-buffered: D2H of chunk i overlaps the sweeps of chunk i+1)
     DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out[2], s_out_sweeps, s_out_conv;   // sweeps/conv: whole batch
-    cudaStream_t copy_stream = nullptr;
-    cudaEvent_t ev_computed[2] = {nullptr, nullptr}, ev_copied[2] = {nullptr, nullptr};
+    DevBuf s_out_all;                   // whole-batch output staging (used when HBM has the room)
+    cudaStream_t copy_stream = nullptr, h2d_stream = nullptr;
+    std::vector<cudaEvent_t> ev_chunk;  // per chunk of the host-buffer call: uploaded, computed, copied
     // column groups of the tiled belief kernel, per (tile width, output element size)
     struct BeliefPlan { DevBuf groups; int n_groups = 0; int stride = 0; size_t smem = 0; bool ok = false; };
     std::map<int, BeliefPlan> belief_plans;
@@ -560,6 +561,61 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     }
     if (planned_sweeps) *planned_sweeps = eps_mode ? -1 : (int64_t)total_sweeps * n;
     return BNBP_OK;
+}
+
+// Cases one full wave of the sweep grid holds (blocks resident on the 148 SMs x cases per tile).
+// The specialised kernels report their occupancy; the generic family is taken at 4 blocks per SM.
+int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
+{
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    int blocks = 4;
+    if (h->run_spec) {
+        const bool plain = !(prm.epsilon > 0.0) && prm.damping == 0.0;
+        const SpecKernel& k = h->spec[plain ? (prm.max_sweeps != 2 ? 0 : 3) : 2];
+        if (k.blocks_per_sm > 0) blocks = k.blocks_per_sm;
+    }
+    if (const char* e = getenv("BNBP_WAVE_BLOCKS")) blocks = std::max(1, atoi(e));
+    return (int64_t)sms * blocks * h->tb;
+}
+
+// Chunk sizes (cases) of the host-buffer call, whole waves each; the last chunk takes the remainder.
+std::vector<int64_t> plan_chunks(int64_t n, int64_t wave)
+{
+    std::vector<int64_t> plan;
+    const int64_t W = wave > 0 ? n / wave : 0;
+    if (W < 3 || getenv("BNBP_ONE_CHUNK")) { plan.push_back(n); return plan; }
+    std::vector<int64_t> w;
+    int64_t rest = W;
+    if (W >= 10) { w = {1, 2}; rest -= 3; }            // ramp-up: the first copy starts after one wave
+    else if (W >= 5) { w = {1}; rest -= 1; }
+    const int k = (int)std::min<int64_t>(6, rest);
+    std::vector<double> ideal((size_t)k);
+    double sum = 0.0, term = 1.0;
+    for (int i = 0; i < k; ++i, term *= 0.7) { ideal[(size_t)i] = term; sum += term; }
+    std::vector<int64_t> g((size_t)k);
+    int64_t used = 0;
+    for (int i = 0; i < k; ++i) {
+        ideal[(size_t)i] *= (double)rest / sum;
+        g[(size_t)i] = std::max<int64_t>(1, (int64_t)ideal[(size_t)i]);
+        used += g[(size_t)i];
+    }
+    while (used < rest) {                              // largest remainder first
+        int best = 0;
+        for (int i = 1; i < k; ++i)
+            if (ideal[(size_t)i] - (double)g[(size_t)i] > ideal[(size_t)best] - (double)g[(size_t)best]) best = i;
+        g[(size_t)best]++; used++;
+    }
+    while (used > rest) {                              // the floor of 1 wave overshot: take from the largest
+        int best = 0;
+        for (int i = 1; i < k; ++i) if (g[(size_t)i] > g[(size_t)best]) best = i;
+        g[(size_t)best]--; used--;
+    }
+    w.insert(w.end(), g.begin(), g.end());
+    int64_t placed = 0;
+    for (int64_t x : w) if (x > 0) { plan.push_back(x * wave); placed += x * wave; }
+    plan.back() += n - placed;                         // the fraction of a wave that is left
+    return plan;
 }
 
 int check_error_flag(bnbp_handle* h, cudaStream_t st)
@@ -1058,10 +1114,7 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     CU_TRY(cudaMemset(h->d_misc.p, 0, 64));
     CU_TRY(cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking));
     CU_TRY(cudaStreamCreateWithFlags(&h->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-        CU_TRY(cudaEventCreateWithFlags(&h->ev_computed[i], cudaEventDisableTiming));
-        CU_TRY(cudaEventCreateWithFlags(&h->ev_copied[i], cudaEventDisableTiming));
-    }
+    CU_TRY(cudaStreamCreateWithFlags(&h->h2d_stream, cudaStreamNonBlocking));
     for (int i = 0; i < 2; ++i) {
         CU_TRY(cudaEventCreate(&h->ev_total[i]));
         CU_TRY(cudaEventCreateWithFlags(&h->ev_poll[i], cudaEventDisableTiming));
@@ -1084,15 +1137,13 @@ void bnbp_destroy(bnbp_handle* h)
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
                       &h->d_djobs, &h->d_dytab, &h->d_ddig, &h->d_cpt_t, &h->d_tscr,
-                      &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1],
+                      &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1], &h->s_out_all,
                       &h->s_out_sweeps, &h->s_out_conv})
         b->release();
     for (auto& kv : h->belief_plans) kv.second.groups.release();
-    for (int i = 0; i < 2; ++i) {
-        if (h->ev_computed[i]) cudaEventDestroy(h->ev_computed[i]);
-        if (h->ev_copied[i]) cudaEventDestroy(h->ev_copied[i]);
-    }
+    for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
+    if (h->h2d_stream) { cudaStreamSynchronize(h->h2d_stream); cudaStreamDestroy(h->h2d_stream); }
     for (int v = 0; v < 5; ++v) spec_unload(&h->spec[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_dense) cudaEventDestroy(e);
@@ -1229,37 +1280,54 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->ev_dense_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
-    // Chunk pipeline: the device->host copy of chunk i (on copy_stream, out of staging buffer i&1)
-    // overlaps init/sweeps/beliefs of chunk i+1.  Marginals are 8*V bytes per case, so the copy is
-    // of the same order as the kernels.  Schedule 3/8, 3/8, 1/8, 1/8 of the batch: big chunks keep
-    // the sweep grids many waves deep (a 128K-case grid is 2.3 waves: +20 % per sweep, r01g trace),
-    // the small last chunk keeps the exposed tail copy short.
-    std::vector<int64_t> plan;
-    {
-        const int64_t n = ev->n_cases;
-        auto up = [](int64_t v) { return (v + 511) / 512 * 512; };
-        if (n >= 262144) {
-            const int64_t big = up(n * 3 / 8), small = up(n / 8);
-            plan = {big, big, small, n};                  // the last entry takes what is left
-        } else if (n >= 32768) {
-            const int64_t q = up((n + 3) / 4);
-            plan = {q, q, q, n};
-        } else {
-            plan = {n};
-        }
-    }
-    int64_t chunk = *std::max_element(plan.begin(), plan.end() - (plan.size() > 1 ? 1 : 0));
+    // Chunk pipeline on three streams: evidence of chunk i+1 goes up (h2d_stream) and the marginals of
+    // chunk i-1 come down (copy_stream) while init/sweeps/beliefs of chunk i run.  Marginals are 8*V
+    // bytes per case, so the copy is of the same order as the kernels.  plan_chunks() cuts the batch
+    // in whole waves of the sweep grid (a 2.3-wave grid pays for 3, r01g/r01k traces): short chunks
+    // first so the copy engine starts early, then chunks shrinking by 0.7 down to one wave so the
+    // exposed tail copy is short.
+    const int64_t wave = wave_cases(h, *prm);
+    std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave);
+    int64_t chunk = *std::max_element(plan.begin(), plan.end());
     if ((rc = ensure_state(h, chunk))) return rc;
     if (h->cap < chunk) {                                 // HBM cannot hold the planned chunk: equal resident chunks
         chunk = h->cap;
-        plan.assign(1, chunk);
+        plan.assign((size_t)((ev->n_cases + chunk - 1) / chunk), chunk);
     }
-    for (int i = 0; i < 2; ++i)
-        if ((rc = h->s_out[i].ensure((size_t)chunk * h->V * 8))) return rc;
+    // Output staging: the whole batch when HBM has the room (no chunk ever waits for a slot),
+    // else a ring of two chunk-sized slots.
+    const size_t row_bytes = (size_t)h->V * 8;
+    bool whole = (size_t)ev->n_cases * row_bytes <= h->s_out_all.bytes;
+    if (!whole && !getenv("BNBP_STAGING_RING")) {
+        size_t free_b = 0, total_b = 0;
+        CU_TRY(cudaMemGetInfo(&free_b, &total_b));
+        whole = (double)ev->n_cases * (double)row_bytes <= 0.5 * (double)(free_b + h->s_out[0].bytes + h->s_out[1].bytes);
+        if (whole) {
+            h->s_out[0].release(); h->s_out[1].release();
+            if ((rc = h->s_out_all.ensure((size_t)ev->n_cases * row_bytes))) return rc;
+        }
+    }
+    if (!whole)
+        for (int i = 0; i < 2; ++i)
+            if ((rc = h->s_out[i].ensure((size_t)chunk * row_bytes))) return rc;
     // per-case sweep counts / flags stay on the device until the end: the caller's arrays are usually
     // pageable, and a pageable D2H per chunk would block the host and serialise the pipeline
     if ((rc = h->s_out_sweeps.ensure((size_t)ev->n_cases * 4))) return rc;
     if ((rc = h->s_out_conv.ensure((size_t)ev->n_cases))) return rc;
+    // evidence staging for the whole batch (absolute offsets, like bnbp_run_batch_device)
+    if ((rc = h->s_ev_off.ensure((size_t)(ev->n_cases + 1) * 8))) return rc;
+    if ((rc = h->s_ev_node.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
+    if (soft) {
+        if ((rc = h->s_ev_val_off.ensure((size_t)(nnz + 1) * 8))) return rc;
+        if ((rc = h->s_ev_values.ensure(std::max<size_t>(16, (size_t)(ev->ev_val_off[nnz] - ev->ev_val_off[0]) * 8)))) return rc;
+    } else {
+        if ((rc = h->s_ev_state.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
+    }
+    while (h->ev_chunk.size() < 3 * plan.size()) {       // per chunk: uploaded, computed, copied
+        cudaEvent_t e;
+        CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+        h->ev_chunk.push_back(e);
+    }
     const bool trace = getenv("BNBP_TRACE") != nullptr;
     const auto t_begin = std::chrono::steady_clock::now();
     auto stamp = [&](const char* what, int i) {
@@ -1267,12 +1335,18 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
             fprintf(stderr, "[bnbp] %8.3f ms  %s %d\n",
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, i);
     };
-    cudaStream_t cs = h->copy_stream;
-    struct Drain {                       // no path leaves this call with copies to host memory in flight
-        cudaStream_t a, b;
-        ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); }
-    } drain{st, cs};
+    if (trace) {
+        fprintf(stderr, "[bnbp] wave %lld cases, staging %s, chunks:", (long long)wave, whole ? "whole batch" : "ring of 2");
+        for (int64_t c : plan) fprintf(stderr, " %lld", (long long)c);
+        fprintf(stderr, "\n");
+    }
+    cudaStream_t cs = h->copy_stream, hs = h->h2d_stream;
+    struct Drain {                       // no path leaves this call with copies from/to host memory in flight
+        cudaStream_t a, b, c;
+        ~Drain() { cudaStreamSynchronize(a); cudaStreamSynchronize(b); cudaStreamSynchronize(c); }
+    } drain{hs, st, cs};
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
+    CU_TRY(cudaStreamWaitEvent(hs, h->ev_total[0], 0));   // uploads start with the call on the device timeline
     std::vector<cudaEvent_t> tev;                     // BNBP_TRACE: device timeline of the pipeline
     auto mark = [&](cudaStream_t s) {
         if (!trace) return;
@@ -1281,62 +1355,66 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         cudaEventRecord(e, s);
         tev.push_back(e);
     };
+    const int64_t val0 = soft ? ev->ev_val_off[0] : 0;
     int idx = 0;
     for (int64_t c0 = 0, n = 0; c0 < ev->n_cases; c0 += n, ++idx) {
-        const int sb = idx & 1;
-        n = std::min<int64_t>(std::min<int64_t>(plan[std::min<size_t>((size_t)idx, plan.size() - 1)], chunk), ev->n_cases - c0);
+        n = (size_t)idx + 1 >= plan.size() ? ev->n_cases - c0 : std::min<int64_t>(plan[(size_t)idx], ev->n_cases - c0);
+        n = std::min<int64_t>(n, chunk);
+        if ((size_t)(3 * idx + 2) >= h->ev_chunk.size()) {
+            for (int k = 0; k < 3; ++k) {
+                cudaEvent_t e;
+                CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->ev_chunk.push_back(e);
+            }
+        }
+        cudaEvent_t e_up = h->ev_chunk[3 * idx], e_done = h->ev_chunk[3 * idx + 1], e_copied = h->ev_chunk[3 * idx + 2];
         const int64_t a = ev->ev_off[c0], b = ev->ev_off[c0 + n];
-        if ((rc = h->s_ev_off.ensure((size_t)(chunk + 1) * 8))) return rc;
-        // evidence staging may have to grow: wait for the chunk that still reads the old buffers
-        if (h->s_ev_node.bytes < (size_t)(b - a) * 4 || h->s_ev_state.bytes < (size_t)(b - a) * 4 ||
-            (soft && (h->s_ev_val_off.bytes < (size_t)(b - a + 1) * 8 ||
-                      h->s_ev_values.bytes < (size_t)(ev->ev_val_off[b] - ev->ev_val_off[a]) * 8)))
-            CU_TRY(cudaStreamSynchronize(st));
-        if ((rc = h->s_ev_node.ensure(std::max<size_t>(16, (size_t)(b - a) * 4)))) return rc;
-        if (idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[sb], 0));   // staging buffer sb is free again
-        CU_TRY(cudaMemcpyAsync(h->s_ev_off.p, ev->ev_off + c0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, st));
-        if (b > a) CU_TRY(cudaMemcpyAsync(h->s_ev_node.p, ev->ev_node + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
-        DevEvidence de{(const int64_t*)h->s_ev_off.p, a, (const int32_t*)h->s_ev_node.p, nullptr, nullptr, nullptr, 0};
+        // evidence of this chunk, into its place in the whole-batch arrays
+        CU_TRY(cudaMemcpyAsync((int64_t*)h->s_ev_off.p + c0, ev->ev_off + c0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, hs));
+        if (b > a) CU_TRY(cudaMemcpyAsync((int32_t*)h->s_ev_node.p + a, ev->ev_node + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, hs));
+        DevEvidence de{(const int64_t*)h->s_ev_off.p + c0, 0, (const int32_t*)h->s_ev_node.p, nullptr, nullptr, nullptr, 0};
         if (soft) {
             const int64_t va = ev->ev_val_off[a], vb = ev->ev_val_off[b];
-            if ((rc = h->s_ev_val_off.ensure((size_t)(b - a + 1) * 8))) return rc;
-            if ((rc = h->s_ev_values.ensure(std::max<size_t>(16, (size_t)(vb - va) * 8)))) return rc;
-            CU_TRY(cudaMemcpyAsync(h->s_ev_val_off.p, ev->ev_val_off + a, (size_t)(b - a + 1) * 8, cudaMemcpyHostToDevice, st));
-            if (vb > va) CU_TRY(cudaMemcpyAsync(h->s_ev_values.p, ev->ev_values + va, (size_t)(vb - va) * 8, cudaMemcpyHostToDevice, st));
+            CU_TRY(cudaMemcpyAsync((int64_t*)h->s_ev_val_off.p + a, ev->ev_val_off + a, (size_t)(b - a + 1) * 8, cudaMemcpyHostToDevice, hs));
+            if (vb > va)
+                CU_TRY(cudaMemcpyAsync((double*)h->s_ev_values.p + (va - val0), ev->ev_values + va, (size_t)(vb - va) * 8, cudaMemcpyHostToDevice, hs));
             de.ev_val_off = (const int64_t*)h->s_ev_val_off.p;
             de.ev_values = (const double*)h->s_ev_values.p;
-            de.ev_val_base = va;
+            de.ev_val_base = val0;
         } else {
-            if ((rc = h->s_ev_state.ensure(std::max<size_t>(16, (size_t)(b - a) * 4)))) return rc;
-            if (b > a) CU_TRY(cudaMemcpyAsync(h->s_ev_state.p, ev->ev_state + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, st));
+            if (b > a) CU_TRY(cudaMemcpyAsync((int32_t*)h->s_ev_state.p + a, ev->ev_state + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, hs));
             de.ev_state = (const int32_t*)h->s_ev_state.p;
         }
+        CU_TRY(cudaEventRecord(e_up, hs));
+        CU_TRY(cudaStreamWaitEvent(st, e_up, 0));
+        double* slot = whole ? (double*)h->s_out_all.p + (size_t)c0 * h->V : (double*)h->s_out[idx & 1].p;
+        if (!whole && idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_chunk[3 * (idx - 2) + 2], 0));   // ring slot is free again
         stamp("enqueue chunk", idx);
         mark(st);
         if (h->precision == BNBP_FP32)
-            rc = run_chunk<float, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps.p + c0,
+            rc = run_chunk<float, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0,
                                           (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         else
-            rc = run_chunk<double, double>(h, n, de, *prm, (double*)h->s_out[sb].p, (int32_t*)h->s_out_sweeps.p + c0,
+            rc = run_chunk<double, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0,
                                            (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         if (rc) return rc;
         mark(st);
-        CU_TRY(cudaEventRecord(h->ev_computed[sb], st));
-        CU_TRY(cudaStreamWaitEvent(cs, h->ev_computed[sb], 0));
+        CU_TRY(cudaEventRecord(e_done, st));
+        CU_TRY(cudaStreamWaitEvent(cs, e_done, 0));
         mark(cs);
-        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, h->s_out[sb].p, (size_t)n * h->V * 8, cudaMemcpyDeviceToHost, cs));
+        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, slot, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, cs));
         mark(cs);
-        CU_TRY(cudaEventRecord(h->ev_copied[sb], cs));
+        CU_TRY(cudaEventRecord(e_copied, cs));
         stamp("enqueued copy", idx);
     }
-    CU_TRY(cudaStreamWaitEvent(cs, h->ev_computed[(idx - 1) & 1], 0));
+    cudaEvent_t e_last = h->ev_chunk[3 * (idx - 1) + 2];
+    // copy_stream is in order: everything before e_last has left when it fires
     if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps, h->s_out_sweeps.p, (size_t)ev->n_cases * 4, cudaMemcpyDeviceToHost, cs));
     if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged, h->s_out_conv.p, (size_t)ev->n_cases, cudaMemcpyDeviceToHost, cs));
-    CU_TRY(cudaEventRecord(h->ev_copied[(idx - 1) & 1], cs));
+    CU_TRY(cudaEventRecord(e_last, cs));
     stamp("all enqueued", idx);
     // the call returns with every result on the host
-    CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[(idx - 1) & 1], 0));
-    if (idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_copied[idx & 1], 0));
+    CU_TRY(cudaStreamWaitEvent(st, e_last, 0));
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
     if ((rc = check_error_flag(h, st))) return rc;

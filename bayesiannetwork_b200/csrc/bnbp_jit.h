@@ -57,6 +57,7 @@ struct SpecKernel {                 // one loaded cubin
     void* function = nullptr;       // CUfunction
     uint64_t cpt_dptr = 0;          // address of bnbp_cpt in the module
     size_t cpt_bytes = 0;
+    int blocks_per_sm = 0;          // resident 128-thread blocks per SM (0: unknown)
     bool from_cache = false;
     double compile_ms = 0.0;
 };
