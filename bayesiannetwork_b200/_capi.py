@@ -48,11 +48,12 @@ class StatsC(C.Structure):
                 ("spec_compile_ms", C.c_double), ("dense_nodes", C.c_int64), ("dense_values_per_case", C.c_int64),
                 ("dense_flops_per_case_sweep", C.c_double), ("last_dense_launches", C.c_int64),
                 ("last_dense_ms", C.c_double), ("dense_tensor_jobs", C.c_int64),
-                ("dense_tensor_flops_per_case_sweep", C.c_double), ("last_dense_tensor_launches", C.c_int64)]
+                ("dense_tensor_flops_per_case_sweep", C.c_double), ("last_dense_tensor_launches", C.c_int64),
+                ("last_fused", C.c_int64)]
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",
-           "bnbp_run_batch_device", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source",
+           "bnbp_run_batch_device", "bnbp_lw_run_batch", "bnbp_estimate_cpt", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source",
            "bnbp_netfile_parse", "bnbp_netfile_load", "bnbp_netfile_network", "bnbp_netfile_name",
            "bnbp_netfile_node_name", "bnbp_netfile_state_name", "bnbp_netfile_free"]
 

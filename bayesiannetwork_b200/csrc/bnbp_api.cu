@@ -4,6 +4,7 @@
 // ONCE in bnbp_create and the sweeps touch only flat device arrays.
 #include "../../include/bnbp.h"
 #include "bnbp_kernels.cuh"
+#include "bnbp_lw.cuh"
 #include "bnbp_variants.h"
 #include "bnbp_jit.h"
 #include "bnbp_dense.h"
@@ -97,8 +98,14 @@ struct bnbp_handle {
     bool spec_eligible_ = false;
     std::string spec_why;              // why the network is not specialised
     int spec_vec = 1, spec_minb = 1, spec_ahead = 1;
-    SpecKernel spec[5];                // + 3 plain-first (no message loads), 4 plain-last (no message stores)
-    int spec_state[5] = {0, 0, 0, 0, 0};   // 0 untried, 1 loaded, -1 failed
+    static constexpr int NSPEC = 8;    // variants of bnbp_spec.cuh
+    SpecKernel spec[NSPEC];            // + 3 plain-first (no message loads), 4 plain-last (no message stores),
+                                       //   5 first + K0, 6/7 last + K4 (marginals in T / in double)
+    int spec_state[NSPEC] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 untried, 1 loaded, -1 failed
+    bool fuse = false;                 // this run: K0 inside the first sweep, K4 inside the last (variants 5, 6/7)
+    int last_fused = 0;
+    bool fuse_ok = true;               // cleared when a fused variant failed to build: the unfused launch sequence runs
+    DevBuf d_evst;                     // [tiles][N][tb] evidence-state bytes of the resident chunk
     bool run_spec = false;             // kernel family of the current run
     int last_specialised = 0;
     double spec_compile_ms = 0.0;
@@ -137,6 +144,12 @@ struct bnbp_handle {
     DevBuf d_pl, d_msg[2], d_evbits, d_delta, d_status, d_sweeps, d_misc;
     // staging for the host API (outputs double-buffered: D2H of chunk i overlaps the sweeps of chunk i+1)
     DevBuf s_ev_off, s_ev_node, s_ev_state, s_ev_val_off, s_ev_values, s_out[2], s_out_sweeps, s_out_conv;   // sweeps/conv: whole batch
+    // likelihood weighting (bnbp_lw.cuh): parent ids, a topological order and the fp64 CPT arena, uploaded on first use
+    std::vector<int32_t> par_host;
+    DevBuf d_lw_order, d_lw_par, d_lw_cpt, d_lw_out, d_lw_wsum;
+    bool lw_ready = false;
+    void* pin_counts = nullptr;         // pinned host staging of the per-case sweep counts / converged flags
+    size_t pin_counts_bytes = 0;
     DevBuf s_out_all;                   // whole-batch output staging (used when HBM has the room)
     cudaStream_t copy_stream = nullptr, h2d_stream = nullptr;
     std::vector<cudaEvent_t> ev_chunk;  // per chunk of the host-buffer call: uploaded, computed, copied
@@ -215,7 +228,7 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
     }
     limit = std::max<int64_t>(TBMAX, limit / TBMAX * TBMAX);
     want = std::min(want, limit);
-    if (want <= h->cap) return BNBP_OK;
+    if (want <= h->cap) return h->fuse ? h->d_evst.ensure((size_t)h->cap * h->N) : BNBP_OK;
     // grow: release first so the new allocation can reuse the space
     h->d_pl.release(); h->d_msg[0].release(); h->d_msg[1].release(); h->d_evbits.release(); h->d_tscr.release();
     h->d_delta.release(); h->d_status.release(); h->d_sweeps.release();
@@ -230,13 +243,14 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
     if ((rc = h->d_status.ensure((size_t)want))) return rc;
     if ((rc = h->d_sweeps.ensure((size_t)want * 4))) return rc;
     h->cap = want;
-    return BNBP_OK;
+    h->d_evst.release();
+    return h->fuse ? h->d_evst.ensure((size_t)h->cap * h->N) : BNBP_OK;
 }
 
 SpecLayout spec_layout(const bnbp_handle* h)
 {
     SpecLayout L;
-    L.N = h->N; L.PL = h->PL; L.M = h->M; L.W = h->W;
+    L.N = h->N; L.PL = h->PL; L.M = h->M; L.W = h->W; L.V = h->V;
     L.cpt_values = h->cpt_values;
     L.nodes = h->nodes.data();
     L.e_card = h->e_card.data();
@@ -280,9 +294,10 @@ int ensure_spec(bnbp_handle* h, int v)
 // Kernel family of one run.  Decided before the state is initialised because the tile width
 // (cases per thread) belongs to the family.  ALWAYS: failure is an error; AUTO: the generic GPU
 // kernel takes over (still CUDA: there is no CPU path).
-int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm)
+int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, bool soft_evidence, bool out_double)
 {
     h->run_spec = false;
+    h->fuse = false;
     const bool want = h->specialize == BNBP_SPEC_ALWAYS ||
                       (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
     if (want) {
@@ -300,6 +315,14 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm)
             if (need[v] && ensure_spec(h, v) != BNBP_OK) ok = false;
         if (!ok && h->specialize == BNBP_SPEC_ALWAYS) return BNBP_ERR_CUDA;   // message already set
         h->run_spec = ok;
+        // fixed sweep count, hard evidence, one case per thread: K0 runs inside the first sweep and K4
+        // inside the last (variants 5 and 6/7), so neither the time-0 pi/lambda nor the final ones
+        // cross HBM.  Soft evidence rows do not fit a state byte: the unfused sequence handles them.
+        if (ok && need[3] && !soft_evidence && h->spec_vec == 1 && h->fuse_ok && !getenv("BNBP_NO_FUSE")) {
+            const int vlast = (h->precision == BNBP_FP32 && out_double) ? 7 : 6;
+            if (ensure_spec(h, 5) == BNBP_OK && ensure_spec(h, vlast) == BNBP_OK) h->fuse = true;
+            else h->fuse_ok = false;
+        }
     }
     h->tb = BLOCK_THREADS * (h->run_spec ? h->spec_vec : h->vec);
     h->last_specialised = h->run_spec ? 1 : 0;
@@ -356,7 +379,22 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         return fail(BNBP_ERR_INVALID, "epsilon <= 0 needs a positive max_sweeps (the loop would never end)");
 
     CU_TRY(cudaMemsetAsync(d_last_active, 0xFF, 4, st));   // -1
-    {
+    const bool fuse = h->fuse && h->run_spec && !eps_mode && prm.damping == 0.0 && max_sweeps >= 2 && !de.ev_values;
+    h->last_fused = fuse ? 1 : 0;
+    if (fuse) {
+        // K0 is part of the first sweep (variant 5): only the observed states are scattered here
+        CU_TRY(cudaMemsetAsync(h->d_evst.p, 0, (size_t)tiles * h->tb * h->N, st));
+        CU_TRY(cudaMemsetAsync(h->d_evbits.p, 0, (size_t)tiles * h->tb * h->W * 4, st));
+        EvidenceArgs ea;
+        ea.nodes = (const NodeMeta*)h->d_nodes.p;
+        ea.evst = (uint8_t*)h->d_evst.p; ea.evbits = (uint32_t*)h->d_evbits.p;
+        ea.W = h->W; ea.TB = h->tb; ea.n_nodes = h->N; ea.n_valid = n;
+        ea.ev_off = de.ev_off; ea.ev_base = de.ev_base; ea.ev_node = de.ev_node; ea.ev_state = de.ev_state;
+        ea.error_flag = d_error;
+        evidence_kernel<<<tiles, h->tb, 0, st>>>(ea);
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+    } else {
         InitArgs<T> ia;
         ia.nodes = (const NodeMeta*)h->d_nodes.p;
         ia.pl_init = (const T*)h->d_pl_init.p;
@@ -428,6 +466,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             sa.delta_next = delta + (size_t)((t + 1) % 3) * h->cap;
             sa.sweep_index = t;
             sa.prev_tested = prev_tested ? 1 : 0;
+            int n_inner = 1;
             if (h->TS > 0) {
                 // dense nodes: this sweep's CPT x batch products (time-t messages and lambda_X), before
                 // the sweep kernel overwrites lambda_X in place
@@ -489,10 +528,19 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 // network-specialised kernel: variant 0 plain, 1 freeze, 2 freeze + check
                 int variant = check ? 2 : (eps_mode ? 1 : 0);
                 if (variant == 0 && max_sweeps >= 2) variant = t == 0 ? 3 : (t == max_sweeps - 1 ? 4 : 0);
+                if (fuse && variant == 3) variant = 5;
+                if (fuse && variant == 4) variant = (sizeof(T) == 4 && sizeof(OUT) == 8) ? 7 : 6;
                 SpecAux<T> ax;
                 ax.delta_prev = sa.delta_prev; ax.delta_cur = sa.delta_cur; ax.delta_next = sa.delta_next;
                 ax.status = sa.status; ax.sweeps = sa.sweeps; ax.last_active = sa.last_active;
                 ax.sweep_index = sa.sweep_index; ax.prev_tested = sa.prev_tested; ax.eps = sa.eps; ax.damping = sa.damping;
+                ax.evst = (const unsigned char*)h->d_evst.p; ax.out = d_out; ax.n_valid = n;
+                // fixed-count runs: the plain sweeps between the first and the last go out as ONE launch
+                // (cases are independent, no barrier between their sweeps is needed)
+                ax.n_inner = 1;
+                if (variant == 0 && !eps_mode && prm.damping == 0.0 && !getenv("BNBP_NO_LOOP"))
+                    ax.n_inner = (max_sweeps >= 2 ? max_sweeps - 1 : max_sweeps) - t;
+                n_inner = ax.n_inner;
                 std::string err;
                 if (!spec_launch(h->spec[variant], (unsigned)tiles, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
                     return fail(BNBP_ERR_CUDA, err);
@@ -501,8 +549,9 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
             }
             prev_tested = tested;
-            h->last_sweep_launches++;
+            h->last_sweep_launches += n_inner;      // counted in sweeps: a looped launch stands for n_inner of them
             h->last_kernel_launches++;
+            t += n_inner - 1;
         }
         if (eps_mode && t < max_sweeps) {
             // asynchronous termination poll: keep one batch of launches in flight while the flag
@@ -540,7 +589,15 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         h->last_kernel_launches++;
     }
 
-    {
+    if (fuse) {
+        // K4 ran inside the last sweep (variants 6/7); only the per-case counts are left
+        if (d_out_sweeps || d_out_conv) {
+            counts_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
+                                                                        d_out_sweeps, d_out_conv, n);
+            CU_TRY(cudaGetLastError());
+            h->last_kernel_launches++;
+        }
+    } else {
         bnbp_handle::BeliefPlan* plan = nullptr;
         int rc = belief_plan(h, h->tb, (int)sizeof(OUT), &plan);
         if (rc) return rc;
@@ -580,19 +637,32 @@ int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
 }
 
 // Chunk sizes (cases) of the host-buffer call, whole waves each; the last chunk takes the remainder.
-std::vector<int64_t> plan_chunks(int64_t n, int64_t wave)
+// rho = estimated copy time / compute time of a chunk (an upper bound: the compute estimate is the HBM
+// floor of the sweeps).  Every chunk boundary costs ~20 dependent-launch drains (0.3 ms on alarm37,
+// r01l trace), so the plan is as short as the overlap allows:
+//   compute-bound (rho < 0.9): 4 chunks shrinking by ~rho, so each copy hides behind the next chunk's
+//                 kernels and the exposed tail copy is the smallest chunk;
+//   copy-bound:   a 1-wave and a 2-wave chunk start the copy engine early, the rest goes in 3 chunks.
+std::vector<int64_t> plan_chunks(int64_t n, int64_t wave, double rho)
 {
     std::vector<int64_t> plan;
     const int64_t W = wave > 0 ? n / wave : 0;
     if (W < 3 || getenv("BNBP_ONE_CHUNK")) { plan.push_back(n); return plan; }
     std::vector<int64_t> w;
     int64_t rest = W;
-    if (W >= 10) { w = {1, 2}; rest -= 3; }            // ramp-up: the first copy starts after one wave
-    else if (W >= 5) { w = {1}; rest -= 1; }
-    const int k = (int)std::min<int64_t>(6, rest);
+    double ratio = std::min(0.8, std::max(0.5, rho));
+    int k = 4;
+    if (rho >= 0.9) {
+        if (W >= 10) { w = {1, 2}; rest -= 3; }
+        else if (W >= 5) { w = {1}; rest -= 1; }
+        ratio = 1.0;
+        k = 3;
+    }
+    if (const char* e = getenv("BNBP_CHUNKS")) k = std::max(1, atoi(e));
+    k = (int)std::min<int64_t>(k, rest);
     std::vector<double> ideal((size_t)k);
     double sum = 0.0, term = 1.0;
-    for (int i = 0; i < k; ++i, term *= 0.7) { ideal[(size_t)i] = term; sum += term; }
+    for (int i = 0; i < k; ++i, term *= ratio) { ideal[(size_t)i] = term; sum += term; }
     std::vector<int64_t> g((size_t)k);
     int64_t used = 0;
     for (int i = 0; i < k; ++i) {
@@ -876,6 +946,7 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     h->N = N;
     h->E = E;
     h->card.assign(net->card, net->card + N);
+    h->par_host.assign(net->parents, net->parents + E);
 
     // ---- validate + derive topology (the checks the reference leaves as UB, graph.hpp:117-124) ----
     int maxcard = 1;
@@ -1136,7 +1207,7 @@ void bnbp_destroy(bnbp_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
-                      &h->d_djobs, &h->d_dytab, &h->d_ddig, &h->d_cpt_t, &h->d_tscr,
+                      &h->d_evst, &h->d_lw_order, &h->d_lw_par, &h->d_lw_cpt, &h->d_lw_out, &h->d_lw_wsum, &h->d_djobs, &h->d_dytab, &h->d_ddig, &h->d_cpt_t, &h->d_tscr,
                       &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1], &h->s_out_all,
                       &h->s_out_sweeps, &h->s_out_conv})
         b->release();
@@ -1144,7 +1215,7 @@ void bnbp_destroy(bnbp_handle* h)
     for (cudaEvent_t e : h->ev_chunk) cudaEventDestroy(e);
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->h2d_stream) { cudaStreamSynchronize(h->h2d_stream); cudaStreamDestroy(h->h2d_stream); }
-    for (int v = 0; v < 5; ++v) spec_unload(&h->spec[v]);
+    for (int v = 0; v < bnbp_handle::NSPEC; ++v) spec_unload(&h->spec[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_dense) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -1152,6 +1223,7 @@ void bnbp_destroy(bnbp_handle* h)
         if (h->ev_poll[i]) cudaEventDestroy(h->ev_poll[i]);
     }
     if (h->pinned_poll) cudaFreeHost(h->pinned_poll);
+    if (h->pin_counts) cudaFreeHost(h->pin_counts);
     if (h->stream) cudaStreamDestroy(h->stream);
     delete h;
 }
@@ -1163,7 +1235,8 @@ int bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values)
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaDeviceSynchronize());          // runs may have been enqueued on caller streams
     h->cpt_host.assign(cpt, cpt + n_values);
-    for (int v = 0; v < 5; ++v) {             // constant banks of the loaded specialised kernels
+    h->lw_ready = false;                      // the fp64 arena of the likelihood-weighting kernel is re-uploaded on next use
+    for (int v = 0; v < bnbp_handle::NSPEC; ++v) {             // constant banks of the loaded specialised kernels
         if (h->spec_state[v] != 1) continue;
         std::string err;
         bool ok;
@@ -1184,8 +1257,9 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
     int rc = build_layout(net, opt, &h);
     if (rc) return rc;
     if (!h.spec_eligible_) return fail(BNBP_ERR_INVALID, "network is not eligible for specialisation: " + h.spec_why);
-    for (int v = 0; v < 5; ++v) {
+    for (int v = 0; v < bnbp_handle::NSPEC; ++v) {
         if (!(variant_mask & (1 << v))) continue;
+        if (v == 7 && h.precision != BNBP_FP32) continue;     // marginals in double from a float kernel only
         SpecConfig cfg;
         cfg.fp32 = h.precision == BNBP_FP32;
         cfg.vec = h.spec_vec; cfg.minb = h.spec_minb; cfg.variant = v; cfg.ahead = h.spec_ahead;
@@ -1199,7 +1273,7 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
 int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant, char* buf, int64_t cap,
                      int64_t* needed)
 {
-    if (variant < 0 || variant > 4) return fail(BNBP_ERR_INVALID, "variant must be 0..4");
+    if (variant < 0 || variant >= bnbp_handle::NSPEC) return fail(BNBP_ERR_INVALID, "variant must be 0..7");
     bnbp_handle h;
     int rc = build_layout(net, opt, &h);
     if (rc) return rc;
@@ -1232,7 +1306,7 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     h->ev_sweep_used = 0;
     h->ev_dense_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
-    if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
+    if ((rc = choose_kernels(h, ev->n_cases, *prm, ev->ev_values != nullptr, h->precision != BNBP_FP32))) return rc;
     if ((rc = ensure_state(h, ev->n_cases))) return rc;
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
     bool exact = true;
@@ -1270,8 +1344,8 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     const bool soft = ev->ev_values != nullptr;
     if (nnz > 0 && !soft && !ev->ev_state) return fail(BNBP_ERR_INVALID, "neither ev_state nor ev_values given");
     if (soft && !ev->ev_val_off) return fail(BNBP_ERR_INVALID, "ev_val_off is NULL");
-    for (int64_t c = 0; c < ev->n_cases; ++c)
-        if (ev->ev_off[c + 1] < ev->ev_off[c]) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
+    if (ev->n_cases > 0 && (ev->ev_off[0] < 0 || nnz < ev->ev_off[0])) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
+    // (the per-case monotonicity check runs chunk by chunk below, while the device works on the chunk before)
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t st = h->stream;
     h->last_sweep_launches = h->last_kernel_launches = h->last_dense_launches = h->last_dense_tc_launches = 0;
@@ -1279,7 +1353,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->ev_sweep_used = 0;
     h->ev_dense_used = 0;
     if (ev->n_cases == 0) return BNBP_OK;
-    if ((rc = choose_kernels(h, ev->n_cases, *prm))) return rc;
+    if ((rc = choose_kernels(h, ev->n_cases, *prm, soft, true))) return rc;
     // Chunk pipeline on three streams: evidence of chunk i+1 goes up (h2d_stream) and the marginals of
     // chunk i-1 come down (copy_stream) while init/sweeps/beliefs of chunk i run.  Marginals are 8*V
     // bytes per case, so the copy is of the same order as the kernels.  plan_chunks() cuts the batch
@@ -1287,7 +1361,11 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     // first so the copy engine starts early, then chunks shrinking by 0.7 down to one wave so the
     // exposed tail copy is short.
     const int64_t wave = wave_cases(h, *prm);
-    std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave);
+    // copy over a ~55 GB/s host link vs the sweeps at the HBM floor (2*S*sizeof(T) bytes per case-sweep)
+    const double sweeps_est = prm->epsilon > 0.0 ? (double)std::min(prm->max_sweeps > 0 ? prm->max_sweeps : 20, 20) : (double)prm->max_sweeps;
+    const double rho = ((double)h->V * 8.0 / 55e9) /
+                       std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / 6.0e12);
+    std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave, rho);
     int64_t chunk = *std::max_element(plan.begin(), plan.end());
     if ((rc = ensure_state(h, chunk))) return rc;
     if (h->cap < chunk) {                                 // HBM cannot hold the planned chunk: equal resident chunks
@@ -1314,6 +1392,15 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     // pageable, and a pageable D2H per chunk would block the host and serialise the pipeline
     if ((rc = h->s_out_sweeps.ensure((size_t)ev->n_cases * 4))) return rc;
     if ((rc = h->s_out_conv.ensure((size_t)ev->n_cases))) return rc;
+    if (h->pin_counts_bytes < (size_t)ev->n_cases * 5) {
+        if (h->pin_counts) cudaFreeHost(h->pin_counts);
+        h->pin_counts = nullptr;
+        h->pin_counts_bytes = 0;
+        CU_TRY(cudaMallocHost(&h->pin_counts, (size_t)ev->n_cases * 5));
+        h->pin_counts_bytes = (size_t)ev->n_cases * 5;
+    }
+    int32_t* const pin_sweeps = (int32_t*)h->pin_counts;
+    uint8_t* const pin_conv = (uint8_t*)h->pin_counts + (size_t)ev->n_cases * 4;
     // evidence staging for the whole batch (absolute offsets, like bnbp_run_batch_device)
     if ((rc = h->s_ev_off.ensure((size_t)(ev->n_cases + 1) * 8))) return rc;
     if ((rc = h->s_ev_node.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
@@ -1336,7 +1423,8 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
                     std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count(), what, i);
     };
     if (trace) {
-        fprintf(stderr, "[bnbp] wave %lld cases, staging %s, chunks:", (long long)wave, whole ? "whole batch" : "ring of 2");
+        fprintf(stderr, "[bnbp] wave %lld cases, copy/compute estimate %.2f, staging %s, chunks:", (long long)wave, rho,
+                whole ? "whole batch" : "ring of 2");
         for (int64_t c : plan) fprintf(stderr, " %lld", (long long)c);
         fprintf(stderr, "\n");
     }
@@ -1369,6 +1457,11 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         }
         cudaEvent_t e_up = h->ev_chunk[3 * idx], e_done = h->ev_chunk[3 * idx + 1], e_copied = h->ev_chunk[3 * idx + 2];
         const int64_t a = ev->ev_off[c0], b = ev->ev_off[c0 + n];
+        {
+            bool mono = a >= 0 && b <= nnz;
+            for (int64_t c = c0; c < c0 + n; ++c) mono &= ev->ev_off[c + 1] >= ev->ev_off[c];
+            if (!mono) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
+        }
         // evidence of this chunk, into its place in the whole-batch arrays
         CU_TRY(cudaMemcpyAsync((int64_t*)h->s_ev_off.p + c0, ev->ev_off + c0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, hs));
         if (b > a) CU_TRY(cudaMemcpyAsync((int32_t*)h->s_ev_node.p + a, ev->ev_node + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, hs));
@@ -1404,14 +1497,17 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         mark(cs);
         CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, slot, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, cs));
         mark(cs);
+        // per-case counts: into the library's pinned staging (the caller's arrays are usually pageable, and
+        // a pageable D2H would block this thread until the chunk is done)
+        if (out_sweeps)
+            CU_TRY(cudaMemcpyAsync(pin_sweeps + c0, (const int32_t*)h->s_out_sweeps.p + c0, (size_t)n * 4, cudaMemcpyDeviceToHost, cs));
+        if (out_converged)
+            CU_TRY(cudaMemcpyAsync(pin_conv + c0, (const uint8_t*)h->s_out_conv.p + c0, (size_t)n, cudaMemcpyDeviceToHost, cs));
         CU_TRY(cudaEventRecord(e_copied, cs));
         stamp("enqueued copy", idx);
     }
     cudaEvent_t e_last = h->ev_chunk[3 * (idx - 1) + 2];
     // copy_stream is in order: everything before e_last has left when it fires
-    if (out_sweeps) CU_TRY(cudaMemcpyAsync(out_sweeps, h->s_out_sweeps.p, (size_t)ev->n_cases * 4, cudaMemcpyDeviceToHost, cs));
-    if (out_converged) CU_TRY(cudaMemcpyAsync(out_converged, h->s_out_conv.p, (size_t)ev->n_cases, cudaMemcpyDeviceToHost, cs));
-    CU_TRY(cudaEventRecord(e_last, cs));
     stamp("all enqueued", idx);
     // the call returns with every result on the host
     CU_TRY(cudaStreamWaitEvent(st, e_last, 0));
@@ -1429,13 +1525,184 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         fprintf(stderr, "[bnbp] chunk %zu: compute %.3f..%.3f ms, copy %.3f..%.3f ms (device timeline)\n", i / 4, a, b, c, d);
     }
     for (cudaEvent_t e : tev) cudaEventDestroy(e);
-    if (out_sweeps) {
+    if (out_sweeps) memcpy(out_sweeps, pin_sweeps, (size_t)ev->n_cases * 4);
+    if (out_converged) memcpy(out_converged, pin_conv, (size_t)ev->n_cases);
+    if (!(prm->epsilon > 0.0)) {
+        h->last_case_sweeps = ev->n_cases * (int64_t)prm->max_sweeps;     // fixed count: every case ran them all
+    } else if (out_sweeps) {
         int64_t s = 0;
         for (int64_t c = 0; c < ev->n_cases; ++c) s += out_sweeps[c];
         h->last_case_sweeps = s;
     } else {
         h->last_case_sweeps = -1;
     }
+    return BNBP_OK;
+}
+
+int bnbp_lw_run_batch(bnbp_handle* h, const bnbp_evidence* ev, int64_t n_samples, uint64_t seed, double* out_marginals,
+                      double* out_weight_sum)
+{
+    if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_lw_run_batch: NULL argument");
+    if (n_samples < 1) return fail(BNBP_ERR_INVALID, "bnbp_lw_run_batch: n_samples < 1");
+    if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
+    if (ev->ev_values) return fail(BNBP_ERR_INVALID, "likelihood weighting takes hard evidence (vertex -> state, likelihood_weighting.hpp:15)");
+    if (ev->n_cases == 0) return BNBP_OK;
+    if (!ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
+    const int64_t nnz = ev->ev_off[ev->n_cases];
+    if (nnz < 0 || ev->ev_off[0] < 0) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
+    if (nnz > 0 && (!ev->ev_node || !ev->ev_state)) return fail(BNBP_ERR_INVALID, "ev_node / ev_state is NULL");
+    for (int64_t c = 0; c < ev->n_cases; ++c)
+        if (ev->ev_off[c + 1] < ev->ev_off[c]) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
+    for (int x = 0; x < h->N; ++x)
+        if (h->card[x] > 255) return fail(BNBP_ERR_INVALID, "likelihood weighting keeps states in bytes: cardinality > 255");
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = h->stream;
+    int rc;
+    if (!h->lw_ready) {
+        // a topological order: parents first (weighted_sample resolves the parents recursively, :131-147)
+        std::vector<int32_t> order, indeg(h->N), stack;
+        std::vector<std::vector<int32_t>> ch(h->N);
+        for (int x = h->N - 1; x >= 0; --x) {
+            indeg[x] = h->nodes[x].k;
+            for (int j = 0; j < h->nodes[x].k; ++j) ch[h->par_host[h->nodes[x].e0 + j]].push_back(x);
+            if (!indeg[x]) stack.push_back(x);
+        }
+        while (!stack.empty()) {
+            const int u = stack.back(); stack.pop_back();
+            order.push_back(u);
+            for (int c : ch[u]) if (--indeg[c] == 0) stack.push_back(c);
+        }
+        if ((rc = h->d_lw_order.ensure(std::max<size_t>(16, order.size() * 4)))) return rc;
+        if ((rc = h->d_lw_par.ensure(std::max<size_t>(16, h->par_host.size() * 4)))) return rc;
+        if ((rc = h->d_lw_cpt.ensure(std::max<size_t>(16, h->cpt_host.size() * 8)))) return rc;
+        CU_TRY(cudaMemcpyAsync(h->d_lw_order.p, order.data(), order.size() * 4, cudaMemcpyHostToDevice, st));
+        if (!h->par_host.empty())
+            CU_TRY(cudaMemcpyAsync(h->d_lw_par.p, h->par_host.data(), h->par_host.size() * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(h->d_lw_cpt.p, h->cpt_host.data(), h->cpt_host.size() * 8, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaStreamSynchronize(st));          // the vectors above go out of scope
+        h->lw_ready = true;
+    }
+    // block shape: one sample per thread; [node][thread] state bytes + the case's histogram in shared memory
+    int threads = 128;
+    auto smem_for = [&](int t) { return (size_t)h->V * 8 + (size_t)h->N * 4 + (size_t)h->N * t; };
+    while (threads > 32 && smem_for(threads) > 200 * 1024) threads /= 2;
+    const size_t smem = smem_for(threads);
+    if (smem > 200 * 1024) return fail(BNBP_ERR_INVALID, "network too large for the likelihood-weighting kernel's shared-memory state");
+    if (smem > 48 * 1024) CU_TRY(cudaFuncSetAttribute(lw_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    if ((rc = h->s_ev_off.ensure((size_t)(ev->n_cases + 1) * 8))) return rc;
+    if ((rc = h->s_ev_node.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
+    if ((rc = h->s_ev_state.ensure(std::max<size_t>(16, (size_t)nnz * 4)))) return rc;
+    CU_TRY(cudaMemcpyAsync(h->s_ev_off.p, ev->ev_off, (size_t)(ev->n_cases + 1) * 8, cudaMemcpyHostToDevice, st));
+    if (nnz > 0) {
+        CU_TRY(cudaMemcpyAsync(h->s_ev_node.p, ev->ev_node, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+        CU_TRY(cudaMemcpyAsync(h->s_ev_state.p, ev->ev_state, (size_t)nnz * 4, cudaMemcpyHostToDevice, st));
+    }
+    const int64_t CH = 1 << 16;                     // cases per launch (bounds the device-side result buffer)
+    if ((rc = h->d_lw_out.ensure((size_t)std::min(CH, ev->n_cases) * h->V * 8))) return rc;
+    if ((rc = h->d_lw_wsum.ensure((size_t)std::min(CH, ev->n_cases) * 8))) return rc;
+    int32_t* d_error = reinterpret_cast<int32_t*>(h->d_misc.p) + 1;
+    h->last_kernel_launches = 0;
+    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += CH) {
+        const int64_t n = std::min(CH, ev->n_cases - c0);
+        LwArgs a;
+        a.nodes = (const NodeMeta*)h->d_nodes.p;
+        a.order = (const int32_t*)h->d_lw_order.p; a.par = (const int32_t*)h->d_lw_par.p;
+        a.cpt = (const double*)h->d_lw_cpt.p;
+        a.n_nodes = h->N; a.V = h->V;
+        a.n_cases = n; a.case_base = c0;
+        a.ev_off = (const int64_t*)h->s_ev_off.p + c0; a.ev_base = 0;
+        a.ev_node = (const int32_t*)h->s_ev_node.p; a.ev_state = (const int32_t*)h->s_ev_state.p;
+        a.n_samples = n_samples; a.seed = seed;
+        a.out = (double*)h->d_lw_out.p; a.out_wsum = (double*)h->d_lw_wsum.p;
+        a.error_flag = d_error;
+        lw_kernel<<<(unsigned)n, threads, smem, st>>>(a);
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, h->d_lw_out.p, (size_t)n * h->V * 8, cudaMemcpyDeviceToHost, st));
+        if (out_weight_sum) CU_TRY(cudaMemcpyAsync(out_weight_sum + c0, h->d_lw_wsum.p, (size_t)n * 8, cudaMemcpyDeviceToHost, st));
+    }
+    return check_error_flag(h, st);
+}
+
+int bnbp_estimate_cpt(const bnbp_flat_network* net, const int32_t* samples, const int64_t* multiplicity, int64_t n_rows,
+                      int32_t device, double* out_cpt)
+{
+    if (!net || !out_cpt || (n_rows > 0 && !samples)) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: NULL argument");
+    if (n_rows < 0) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: n_rows < 0");
+    const int N = net->n_nodes;
+    if (N < 1 || !net->card || !net->parent_off || !net->cpt_off) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: malformed network");
+    const int E = net->parent_off[N];
+    if (E > 0 && !net->parents) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: parents is NULL");
+    std::vector<NodeMeta> nodes((size_t)N);
+    std::vector<int64_t> row_start((size_t)N + 1, 0);
+    for (int x = 0; x < N; ++x) {
+        NodeMeta& nd = nodes[(size_t)x];
+        memset(&nd, 0, sizeof nd);
+        nd.card = net->card[x];
+        nd.k = net->parent_off[x + 1] - net->parent_off[x];
+        nd.e0 = net->parent_off[x];
+        nd.cpt_off = net->cpt_off[x];
+        if (nd.card < 1 || nd.k < 0) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: bad cardinality / parent_off");
+        int64_t Q = 1;
+        for (int e = nd.e0; e < nd.e0 + nd.k; ++e) {
+            const int u = net->parents[e];
+            if (u < 0 || u >= N || u == x) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: bad parent id");
+            Q *= net->card[u];
+        }
+        if (net->cpt_off[x + 1] - net->cpt_off[x] != Q * nd.card)
+            return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: cpt_off does not match the parent configurations");
+        row_start[(size_t)x + 1] = row_start[(size_t)x] + Q;
+    }
+    const int64_t n_values = net->cpt_off[N], n_cpt_rows = row_start[(size_t)N];
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev < 1) {
+        cudaGetLastError();
+        return fail(BNBP_ERR_NO_DEVICE, "no CUDA device: libbnbp has no CPU fallback");
+    }
+    if (device >= 0) CU_TRY(cudaSetDevice(device));
+    DevBuf d_nodes, d_par, d_rows, d_samples, d_mult, d_counts, d_cpt, d_flag;
+    struct Free { std::vector<DevBuf*> b; ~Free() { for (DevBuf* x : b) x->release(); } }
+        guard{{&d_nodes, &d_par, &d_rows, &d_samples, &d_mult, &d_counts, &d_cpt, &d_flag}};
+    int rc;
+    if ((rc = d_nodes.ensure(nodes.size() * sizeof(NodeMeta)))) return rc;
+    if ((rc = d_par.ensure(std::max<size_t>(16, (size_t)E * 4)))) return rc;
+    if ((rc = d_rows.ensure(row_start.size() * 8))) return rc;
+    if ((rc = d_counts.ensure(std::max<size_t>(16, (size_t)n_values * 8)))) return rc;
+    if ((rc = d_cpt.ensure(std::max<size_t>(16, (size_t)n_values * 8)))) return rc;
+    if ((rc = d_flag.ensure(16))) return rc;
+    CU_TRY(cudaMemcpy(d_nodes.p, nodes.data(), nodes.size() * sizeof(NodeMeta), cudaMemcpyHostToDevice));
+    if (E > 0) CU_TRY(cudaMemcpy(d_par.p, net->parents, (size_t)E * 4, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemcpy(d_rows.p, row_start.data(), row_start.size() * 8, cudaMemcpyHostToDevice));
+    CU_TRY(cudaMemset(d_counts.p, 0, (size_t)n_values * 8));
+    CU_TRY(cudaMemset(d_flag.p, 0, 16));
+    // the sample table goes through HBM in slabs of <= 256 MB
+    const int64_t slab = std::max<int64_t>(1, (int64_t)(256u << 20) / ((int64_t)N * 4));
+    if (n_rows > 0) {
+        if ((rc = d_samples.ensure((size_t)std::min(slab, n_rows) * N * 4))) return rc;
+        if (multiplicity && (rc = d_mult.ensure((size_t)std::min(slab, n_rows) * 8))) return rc;
+    }
+    for (int64_t r0 = 0; r0 < n_rows; r0 += slab) {
+        const int64_t n = std::min(slab, n_rows - r0);
+        CU_TRY(cudaMemcpy(d_samples.p, samples + r0 * N, (size_t)n * N * 4, cudaMemcpyHostToDevice));
+        if (multiplicity) CU_TRY(cudaMemcpy(d_mult.p, multiplicity + r0, (size_t)n * 8, cudaMemcpyHostToDevice));
+        CountArgs a;
+        a.nodes = (const NodeMeta*)d_nodes.p; a.par = (const int32_t*)d_par.p;
+        a.samples = (const int32_t*)d_samples.p; a.mult = multiplicity ? (const int64_t*)d_mult.p : nullptr;
+        a.n_rows = n; a.n_nodes = N;
+        a.counts = (unsigned long long*)d_counts.p; a.error_flag = (int32_t*)d_flag.p;
+        const int64_t work = n * N;
+        const unsigned blocks = (unsigned)std::min<int64_t>((work + 255) / 256, 148 * 32);
+        cpt_count_kernel<<<blocks, 256>>>(a);
+        CU_TRY(cudaGetLastError());
+    }
+    cpt_normalize_kernel<<<(unsigned)((n_cpt_rows + 255) / 256), 256>>>((const NodeMeta*)d_nodes.p, (const int64_t*)d_rows.p, N, n_cpt_rows,
+                                                                     (const unsigned long long*)d_counts.p, (double*)d_cpt.p);
+    CU_TRY(cudaGetLastError());
+    int32_t flag = 0;
+    CU_TRY(cudaMemcpy(&flag, d_flag.p, 4, cudaMemcpyDeviceToHost));
+    if (flag == 3) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: a sample holds a state outside [0, cardinality)");
+    if (flag == 4) return fail(BNBP_ERR_INVALID, "bnbp_estimate_cpt: negative multiplicity");
+    CU_TRY(cudaMemcpy(out_cpt, d_cpt.p, (size_t)n_values * 8, cudaMemcpyDeviceToHost));
     return BNBP_OK;
 }
 
@@ -1463,6 +1730,7 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->dense_tensor_jobs = h->dense_tc_jobs;
     out->dense_tensor_flops_per_case_sweep = h->dense_tc_flops_per_case;
     out->last_dense_tensor_launches = h->last_dense_tc_launches;
+    out->last_fused = h->last_fused;
     out->last_dense_ms = -1.0;
     out->last_sweep_ms = -1.0;
     out->last_total_ms = -1.0;

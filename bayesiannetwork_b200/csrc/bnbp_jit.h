@@ -17,7 +17,7 @@
 namespace bnbp {
 
 struct SpecLayout {                 // host view of the network the generator needs
-    int N = 0, PL = 0, M = 0, W = 0;
+    int N = 0, PL = 0, M = 0, W = 0, V = 0;
     int64_t cpt_values = 0;
     const NodeMeta* nodes = nullptr;
     const int32_t* e_card = nullptr;      // [E] parent cardinality per in-edge
@@ -29,7 +29,7 @@ struct SpecConfig {
     bool fp32 = false;
     int vec = 1;        // cases per thread
     int minb = 1;       // __launch_bounds__ min blocks per SM
-    int variant = 0;    // 0 plain, 1 freeze, 2 freeze + check
+    int variant = 0;    // 0 plain, 1 freeze, 2 freeze + check, 3 first, 4 last, 5 first + K0, 6/7 last + K4 (bnbp_spec.cuh)
     int ahead = 1;      // software-pipeline depth of the input loads
 };
 
@@ -50,6 +50,10 @@ template <typename T> struct SpecAux {
     int prev_tested;
     T eps;
     T damping;
+    int n_inner;                 // variant 0: sweeps per launch
+    const unsigned char* evst;   // variant 5: evidence-state bytes [tiles][N][TBC]
+    void* out;                   // variants 6/7: case-major marginals
+    long long n_valid;
 };
 
 struct SpecKernel {                 // one loaded cubin

@@ -91,6 +91,13 @@ template <> struct Lim<float>  { static __device__ __forceinline__ float floor_(
 __device__ __forceinline__ double absdiff_max(double run, double a, double b) { return fmax(run, fabs(a - b)); }
 __device__ __forceinline__ float  absdiff_max(float run, float a, float b) { return fmaxf(run, fabsf(a - b)); }
 
+// belief = (pi*lambda) / sum(pi*lambda) (:151-158): the sum is accumulated with explicit fused
+// multiply-adds and the numerator is an explicitly rounded product, so that the compiler's choice of
+// contraction cannot differ between the stand-alone belief kernels and the fused last sweep of
+// bnbp_spec.cuh (which must agree bit for bit)
+__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ float  mul_rn(float a, float b) { return __fmul_rn(a, b); }
+
 // non-negative IEEE values order like their bit patterns
 __device__ __forceinline__ void atomic_max_nonneg(double* p, double v)
 {
@@ -170,6 +177,50 @@ __global__ void __launch_bounds__(512) init_kernel(const InitArgs<T> a)
     }
 }
 
+// K0 of the fused launch sequence (specialised variants 5, 6/7 of bnbp_spec.cuh): the first sweep forms
+// the time-0 pi/lambda itself, so all that is left of :33-73 is one state byte per (node, case)
+// -- 0 not observed, s+1 observed in state s -- and the evidence bit masks the later sweeps read.
+// Both arenas are zeroed by the caller; one thread per case scatters its observations.
+struct EvidenceArgs {
+    const NodeMeta* nodes;
+    uint8_t* evst;              // [tiles][n_nodes][TB]
+    uint32_t* evbits;           // [tiles][W][TB]
+    int32_t W, TB, n_nodes;
+    int64_t n_valid;
+    const int64_t* ev_off; int64_t ev_base;
+    const int32_t* ev_node; const int32_t* ev_state;
+    int32_t* error_flag;
+};
+
+static __global__ void __launch_bounds__(512) evidence_kernel(const EvidenceArgs a)
+{
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const size_t TB = (size_t)a.TB;
+    const int64_t c = (int64_t)tile * a.TB + lane;
+    if (c >= a.n_valid) return;
+    uint8_t* est = a.evst + ((size_t)tile * a.n_nodes) * TB + lane;
+    uint32_t* evb = a.evbits + ((size_t)tile * a.W) * TB + lane;
+    const int64_t e0 = a.ev_off[c] - a.ev_base, e1 = a.ev_off[c + 1] - a.ev_base;
+    for (int64_t e = e0; e < e1; ++e) {
+        const int node = a.ev_node[e];
+        if (node < 0 || node >= a.n_nodes) { *a.error_flag = 1; continue; }
+        const int st = a.ev_state[e];
+        if (st < 0 || st >= a.nodes[node].card) { *a.error_flag = 3; continue; }
+        est[(size_t)node * TB] = (uint8_t)(st + 1);
+        evb[(size_t)(node >> 5) * TB] |= 1u << (node & 31);
+    }
+}
+
+// per-case sweep counts and converged flags of a chunk, when no belief kernel follows (fused sequence)
+static __global__ void counts_kernel(const uint8_t* __restrict__ status, const int32_t* __restrict__ sweeps,
+                              int32_t* __restrict__ out_sweeps, uint8_t* __restrict__ out_conv, int64_t n)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (c >= n) return;
+    if (out_sweeps) out_sweeps[c] = sweeps[c];
+    if (out_conv) out_conv[c] = status[c];
+}
+
 // After the last sweep: cases still active get their sweep count and converged flag.
 template <typename T>
 __global__ void finalize_kernel(uint8_t* status, int32_t* sweeps, const T* delta_last, int last_tested,
@@ -201,9 +252,9 @@ belief_kernel(const NodeMeta* nodes, int n_nodes, const T* pl_all, int PL, int T
         const int r = nd.card;
         T s = T(0);
         for (int x = 0; x < r; ++x)
-            s += pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB];
+            s = fma(pl[(size_t)(nd.pl_off + x) * TB], pl[(size_t)(nd.pl_off + r + x) * TB], s);
         for (int x = 0; x < r; ++x)
-            o[nd.bel_off + x] = (OUT)((pl[(size_t)(nd.pl_off + x) * TB] * pl[(size_t)(nd.pl_off + r + x) * TB]) / s);
+            o[nd.bel_off + x] = (OUT)(mul_rn(pl[(size_t)(nd.pl_off + x) * TB], pl[(size_t)(nd.pl_off + r + x) * TB]) / s);
     }
     if (out_sweeps) out_sweeps[c] = sweeps[c];
     if (out_conv) out_conv[c] = status[c];
@@ -244,9 +295,9 @@ belief_tiled_kernel(const NodeMeta* __restrict__ nodes, const BeliefGroup* __res
                 const int r = nd.card;
                 const T* const p = pl + (size_t)nd.pl_off * TB;
                 T s = T(0);
-                for (int x = 0; x < r; ++x) s += p[(size_t)x * TB] * p[(size_t)(r + x) * TB];
+                for (int x = 0; x < r; ++x) s = fma(p[(size_t)x * TB], p[(size_t)(r + x) * TB], s);
                 for (int x = 0; x < r; ++x)
-                    mine[nd.bel_off - gr.j0 + x] = (OUT)((p[(size_t)x * TB] * p[(size_t)(r + x) * TB]) / s);
+                    mine[nd.bel_off - gr.j0 + x] = (OUT)(mul_rn(p[(size_t)x * TB], p[(size_t)(r + x) * TB]) / s);
             }
         }
         __syncwarp();

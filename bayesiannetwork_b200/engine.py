@@ -43,6 +43,24 @@ def spec_source(net: FlatNetwork, precision: str = "fp64", variant: int = 0) -> 
     return buf.value.decode()
 
 
+def estimate_cpt(net: FlatNetwork, samples: np.ndarray, multiplicity: Optional[np.ndarray] = None,
+                 device: int = -1) -> np.ndarray:
+    """``sampler::make_cpt`` (sampler.hpp:81-163) on the GPU (``bnbp_estimate_cpt``): the CPT arena of
+    ``net``'s topology estimated from ``samples`` [n_rows, N] (state of every node per distinct sample)
+    and their multiplicities.  ``net.cpt`` is not read; the result has its layout."""
+    lib = _capi.load()
+    samples = np.ascontiguousarray(samples, dtype=np.int32)
+    if samples.ndim != 2 or samples.shape[1] != net.n_nodes:
+        raise ValueError("samples must be [n_rows, n_nodes]")
+    mult = None if multiplicity is None else np.ascontiguousarray(multiplicity, dtype=np.int64)
+    if mult is not None and mult.shape != (samples.shape[0],):
+        raise ValueError("multiplicity must be [n_rows]")
+    out = np.empty(int(net.cpt_off[-1]), dtype=np.float64)
+    _capi.check(lib.bnbp_estimate_cpt(C.byref(_net_c(net)), _vp(samples), _vp(mult), C.c_int64(samples.shape[0]),
+                                      C.c_int32(device), _vp(out)))
+    return out
+
+
 @dataclass
 class BPResult:
     marginals: np.ndarray      # [n_cases, sum r_X] (float64 on the host path)
@@ -124,6 +142,23 @@ class BeliefPropagation:
         prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval))
         _capi.check(self._lib.bnbp_run_batch_device(self._h, C.byref(evc), C.byref(prm), dp(out), dp(out_sweeps),
                                                     dp(out_converged), C.c_void_p(stream) if stream else None))
+
+    # ---- likelihood weighting ------------------------------------------------------
+    def likelihood_weighting(self, evidence: EvidenceBatch, n_samples: int = 10000, seed: int = 1,
+                             return_weight: bool = False):
+        """``likelihood_weighting::operator()(evidence_list, sample_num)`` (likelihood_weighting.hpp:28-59)
+        for a batch of hard-evidence cases on the GPU (``bnbp_lw_run_batch``): marginals [n_cases, sum r_X]
+        (and the total sample weight per case).  Reproducible: the variates are a function of ``seed``."""
+        ev = evidence
+        if ev.is_soft:
+            raise ValueError("likelihood weighting takes hard evidence (vertex -> state)")
+        n, V = ev.n_cases, self.net.belief_values
+        out = np.empty((n, V), dtype=np.float64)
+        wsum = np.empty(n, dtype=np.float64)
+        evc = _capi.EvidenceC(n, _vp(ev.ev_off), _vp(ev.ev_node), _vp(ev.ev_state), None, None)
+        _capi.check(self._lib.bnbp_lw_run_batch(self._h, C.byref(evc), C.c_int64(int(n_samples)),
+                                                C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _vp(out), _vp(wsum)))
+        return (out, wsum) if return_weight else out
 
     def stats(self) -> dict:
         st = _capi.StatsC()

@@ -68,6 +68,15 @@ class ClockSampler:
         for line in self.proc.stdout:
             self.rows.append(line.strip())
 
+    def wait_first(self, timeout: float = 3.0) -> None:
+        t0 = time.time()
+        while self.proc is not None and not self.rows and time.time() - t0 < timeout:
+            time.sleep(0.02)
+
+    def mark(self) -> None:
+        """Samples before this point (warm-up) are not part of the report."""
+        self.first = len(self.rows)
+
     def stop(self) -> dict:
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
@@ -78,7 +87,8 @@ class ClockSampler:
         except Exception:
             self.proc.kill()
         sm, mx, reasons, power = [], [], set(), []
-        for row in self.rows:
+        rows = self.rows[getattr(self, "first", 0):] or self.rows[-1:]
+        for row in rows:
             f = [x.strip() for x in row.split(",")]
             if len(f) < 7:
                 continue
@@ -193,7 +203,7 @@ def run_reference_arm(args, rank: int, world: int):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=20)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="bnbp", choices=["bnbp", "reference"])
     ap.add_argument("--workload", default="alarm37", choices=sorted(synth.WORKLOADS))
@@ -276,12 +286,19 @@ def main():
             dist.barrier()
         torch.cuda.synchronize()
 
+    # nvidia-smi is started BEFORE the warm-up: its NVML initialisation takes driver locks and, started
+    # right in front of the timed region, stalled the first timed launches by 7-70 ms (r01l); only the
+    # samples taken after mark() are reported
+    sampler = ClockSampler(local_rank) if rank == 0 else None
+    if sampler:
+        sampler.wait_first()
     for _ in range(args.warmup):
         step()
     barrier()
-    sampler = ClockSampler(local_rank) if rank == 0 else None
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
+    if sampler:
+        sampler.mark()
     e0.record()
     for _ in range(args.steps):
         step()
@@ -383,7 +400,7 @@ def main():
         p_out = torch.empty((n, V), dtype=torch.float64, pin_memory=True)
         ev_pinned = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
         out_np = p_out.numpy()
-        e2e_steps = max(1, min(args.steps, 5))
+        e2e_steps = max(1, min(args.steps, 10))
         bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)      # warm-up (staging buffers)
         barrier()
         t0 = time.perf_counter()
@@ -410,7 +427,8 @@ def main():
                "h2d_bytes_per_step": int(ev.nbytes()), "d2h_bytes_per_step": int(n * V * 8 + n * 5),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "d2h_link_gbs_measured": d2h_gbs, "d2h_floor_ms_per_step": 1e3 * n * V * 8 / (d2h_gbs * 1e9),
-               "pipeline": "8 chunks, D2H of chunk i overlaps init/sweeps/beliefs of chunk i+1"}
+               "pipeline": "three streams: evidence H2D of chunk i+1 and marginal D2H of chunk i-1 overlap the kernels "
+                           "of chunk i; chunks cut in whole waves of the sweep grid (BNBP_TRACE=1 prints the plan)"}
 
     # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle port on all host cores ---------------
     cpu = None

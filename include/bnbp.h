@@ -19,6 +19,8 @@
  *   bnbp_refresh_cpt   <- the reference reads vertex_t::cpt at call time (graph.hpp:157-161), so
  *                         CPT edits between calls are visible; here they need this call
  *   bnbp_precompile / bnbp_spec_source  (new: the network compiler, see BNBP_SPEC_* below)
+ *   bnbp_lw_run_batch  <- likelihood_weighting::operator()  bayesian/inference/likelihood_weighting.hpp:28-59
+ *   bnbp_estimate_cpt  <- sampler::make_cpt                  bayesian/sampler.hpp:81-163
  *   bnbp_netfile_*     <- serializer::bif::parse (serializer/bif.hpp:41-132) and serializer::dsc::parse
  *                         (serializer/dsc.hpp:33-232): network files -> bnbp_flat_network
  *
@@ -127,7 +129,8 @@ typedef struct bnbp_stats {
     int64_t cpt_values;              /* reference-layout CPT entries                             */
     int64_t bytes_per_value;         /* 8 or 4                                                   */
     int64_t last_case_sweeps;        /* sum over cases of sweeps executed by the last run       */
-    int64_t last_sweep_launches;     /* sweep-kernel launches of the last run                   */
+    int64_t last_sweep_launches;     /* sweeps enqueued by the last run (a fixed-count run of a specialised
+                                        network puts its middle sweeps into ONE looping launch)  */
     int64_t last_kernel_launches;    /* all kernel launches of the last run                     */
     double  last_sweep_ms;           /* device time of the sweep launches (CUDA events)         */
     double  last_total_ms;           /* device time init..beliefs of the last run               */
@@ -143,6 +146,8 @@ typedef struct bnbp_stats {
     int64_t dense_tensor_jobs;       /* dense products (two per node) that run on the tensor cores */
     double  dense_tensor_flops_per_case_sweep; /* their algorithmic flops, 2*K*N each (x3 issued: hi/lo split) */
     int64_t last_dense_tensor_launches;
+    int64_t last_fused;              /* 1 if the last run formed the time-0 state inside the first sweep and the
+                                        marginals inside the last one (no separate init / belief kernels) */
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;
@@ -167,6 +172,25 @@ int  bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_para
 int  bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm,
                            void* out_marginals, int32_t* out_sweeps, uint8_t* out_converged,
                            void* stream);
+
+/* Likelihood weighting for a batch of HARD-evidence cases: the independent statistical
+ * check of BP marginals on loopy networks.  Replaces likelihood_weighting::operator()(evidence_list,
+ * sample_num) (bayesian/inference/likelihood_weighting.hpp:28-59, weighted_sample :122-173) for
+ * n_cases evidence sets at once.  The reference seeds a mt19937 from std::random_device; here the
+ * uniform variate of (case, sample, node) is a pure function of `seed` (splitmix64), so a run is
+ * reproducible and independent of how cases are spread over launches or GPUs.
+ *   out_marginals  [n_cases][belief_values_per_case], same layout as bnbp_run_batch
+ *   out_weight_sum [n_cases] total sample weight (estimate of n_samples * P(evidence)); may be NULL */
+int  bnbp_lw_run_batch(bnbp_handle* h, const bnbp_evidence* ev, int64_t n_samples, uint64_t seed,
+                       double* out_marginals, double* out_weight_sum);
+
+/* CPT estimation from a table of samples on the device.  Replaces sampler::make_cpt
+ * (bayesian/sampler.hpp:81-163): samples[row][node] is the state of every node in one distinct sample,
+ * multiplicity[row] how often it occurred (NULL = once; the first column of the reference's sample
+ * file, sampler.hpp:53-76).  out_cpt gets the CPT arena in the layout of bnbp_flat_network.cpt
+ * (net->cpt itself is not read): count / row total, uniform 1/card for configurations never seen. */
+int  bnbp_estimate_cpt(const bnbp_flat_network* net, const int32_t* samples, const int64_t* multiplicity,
+                       int64_t n_rows, int32_t device, double* out_cpt);
 
 int  bnbp_get_stats(const bnbp_handle* h, bnbp_stats* out);
 

@@ -324,3 +324,132 @@ int bp_oracle_run(int32_t n_nodes, const int32_t* card, const int32_t* parent_of
     free_net(&g);
     return err;
 }
+
+/* ------------------------------------------------------------------------------------------------
+ * Likelihood weighting -- restatement of bayesian/inference/likelihood_weighting.hpp
+ *   operator()             :28-59
+ *   weighted_sample        :122-173  (parents before children; observed node: w *= CPT entry)
+ *   make_random_by_weight  :177-194
+ *   normalize              :198-224  (sum < 1e-20 -> uniform)
+ * The reference draws from a std::mt19937 seeded by std::random_device (:229-237), so its output is not
+ * reproducible: parity with it is statistical (tests/test_lw.py compares against oracle/_ref/libbnref_lw.so
+ * within sampling error, and against exact enumeration).  The variate of (case, sample, node) used here is
+ * the counter-based one of csrc/bnbp_lw.cuh, restated below, so the CUDA kernel can be checked draw for draw. */
+static uint64_t lw_mix(uint64_t z)
+{
+    z += 0x9E3779B97F4A7C15ull;
+    z = (z ^ (z >> 30)) * 0xBF58476D1CE4E5B9ull;
+    z = (z ^ (z >> 27)) * 0x94D049BB133111EBull;
+    return z ^ (z >> 31);
+}
+
+int bp_oracle_lw(int32_t n_nodes, const int32_t* card, const int32_t* parent_off,
+                 const int32_t* parents, const int64_t* cpt_off, const double* cpt,
+                 int64_t n_cases, const int64_t* ev_off, const int32_t* ev_node, const int32_t* ev_state,
+                 int64_t n_samples, uint64_t seed, int64_t case_base, double* out, double* out_wsum)
+{
+    int32_t n = n_nodes;
+    int64_t V = 0;
+    int64_t* voff = (int64_t*)malloc(sizeof(int64_t) * ((size_t)n + 1));
+    int32_t* order = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* indeg = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* obs = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    int32_t* st = (int32_t*)malloc(sizeof(int32_t) * (size_t)n);
+    if (!voff || !order || !indeg || !obs || !st) return -1;
+    voff[0] = 0;
+    for (int32_t i = 0; i < n; ++i) voff[i + 1] = voff[i] + card[i];
+    V = voff[n];
+    double* hist = (double*)malloc(sizeof(double) * (size_t)V);
+    if (!hist) return -1;
+    /* any topological order gives the same sample: the variates are keyed by node, not by draw order */
+    int32_t done = 0;
+    for (int32_t i = 0; i < n; ++i) indeg[i] = parent_off[i + 1] - parent_off[i];
+    while (done < n) {
+        int32_t before = done;
+        for (int32_t i = 0; i < n; ++i) {
+            if (indeg[i] != 0) continue;
+            order[done++] = i;
+            indeg[i] = -1;
+            for (int32_t j = 0; j < n; ++j)
+                for (int32_t e = parent_off[j]; e < parent_off[j + 1]; ++e)
+                    if (parents[e] == i) indeg[j]--;
+        }
+        if (done == before) return -2;          /* cycle */
+    }
+    for (int64_t c = 0; c < n_cases; ++c) {
+        for (int64_t j = 0; j < V; ++j) hist[j] = 0.0;
+        for (int32_t i = 0; i < n; ++i) obs[i] = -1;
+        for (int64_t e = ev_off[c]; e < ev_off[c + 1]; ++e) obs[ev_node[e]] = ev_state[e];
+        uint64_t ckey = lw_mix(seed ^ lw_mix((uint64_t)(case_base + c)));
+        for (int64_t s = 0; s < n_samples; ++s) {
+            uint64_t skey = lw_mix(ckey + (uint64_t)s);
+            double w = 1.0;
+            for (int32_t i = 0; i < n; ++i) {
+                int32_t x = order[i];
+                int64_t q = 0;
+                for (int32_t e = parent_off[x]; e < parent_off[x + 1]; ++e) q = q * card[parents[e]] + st[parents[e]];
+                const double* row = cpt + cpt_off[x] + q * card[x];
+                if (obs[x] >= 0) {                              /* :152-156 */
+                    w *= row[obs[x]];
+                    st[x] = obs[x];
+                } else {                                        /* :157-161, :177-194 */
+                    double u = (double)(lw_mix(skey ^ (uint64_t)(uint32_t)x) >> 11) * (1.0 / 9007199254740992.0);
+                    int32_t sel = card[x] - 1;
+                    double total = 0.0;
+                    for (int32_t v = 0; v < card[x]; ++v) {
+                        double old_total = total;
+                        total += row[v];
+                        if (old_total <= u && u < total) { sel = v; break; }
+                    }
+                    st[x] = sel;
+                }
+            }
+            for (int32_t x = 0; x < n; ++x) hist[voff[x] + st[x]] += w;      /* :44-48 */
+        }
+        for (int32_t x = 0; x < n; ++x) {                       /* :52-55 */
+            double sum = 0.0;
+            for (int32_t v = 0; v < card[x]; ++v) sum += hist[voff[x] + v];
+            for (int32_t v = 0; v < card[x]; ++v)
+                out[c * V + voff[x] + v] = sum < 1.0e-20 ? 1.00 / card[x] : hist[voff[x] + v] / sum;
+            if (x == 0 && out_wsum) out_wsum[c] = sum;
+        }
+    }
+    free(voff); free(order); free(indeg); free(obs); free(st); free(hist);
+    return 0;
+}
+
+/* ------------------------------------------------------------------------------------------------
+ * CPT estimation -- restatement of bayesian/sampler.hpp make_cpt :81-163 over flat arrays:
+ * counter[(node, parent configuration)][state] += multiplicity (:104-128); row = count / total,
+ * uniform 1/r for a configuration that never occurred (:131-160).
+ * Parity status: the reference's sampler.hpp needs Boost (absent here), so this restatement is pinned by
+ * hand-computed known answers and by the reference's own bayesian_network/sampler test data where they
+ * apply (tests/test_cpt_estimation.py), not by a compiled reference. */
+int bp_oracle_make_cpt(int32_t n_nodes, const int32_t* card, const int32_t* parent_off, const int32_t* parents,
+                       const int64_t* cpt_off, const int32_t* samples, const int64_t* mult, int64_t n_rows, double* out_cpt)
+{
+    int64_t total = cpt_off[n_nodes];
+    uint64_t* cnt = (uint64_t*)calloc((size_t)(total > 0 ? total : 1), sizeof(uint64_t));
+    if (!cnt) return -1;
+    for (int64_t r = 0; r < n_rows; ++r) {
+        const int32_t* s = samples + r * n_nodes;
+        for (int32_t x = 0; x < n_nodes; ++x) {
+            int64_t q = 0;
+            for (int32_t e = parent_off[x]; e < parent_off[x + 1]; ++e) q = q * card[parents[e]] + s[parents[e]];
+            cnt[cpt_off[x] + q * card[x] + s[x]] += (uint64_t)(mult ? mult[r] : 1);
+        }
+    }
+    for (int32_t x = 0; x < n_nodes; ++x) {
+        int64_t rows = (cpt_off[x + 1] - cpt_off[x]) / card[x];
+        for (int64_t q = 0; q < rows; ++q) {
+            uint64_t tot = 0;
+            for (int32_t v = 0; v < card[x]; ++v) tot += cnt[cpt_off[x] + q * card[x] + v];
+            double parameter = (double)tot;
+            for (int32_t v = 0; v < card[x]; ++v)
+                out_cpt[cpt_off[x] + q * card[x] + v] = tot == 0 ? 1.0 / (double)card[x]
+                                                                 : (double)cnt[cpt_off[x] + q * card[x] + v] / parameter;
+        }
+    }
+    free(cnt);
+    return 0;
+}

@@ -77,6 +77,61 @@ def run_port(net, ev, eps=1e-3, max_sweeps=0, damping=0.0, check_interval=1, thr
     return out, sweeps, conv
 
 
+def run_port_lw(net, ev, n_samples, seed=1, case_base=0):
+    """C restatement of the reference's likelihood weighting with the counter-based variates of
+    csrc/bnbp_lw.cuh.  Returns (marginals [B, sum r], total weight [B])."""
+    global _port
+    if _port is None:
+        _port = C.CDLL(PORT_SO)
+    out = np.empty((ev.n_cases, net.belief_values), dtype=np.float64)
+    wsum = np.empty(ev.n_cases, dtype=np.float64)
+    _port.bp_oracle_lw.restype = C.c_int
+    rc = _port.bp_oracle_lw(*_net_args(net), C.c_int64(ev.n_cases), _ptr(ev.ev_off, C.c_int64),
+                            _ptr(ev.ev_node, C.c_int32), _ptr(ev.ev_state, C.c_int32), C.c_int64(n_samples),
+                            C.c_uint64(seed), C.c_int64(case_base), _ptr(out, C.c_double), _ptr(wsum, C.c_double))
+    if rc != 0:
+        raise RuntimeError("bp_oracle_lw failed")
+    return out, wsum
+
+
+def port_make_cpt(net, samples, multiplicity=None):
+    """C restatement of sampler::make_cpt (sampler.hpp:81-163) over flat arrays."""
+    global _port
+    if _port is None:
+        _port = C.CDLL(PORT_SO)
+    samples = np.ascontiguousarray(samples, dtype=np.int32)
+    mult = None if multiplicity is None else np.ascontiguousarray(multiplicity, dtype=np.int64)
+    out = np.empty(int(net.cpt_off[-1]), dtype=np.float64)
+    _port.bp_oracle_make_cpt.restype = C.c_int
+    rc = _port.bp_oracle_make_cpt(C.c_int32(net.n_nodes), _ptr(net.card, C.c_int32), _ptr(net.parent_off, C.c_int32),
+                                  _ptr(net.parents, C.c_int32), _ptr(net.cpt_off, C.c_int64), _ptr(samples, C.c_int32),
+                                  _ptr(mult, C.c_int64), C.c_int64(samples.shape[0]), _ptr(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError("bp_oracle_make_cpt failed")
+    return out
+
+
+REF_LW_SO = os.path.join(HERE, "_ref", "libbnref_lw.so")
+
+
+def have_reference_lw() -> bool:
+    return os.path.exists(REF_LW_SO)
+
+
+def run_reference_lw(net, ev, n_samples):
+    """The reference's own likelihood_weighting (random_device-seeded: differs run to run)."""
+    if REF_LW_SO not in _ref:
+        _ref[REF_LW_SO] = C.CDLL(REF_LW_SO)
+    lib = _ref[REF_LW_SO]
+    out = np.empty((ev.n_cases, net.belief_values), dtype=np.float64)
+    lib.bnref_lw.restype = C.c_int
+    rc = lib.bnref_lw(*_net_args(net), C.c_int64(ev.n_cases), _ptr(ev.ev_off, C.c_int64), _ptr(ev.ev_node, C.c_int32),
+                      _ptr(ev.ev_state, C.c_int32), C.c_int64(n_samples), _ptr(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError("bnref_lw failed")
+    return out
+
+
 _ref = {}
 
 

@@ -19,13 +19,13 @@ def jobs():
         for prec in ("fp64", "fp32"):
             if prec == "fp32" and eps > 0:
                 continue
-            out.append((net, prec, 0b00100 if eps > 0 else 0b11001))
+            out.append((net, prec, 0b00100 if eps > 0 else 0b11111001))
     fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz"), allow_pickle=False)
     for name in ["pearl_tests", "pearl_nan_fixed6", "resume_tests"]:
         f = load_fixture(fx, name)
-        out.append((f["net"], "fp64", 0b11101))
+        out.append((f["net"], "fp64", 0b11111101))
     from bayesiannetwork_b200 import synth
-    out.append((synth.grid(5, seed=8), "fp64", 0b11111))
+    out.append((synth.grid(5, seed=8), "fp64", 0b11111111))
     return out
 
 

@@ -65,3 +65,10 @@ def test_reference_bp_tests_pass_on_the_gpu_backend():
 def test_own_cpp_tests_on_the_gpu_backend():
     out = _run(os.path.join(OWN_BIN, "test_dropin_batch"))
     assert out.count("[  ok  ]") == 8, out
+
+
+@pytest.mark.gpu
+def test_own_cpp_lw_and_sampler_tests_on_the_gpu_backend():
+    """likelihood_weighting.hpp / sampler.hpp drop-ins through the reference's call shapes."""
+    out = _run(os.path.join(OWN_BIN, "test_dropin_lw"))
+    assert out.count("[  ok  ]") == 2, out

@@ -92,6 +92,54 @@ def test_specialised_short_fixed_runs(BP, oracle_mod, cap):
     assert_close(res.marginals, om, what=f"{cap} sweeps", **TOL["fp64"])
 
 
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+@pytest.mark.parametrize("n_cases", [1, 777, 4096 + 33])
+def test_fused_first_and_last_sweep_bitwise(BP, monkeypatch, precision, n_cases):
+    """Fixed sweeps + hard evidence: K0 runs inside the first sweep and K4 inside the last (variants 5
+    and 6/7 of bnbp_spec.cuh).  Same arithmetic in the same order as the unfused launch sequence, so
+    the marginals are bit-identical -- through the host-buffer call (doubles out of a float kernel:
+    variant 7) and through the device call (marginals in the kernel's own type: variant 6)."""
+    import torch
+    net = synth.alarm37()
+    ev = synth.make_evidence(net, n_cases, exact_k=4, seed=3)
+    bp = BP(net, precision, specialize="always")
+    dev = torch.device("cuda", 0)
+    d_off, d_node, d_state = (torch.from_numpy(a).to(dev) for a in (ev.ev_off, ev.ev_node, ev.ev_state))
+    tdt = torch.float64 if precision == "fp64" else torch.float32
+
+    def both():
+        host = bp(ev, 0.0, max_sweeps=6)
+        fused = bp.stats()["last_fused"]
+        d_out = torch.full((n_cases, net.belief_values), -7.0, dtype=tdt, device=dev)
+        d_sw = torch.zeros(n_cases, dtype=torch.int32, device=dev)
+        bp.run_device(n_cases, d_off, d_node, d_state, d_out, epsilon=0.0, max_sweeps=6, out_sweeps=d_sw)
+        torch.cuda.synchronize()
+        return host, d_out.cpu().numpy(), d_sw.cpu().numpy(), fused, bp.stats()["last_fused"]
+
+    h1, dv1, sw1, f1a, f1b = both()
+    assert f1a == 1 and f1b == 1
+    monkeypatch.setenv("BNBP_NO_FUSE", "1")
+    h0, dv0, sw0, f0a, f0b = both()
+    assert f0a == 0 and f0b == 0
+    assert np.array_equal(h1.marginals, h0.marginals, equal_nan=True)
+    assert np.array_equal(dv1, dv0, equal_nan=True)
+    assert np.array_equal(h1.sweeps, h0.sweeps) and np.array_equal(sw1, sw0) and np.all(sw1 == 6)
+    assert np.array_equal(h1.converged, h0.converged)
+
+
+def test_fused_sequence_soft_evidence_falls_back_to_k0_k4(BP, oracle_mod):
+    """Soft evidence rows do not fit the one-byte state table of the fused first sweep: the unfused
+    sequence (still the specialised GPU kernels) runs, and matches the oracle."""
+    net = synth.alarm37()
+    ev = synth.make_evidence(net, 500, exact_k=4, soft=True, seed=5)
+    bp = BP(net, "fp64", specialize="always")
+    res = bp(ev, 0.0, max_sweeps=8)
+    st = bp.stats()
+    assert st["last_specialised"] == 1 and st["last_fused"] == 0
+    om, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=8, threads=0)
+    assert_close(res.marginals, om, what="soft", **TOL["fp64"])
+
+
 def test_specialised_equals_generic_bitwise_shape(BP):
     """Both kernel families implement the same schedule: fixed sweeps, same sweep counts, results
     within a few ulp of each other (they differ only in the order of some products)."""
