@@ -85,6 +85,10 @@ def load():
     lib.bnbp_run_batch_device.restype = C.c_int
     lib.bnbp_run_batch_device.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.POINTER(RunParamsC),
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bnbp_lw_run_batch.restype = C.c_int
+    lib.bnbp_lw_run_batch.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
+    lib.bnbp_estimate_cpt.restype = C.c_int
+    lib.bnbp_estimate_cpt.argtypes = [C.POINTER(FlatNetworkC), C.c_void_p, C.c_void_p, C.c_int64, C.c_int32, C.c_void_p]
     lib.bnbp_get_stats.restype = C.c_int
     lib.bnbp_get_stats.argtypes = [C.c_void_p, C.POINTER(StatsC)]
     lib.bnbp_refresh_cpt.restype = C.c_int

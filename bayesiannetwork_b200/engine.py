@@ -56,8 +56,8 @@ def estimate_cpt(net: FlatNetwork, samples: np.ndarray, multiplicity: Optional[n
     if mult is not None and mult.shape != (samples.shape[0],):
         raise ValueError("multiplicity must be [n_rows]")
     out = np.empty(int(net.cpt_off[-1]), dtype=np.float64)
-    _capi.check(lib.bnbp_estimate_cpt(C.byref(_net_c(net)), _vp(samples), _vp(mult), C.c_int64(samples.shape[0]),
-                                      C.c_int32(device), _vp(out)))
+    _capi.check(lib.bnbp_estimate_cpt(C.byref(_net_c(net)), _vp(samples), _vp(mult), int(samples.shape[0]),
+                                      int(device), _vp(out)))
     return out
 
 
@@ -156,8 +156,8 @@ class BeliefPropagation:
         out = np.empty((n, V), dtype=np.float64)
         wsum = np.empty(n, dtype=np.float64)
         evc = _capi.EvidenceC(n, _vp(ev.ev_off), _vp(ev.ev_node), _vp(ev.ev_state), None, None)
-        _capi.check(self._lib.bnbp_lw_run_batch(self._h, C.byref(evc), C.c_int64(int(n_samples)),
-                                                C.c_uint64(int(seed) & 0xFFFFFFFFFFFFFFFF), _vp(out), _vp(wsum)))
+        _capi.check(self._lib.bnbp_lw_run_batch(self._h, C.byref(evc), int(n_samples), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                                _vp(out), _vp(wsum)))
         return (out, wsum) if return_weight else out
 
     def stats(self) -> dict:
