@@ -105,6 +105,10 @@ struct bnbp_handle {
     bool fuse = false;                 // this run: K0 inside the first sweep, K4 inside the last (variants 5, 6/7)
     int last_fused = 0;
     bool fuse_ok = true;               // cleared when a fused variant failed to build: the unfused launch sequence runs
+    // eps mode: compaction of the still-active cases into a second arena (compact_* kernels, bnbp_kernels.cuh)
+    DevBuf d_pl2, d_msg2[2], d_evbits2, d_orig[2], d_src_pos, d_tile_count;
+    bool compact_ok = true;            // cleared when the second arena does not fit
+    int64_t last_compactions = 0;
     DevBuf d_evst;                     // [tiles][N][tb] evidence-state bytes of the resident chunk
     bool run_spec = false;             // kernel family of the current run
     int last_specialised = 0;
@@ -413,6 +417,19 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         h->last_kernel_launches++;
     }
 
+    // the arena the sweeps work on: the handle's own, or (eps mode, after a compaction) the second one
+    T* pl_p = (T*)h->d_pl.p;
+    T* msg_p[2] = {(T*)h->d_msg[0].p, (T*)h->d_msg[1].p};
+    uint32_t* evb_p = (uint32_t*)h->d_evbits.p;
+    int arena_set = 0;
+    int64_t n_cur = n;                       // cases (positions) of the current arena
+    int tiles_cur = tiles;
+    const int32_t* orig = nullptr;           // position -> case of the chunk (nullptr: identity)
+    int orig_set = 0;
+    // Compaction pays when the sweep counts spread (alarm37, eps 1e-6: mean 13, max 40 sweeps).  Not with
+    // dense nodes (their per-case tables live in a third arena) and not for small batches.
+    const bool compact = eps_mode && h->compact_ok && h->TS == 0 && n >= 16384 && !getenv("BNBP_NO_COMPACT");
+
     SweepArgs<T> sa;
     memset(&sa, 0, sizeof sa);
     sa.nodes = (const NodeMeta*)h->d_nodes.p;
@@ -420,8 +437,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.e_lam_out = (const int32_t*)h->d_e_lam_out.p;
     sa.c_pi_out = (const int32_t*)h->d_c_pi_out.p;
     sa.cpt = (const T*)h->d_cpt.p;
-    sa.pl = (T*)h->d_pl.p;
-    sa.evbits = (const uint32_t*)h->d_evbits.p;
+    sa.pl = pl_p;
+    sa.evbits = evb_p;
     sa.PL = h->PL; sa.M = h->M; sa.W = h->W; sa.TS = h->TS;
     sa.tscr = (const T*)h->d_tscr.p;
     // enough threads to fill 148 SMs a few times over: split the node walk when the batch is small
@@ -438,6 +455,14 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     T* delta = (T*)h->d_delta.p;
     const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * sizeof(T);
     dim3 grid(tiles, n_chunks);
+    auto regrid = [&]() {                    // after a compaction: fewer tiles, maybe more node chunks
+        const int64_t tpr = (int64_t)tiles_cur * BLOCK_THREADS;
+        n_chunks = (int)std::min<int64_t>(std::min(MAX_CHUNKS, std::max(1, h->N / 8)),
+                                          std::max<int64_t>(1, (148 * 2048 * 2 + tpr - 1) / tpr));
+        sa.n_chunks = n_chunks;
+        make_chunks(h, n_chunks, sa.chunk_off);
+        grid = dim3(tiles_cur, n_chunks);
+    };
 
     // event pair around the sweeps of this chunk
     if ((int)h->ev_sweep.size() < 2 * (h->ev_sweep_used + 1)) {
@@ -451,7 +476,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
 
     int t = 0;
     bool prev_tested = false;
-    const int POLL = 8;
+    const int POLL = compact ? 4 : 8;
     int polls_issued = 0;
     bool stop = false;
     while (t < max_sweeps && !stop) {
@@ -459,8 +484,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         for (; t < t_end; ++t) {
             const bool tested = eps_mode && (((t + 1) % interval) == 0 || t + 1 >= max_sweeps);
             const bool check = tested || prm.damping != 0.0;
-            sa.msg_cur = (const T*)h->d_msg[t & 1].p;
-            sa.msg_nxt = (T*)h->d_msg[(t + 1) & 1].p;
+            sa.msg_cur = msg_p[t & 1];
+            sa.msg_nxt = msg_p[(t + 1) & 1];
             sa.delta_prev = delta + (size_t)((t + 2) % 3) * h->cap;
             sa.delta_cur = delta + (size_t)(t % 3) * h->cap;
             sa.delta_next = delta + (size_t)((t + 1) % 3) * h->cap;
@@ -535,14 +560,22 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 ax.status = sa.status; ax.sweeps = sa.sweeps; ax.last_active = sa.last_active;
                 ax.sweep_index = sa.sweep_index; ax.prev_tested = sa.prev_tested; ax.eps = sa.eps; ax.damping = sa.damping;
                 ax.evst = (const unsigned char*)h->d_evst.p; ax.out = d_out; ax.n_valid = n;
-                // fixed-count runs: the plain sweeps between the first and the last go out as ONE launch
-                // (cases are independent, no barrier between their sweeps is needed)
+                // fixed-count runs: the plain sweeps between the first and the last can go out as ONE launch
+                // (cases are independent, no barrier between their sweeps is needed).  A looped launch ends with
+                // ONE tail of up to a whole block lifetime (n_inner sweeps), separate launches with n_inner short
+                // ones: looping wins for grids of whole waves and for short grids (the chunks of the host-buffer
+                // pipeline, +3 % e2e), separate launches for one long ragged grid (18.45 waves: -3 %, r01o).
                 ax.n_inner = 1;
-                if (variant == 0 && !eps_mode && prm.damping == 0.0 && !getenv("BNBP_NO_LOOP"))
-                    ax.n_inner = (max_sweeps >= 2 ? max_sweeps - 1 : max_sweeps) - t;
+                if (variant == 0 && !eps_mode && prm.damping == 0.0 && !getenv("BNBP_NO_LOOP")) {
+                    int sms = 148;
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+                    const int64_t wave_blocks = (int64_t)sms * std::max(1, h->spec[0].blocks_per_sm);
+                    if (tiles_cur % wave_blocks == 0 || tiles_cur < 12 * wave_blocks || getenv("BNBP_LOOP_ALWAYS"))
+                        ax.n_inner = (max_sweeps >= 2 ? max_sweeps - 1 : max_sweeps) - t;
+                }
                 n_inner = ax.n_inner;
                 std::string err;
-                if (!spec_launch(h->spec[variant], (unsigned)tiles, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
+                if (!spec_launch(h->spec[variant], (unsigned)tiles_cur, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
                     return fail(BNBP_ERR_CUDA, err);
             } else {
                 cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode, check, st);
@@ -553,7 +586,85 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             h->last_kernel_launches++;
             t += n_inner - 1;
         }
-        if (eps_mode && t < max_sweeps) {
+        if (compact && t < max_sweeps && t >= 8) {
+            // census: the freeze rule of the next launch, active cases per tile and in total (one host
+            // round trip per POLL sweeps; the grid that follows is sized by its answer)
+            int rc;
+            if ((rc = h->d_tile_count.ensure((size_t)tiles * 8))) return rc;
+            int32_t* const d_total = d_last_active + 2;
+            int32_t* const d_tile_cnt = (int32_t*)h->d_tile_count.p;
+            int32_t* const d_tile_off = d_tile_cnt + tiles;
+            CU_TRY(cudaMemsetAsync(d_total, 0, 4, st));
+            compact_census_kernel<T><<<tiles_cur, h->tb, 0, st>>>((uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p,
+                                                                  delta + (size_t)((t + 2) % 3) * h->cap, prev_tested ? 1 : 0,
+                                                                  (T)prm.epsilon, t, d_tile_cnt, d_total);
+            CU_TRY(cudaGetLastError());
+            h->last_kernel_launches++;
+            CU_TRY(cudaMemcpyAsync(&h->pinned_poll[2], d_total, 4, cudaMemcpyDeviceToHost, st));
+            CU_TRY(cudaStreamSynchronize(st));
+            const int64_t n_active = h->pinned_poll[2];
+            if (n_active == 0) {
+                stop = true;
+            } else if (n_active * 10 <= n_cur * 7 && n_cur >= 8192) {
+                const int64_t tiles_new = (n_active + h->tb - 1) / h->tb;
+                const size_t want = (size_t)tiles_new * h->tb;
+                DevBuf* pl_b[2] = {&h->d_pl, &h->d_pl2};
+                DevBuf* m0_b[2] = {&h->d_msg[0], &h->d_msg2[0]};
+                DevBuf* m1_b[2] = {&h->d_msg[1], &h->d_msg2[1]};
+                DevBuf* ev_b[2] = {&h->d_evbits, &h->d_evbits2};
+                const int dst = arena_set ^ 1;
+                bool fits = true;
+                if (dst == 1) {                                  // set 0 is the handle's full-size arena
+                    cudaGetLastError();
+                    fits = h->d_pl2.ensure(want * h->PL * sizeof(T)) == BNBP_OK &&
+                           h->d_msg2[0].ensure(std::max<size_t>(16, want * h->M * sizeof(T))) == BNBP_OK &&
+                           h->d_msg2[1].ensure(std::max<size_t>(16, want * h->M * sizeof(T))) == BNBP_OK &&
+                           h->d_evbits2.ensure(want * h->W * 4) == BNBP_OK;
+                    if (!fits) {                                 // HBM is full: carry on in place, never try again
+                        cudaGetLastError();
+                        h->d_pl2.release(); h->d_msg2[0].release(); h->d_msg2[1].release(); h->d_evbits2.release();
+                        h->compact_ok = false;
+                    }
+                }
+                if (fits && (h->d_orig[0].ensure((size_t)h->cap * 4) || h->d_orig[1].ensure((size_t)h->cap * 4) ||
+                             h->d_src_pos.ensure((size_t)h->cap * 4)))
+                    fits = false;
+                if (fits) {
+                    // 1. retire the converged cases: their state is final (:135-147), write their beliefs now
+                    bnbp_handle::BeliefPlan* plan = nullptr;
+                    if ((rc = belief_plan(h, h->tb, (int)sizeof(OUT), &plan))) return rc;
+                    if (plan->smem > 48 * 1024)
+                        CU_TRY(cudaFuncSetAttribute(belief_tiled_kernel<T, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
+                    belief_tiled_kernel<T, OUT><<<tiles_cur, h->tb, plan->smem, st>>>(
+                        (const NodeMeta*)h->d_nodes.p, (const BeliefGroup*)plan->groups.p, plan->n_groups, pl_p, h->PL,
+                        h->tb, h->V, plan->stride, n_cur, d_out, (const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
+                        d_out_sweeps, d_out_conv, orig, 1);
+                    CU_TRY(cudaGetLastError());
+                    // 2. new position -> old position (stable), 3. gather into the other arena
+                    compact_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, d_tile_off, tiles_cur);
+                    int32_t* const orig_new = (int32_t*)h->d_orig[orig_set ^ 1].p;
+                    compact_index_kernel<<<tiles_cur, h->tb, 0, st>>>((const uint8_t*)h->d_status.p, d_tile_off, orig,
+                                                                      (int32_t*)h->d_src_pos.p, orig_new);
+                    CU_TRY(cudaGetLastError());
+                    T* const pl_d = (T*)pl_b[dst]->p;
+                    T* const md[2] = {(T*)m0_b[dst]->p, (T*)m1_b[dst]->p};
+                    uint32_t* const ev_d = (uint32_t*)ev_b[dst]->p;
+                    compact_gather_kernel<T><<<(unsigned)tiles_new, h->tb, 0, st>>>(
+                        (const int32_t*)h->d_src_pos.p, (int32_t)n_active, h->tb, h->PL, h->M, h->W, pl_p, msg_p[t & 1], evb_p,
+                        pl_d, md[t & 1], ev_d, (uint8_t*)h->d_status.p, delta, h->cap);
+                    CU_TRY(cudaGetLastError());
+                    h->last_kernel_launches += 4;
+                    h->last_compactions++;
+                    pl_p = pl_d; msg_p[0] = md[0]; msg_p[1] = md[1]; evb_p = ev_d;
+                    arena_set = dst;
+                    orig = orig_new; orig_set ^= 1;
+                    n_cur = n_active; tiles_cur = (int)tiles_new;
+                    sa.pl = pl_p; sa.evbits = evb_p;
+                    regrid();
+                    prev_tested = false;                         // the census already froze what the last test found
+                }
+            }
+        } else if (eps_mode && !compact && t < max_sweeps) {
             // asynchronous termination poll: keep one batch of launches in flight while the flag
             // of the batch before travels back (speculative launches exit on the device at once)
             const int slot = polls_issued & 1;
@@ -575,9 +686,9 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     h->ev_sweep_used++;
     if (eps_mode) {
         const int last = total_sweeps - 1;
-        finalize_kernel<T><<<(unsigned)((h->cap + 255) / 256), 256, 0, st>>>(
+        finalize_kernel<T><<<(unsigned)(((int64_t)tiles_cur * h->tb + 255) / 256), 256, 0, st>>>(
             (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta + (size_t)(last % 3) * h->cap,
-            prev_tested ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles * h->tb);
+            prev_tested ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles_cur * h->tb);
         CU_TRY(cudaGetLastError());
         h->last_kernel_launches++;
     } else {
@@ -604,10 +715,10 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         if (plan->ok) {
             if (plan->smem > 48 * 1024)
                 CU_TRY(cudaFuncSetAttribute(belief_tiled_kernel<T, OUT>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)plan->smem));
-            belief_tiled_kernel<T, OUT><<<tiles, h->tb, plan->smem, st>>>(
-                (const NodeMeta*)h->d_nodes.p, (const BeliefGroup*)plan->groups.p, plan->n_groups, (const T*)h->d_pl.p, h->PL,
-                h->tb, h->V, plan->stride, n, d_out, (const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
-                d_out_sweeps, d_out_conv);
+            belief_tiled_kernel<T, OUT><<<tiles_cur, h->tb, plan->smem, st>>>(
+                (const NodeMeta*)h->d_nodes.p, (const BeliefGroup*)plan->groups.p, plan->n_groups, pl_p, h->PL,
+                h->tb, h->V, plan->stride, n_cur, d_out, (const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
+                d_out_sweeps, d_out_conv, orig, 0);
         } else {
             belief_kernel<T, OUT><<<tiles, h->tb, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, h->tb,
                                                         h->V, n, d_out, (const uint8_t*)h->d_status.p,
@@ -1207,6 +1318,7 @@ void bnbp_destroy(bnbp_handle* h)
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
+                      &h->d_pl2, &h->d_msg2[0], &h->d_msg2[1], &h->d_evbits2, &h->d_orig[0], &h->d_orig[1], &h->d_src_pos, &h->d_tile_count,
                       &h->d_evst, &h->d_lw_order, &h->d_lw_par, &h->d_lw_cpt, &h->d_lw_out, &h->d_lw_wsum, &h->d_djobs, &h->d_dytab, &h->d_ddig, &h->d_cpt_t, &h->d_tscr,
                       &h->s_ev_off, &h->s_ev_node, &h->s_ev_state, &h->s_ev_val_off, &h->s_ev_values, &h->s_out[0], &h->s_out[1], &h->s_out_all,
                       &h->s_out_sweeps, &h->s_out_conv})
@@ -1305,6 +1417,7 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
     h->ev_dense_used = 0;
+    h->last_compactions = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm, ev->ev_values != nullptr, h->precision != BNBP_FP32))) return rc;
     if ((rc = ensure_state(h, ev->n_cases))) return rc;
@@ -1352,6 +1465,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->last_case_sweeps = 0;
     h->ev_sweep_used = 0;
     h->ev_dense_used = 0;
+    h->last_compactions = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm, soft, true))) return rc;
     // Chunk pipeline on three streams: evidence of chunk i+1 goes up (h2d_stream) and the marginals of
@@ -1731,6 +1845,7 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->dense_tensor_flops_per_case_sweep = h->dense_tc_flops_per_case;
     out->last_dense_tensor_launches = h->last_dense_tc_launches;
     out->last_fused = h->last_fused;
+    out->last_compactions = h->last_compactions;
     out->last_dense_ms = -1.0;
     out->last_sweep_ms = -1.0;
     out->last_total_ms = -1.0;

@@ -274,8 +274,11 @@ __global__ void __launch_bounds__(512)
 belief_tiled_kernel(const NodeMeta* __restrict__ nodes, const BeliefGroup* __restrict__ groups, int n_groups,
                     const T* __restrict__ pl_all, int PL, int TBi, int V, int stride, int64_t n_valid,
                     OUT* __restrict__ out, const uint8_t* __restrict__ status, const int32_t* __restrict__ sweeps,
-                    int32_t* __restrict__ out_sweeps, uint8_t* __restrict__ out_conv)
+                    int32_t* __restrict__ out_sweeps, uint8_t* __restrict__ out_conv,
+                    const int32_t* __restrict__ orig = nullptr, int only_frozen = 0)
 {
+    // orig != nullptr: position p of the arena holds case orig[p] of the chunk (the arena was compacted,
+    // see compact_* below); only_frozen: write the cases whose status is set and leave the others alone
     extern __shared__ __align__(16) unsigned char belief_smem[];
     const int tile = blockIdx.x, lane = threadIdx.x;
     const int warp = lane >> 5, wl = lane & 31;
@@ -303,16 +306,124 @@ belief_tiled_kernel(const NodeMeta* __restrict__ nodes, const BeliefGroup* __res
         __syncwarp();
         const int w = gr.j1 - gr.j0;
         for (int row = 0; row < rows; ++row) {
-            OUT* const dst = out + (size_t)(w0 + row) * V + gr.j0;
+            if (only_frozen && status[w0 + row] == 0) continue;          // warp-uniform
+            const int64_t dcase = orig ? (int64_t)orig[w0 + row] : w0 + row;
+            OUT* const dst = out + (size_t)dcase * V + gr.j0;
             const OUT* const src = tile_buf + (size_t)row * stride;
             for (int j = wl; j < w; j += 32) dst[j] = src[j];
         }
         __syncwarp();
     }
-    if (c < n_valid) {
-        if (out_sweeps) out_sweeps[c] = sweeps[c];
-        if (out_conv) out_conv[c] = status[c];
+    if (c < n_valid && !(only_frozen && status[c] == 0)) {
+        const int64_t dcase = orig ? (int64_t)orig[c] : c;
+        if (out_sweeps) out_sweeps[dcase] = sweeps[c];
+        if (out_conv) out_conv[dcase] = status[c];
     }
+}
+
+// ------------------------------------------------------------------------------------------------
+// Compaction of the still-active cases (eps mode).  The reference stops every case at its own sweep
+// (:147); in a batch the sweep counts spread widely (alarm37, eps 1e-6: mean 13, max 40), and a warp keeps
+// issuing the whole node walk as long as ONE of its 32 cases is active.  At a checkpoint the converged
+// cases are retired (their beliefs are written, belief_tiled_kernel with only_frozen) and the active ones
+// are gathered into dense tiles of a second arena, so the later sweeps launch a grid of the size of the
+// work that is left.  A case's arithmetic does not depend on its position: results are bit-identical.
+//
+// census:  applies the freeze rule of the next sweep launch (status / sweeps, see the FREEZE prologue of
+//          the sweep kernels) and counts the active cases per tile and in total.
+template <typename T>
+__global__ void compact_census_kernel(uint8_t* __restrict__ status, int32_t* __restrict__ sweeps, const T* __restrict__ delta_prev,
+                                      int prev_tested, T eps, int32_t sweeps_done, int32_t* __restrict__ tile_count,
+                                      int32_t* __restrict__ total)
+{
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;     // blockDim.x = cases per tile
+    bool frozen = status[c] != 0;
+    if (!frozen && prev_tested && delta_prev[c] < eps) {
+        frozen = true;
+        status[c] = 1;
+        sweeps[c] = sweeps_done;
+    }
+    const int n = __syncthreads_count(!frozen);
+    if (threadIdx.x == 0) {
+        tile_count[blockIdx.x] = n;
+        if (n) atomicAdd(total, n);
+    }
+}
+
+// exclusive scan of the tile counts (one block; a batch has at most a few thousand tiles)
+static __global__ void compact_scan_kernel(const int32_t* __restrict__ tile_count, int32_t* __restrict__ tile_off, int n_tiles)
+{
+    __shared__ int32_t part[1024];
+    __shared__ int32_t carry;
+    if (threadIdx.x == 0) carry = 0;
+    __syncthreads();
+    for (int base = 0; base < n_tiles; base += 1024) {
+        const int i = base + threadIdx.x;
+        const int32_t v = i < n_tiles ? tile_count[i] : 0;
+        part[threadIdx.x] = v;
+        __syncthreads();
+        for (int d = 1; d < 1024; d <<= 1) {                                // Hillis-Steele inclusive scan
+            const int32_t add = threadIdx.x >= d ? part[threadIdx.x - d] : 0;
+            __syncthreads();
+            part[threadIdx.x] += add;
+            __syncthreads();
+        }
+        if (i < n_tiles) tile_off[i] = carry + part[threadIdx.x] - v;
+        __syncthreads();
+        if (threadIdx.x == 1023) carry += part[1023];
+        __syncthreads();
+    }
+}
+
+// new position -> old position, in the old order (stable), and the chunk-relative case index it holds
+static __global__ void compact_index_kernel(const uint8_t* __restrict__ status, const int32_t* __restrict__ tile_off,
+                                            const int32_t* __restrict__ orig_old, int32_t* __restrict__ src_pos,
+                                            int32_t* __restrict__ orig_new)
+{
+    __shared__ int32_t warp_base[32];
+    const int64_t c = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool active = status[c] == 0;
+    const unsigned m = __ballot_sync(0xFFFFFFFFu, active);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    if (lane == 0) warp_base[warp] = __popc(m);
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        int32_t run = 0;
+        for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { const int32_t n = warp_base[w]; warp_base[w] = run; run += n; }
+    }
+    __syncthreads();
+    if (active) {
+        const int32_t p = tile_off[blockIdx.x] + warp_base[warp] + __popc(m & ((1u << lane) - 1u));
+        src_pos[p] = (int32_t)c;
+        orig_new[p] = orig_old ? orig_old[c] : (int32_t)c;
+    }
+}
+
+// gather pi/lambda, the current message buffer and the evidence masks of the active cases into dense
+// tiles; reset the per-position bookkeeping (positions >= n_active of the last tile are padding: frozen)
+template <typename T>
+__global__ void compact_gather_kernel(const int32_t* __restrict__ src_pos, int32_t n_active, int TBi, int PL, int M, int W,
+                                      const T* __restrict__ pl_src, const T* __restrict__ msg_src, const uint32_t* __restrict__ evb_src,
+                                      T* __restrict__ pl_dst, T* __restrict__ msg_dst, uint32_t* __restrict__ evb_dst,
+                                      uint8_t* __restrict__ status, T* __restrict__ delta, int64_t cap)
+{
+    const size_t TB = (size_t)TBi;
+    const int tile = blockIdx.x, lane = threadIdx.x;
+    const int64_t p = (int64_t)tile * TBi + lane;
+    for (int i = 0; i < 3; ++i) delta[(size_t)i * cap + p] = Lim<T>::floor_();
+    status[p] = p < n_active ? 0 : 1;
+    if (p >= n_active) return;
+    const int64_t q = src_pos[p];
+    const size_t st = (size_t)(q / TBi), sl = (size_t)(q % TBi);
+    const T* ps = pl_src + (st * PL) * TB + sl;
+    T* pd = pl_dst + ((size_t)tile * PL) * TB + lane;
+    for (int s = 0; s < PL; ++s) pd[(size_t)s * TB] = ps[(size_t)s * TB];
+    const T* ms = msg_src + (st * M) * TB + sl;
+    T* md = msg_dst + ((size_t)tile * M) * TB + lane;
+    for (int s = 0; s < M; ++s) md[(size_t)s * TB] = ms[(size_t)s * TB];
+    const uint32_t* es = evb_src + (st * W) * TB + sl;
+    uint32_t* ed = evb_dst + ((size_t)tile * W) * TB + lane;
+    for (int s = 0; s < W; ++s) ed[(size_t)s * TB] = es[(size_t)s * TB];
 }
 
 } // namespace bnbp

@@ -148,6 +148,7 @@ typedef struct bnbp_stats {
     int64_t last_dense_tensor_launches;
     int64_t last_fused;              /* 1 if the last run formed the time-0 state inside the first sweep and the
                                         marginals inside the last one (no separate init / belief kernels) */
+    int64_t last_compactions;        /* eps mode: how often the still-active cases were gathered into dense tiles */
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;

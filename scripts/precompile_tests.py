@@ -26,6 +26,8 @@ def jobs():
         out.append((f["net"], "fp64", 0b11111101))
     from bayesiannetwork_b200 import synth
     out.append((synth.grid(5, seed=8), "fp64", 0b11111111))
+    out.append((synth.alarm37(), "fp64", 0b00000110))           # eps-mode compaction tests
+    out.append((synth.alarm37(), "fp32", 0b00000110))
     return out
 
 

@@ -140,6 +140,57 @@ def test_fused_sequence_soft_evidence_falls_back_to_k0_k4(BP, oracle_mod):
     assert_close(res.marginals, om, what="soft", **TOL["fp64"])
 
 
+@pytest.mark.parametrize("family", ["always", "never"])
+@pytest.mark.parametrize("kw", [dict(), dict(damping=0.2), dict(check_interval=3)], ids=["plain", "damped", "interval3"])
+def test_eps_mode_compaction_of_active_cases(BP, oracle_mod, monkeypatch, family, kw):
+    """eps mode on a batch whose sweep counts spread: the converged cases are retired and the active ones
+    gathered into dense tiles at checkpoints (compact_* kernels).  A case's arithmetic does not depend on
+    its position, so marginals, sweep counts and flags are bit-identical to the run without compaction,
+    and match the oracle."""
+    net = synth.alarm37()
+    n = 20000 + 77
+    ev = synth.make_evidence(net, n, exact_k=4, seed=13)
+    bp = BP(net, "fp64", specialize=family)
+    a = bp(ev, 1e-6, max_sweeps=200, **kw)
+    st = bp.stats()
+    assert st["last_compactions"] >= 1, st
+    monkeypatch.setenv("BNBP_NO_COMPACT", "1")
+    b = bp(ev, 1e-6, max_sweeps=200, **kw)
+    assert bp.stats()["last_compactions"] == 0
+    assert np.array_equal(a.sweeps, b.sweeps) and np.array_equal(a.converged, b.converged)
+    assert np.array_equal(a.marginals, b.marginals, equal_nan=True)
+    om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=200, threads=0, **kw)
+    assert np.array_equal(a.sweeps, osw) and np.array_equal(a.converged, ocv)
+    assert_close(a.marginals, om, what="compaction " + family, **TOL["fp64"])
+    assert a.sweeps.max() > 2 * a.sweeps.min()                 # the spread that makes compaction pay
+
+
+def test_eps_mode_compaction_with_sweep_cap_and_fp32(BP, oracle_mod):
+    """Cases that hit max_sweeps without converging stay in the arena to the end; fp32 handle, device call."""
+    import torch
+    net = synth.alarm37()
+    n = 40000
+    ev = synth.make_evidence(net, n, exact_k=4, seed=14)
+    bp = BP(net, "fp64", specialize="always")
+    res = bp(ev, 1e-9, max_sweeps=14)                          # most cases do not make 1e-9 in 14 sweeps
+    om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-9, max_sweeps=14, threads=0)
+    assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv)
+    assert 0 < int(ocv.sum()) < n
+    assert_close(res.marginals, om, what="capped", **TOL["fp64"])
+    bp32 = BP(net, "fp32", specialize="always")
+    dev = torch.device("cuda", 0)
+    d_off, d_node, d_state = (torch.from_numpy(a).to(dev) for a in (ev.ev_off, ev.ev_node, ev.ev_state))
+    d_out = torch.zeros((n, net.belief_values), dtype=torch.float32, device=dev)
+    d_sw = torch.zeros(n, dtype=torch.int32, device=dev)
+    bp32.run_device(n, d_off, d_node, d_state, d_out, epsilon=1e-3, max_sweeps=100, out_sweeps=d_sw)
+    torch.cuda.synchronize()
+    assert bp32.stats()["last_compactions"] >= 1
+    ref, rsw, _ = oracle_mod.run_port(net, ev, eps=1e-3, max_sweeps=100, threads=0)
+    # fp32 sweep counts may differ by one where delta sits at the threshold; the marginals agree to fp32 accuracy
+    assert np.mean(d_sw.cpu().numpy() == rsw) > 0.99
+    assert np.abs(d_out.cpu().numpy() - ref).max() < 5e-3
+
+
 def test_specialised_equals_generic_bitwise_shape(BP):
     """Both kernel families implement the same schedule: fixed sweeps, same sweep counts, results
     within a few ulp of each other (they differ only in the order of some products)."""
