@@ -263,6 +263,20 @@ SpecLayout spec_layout(const bnbp_handle* h)
     return L;
 }
 
+// __launch_bounds__ min blocks per SM of variant v.  The freeze+check variant (2) also holds the old value
+// of every message it emits (the delta of :105-131): under the register cap of 3 (fp64) / 4 (fp32) blocks
+// per SM it spills (alarm37 fp64: 364 B of spill stores per thread, 2.4 ms per sweep instead of 1.1,
+// r01q); one block per SM less lets it keep everything in registers.
+int spec_minb_for(const bnbp_handle* h, int v)
+{
+    int mb = h->spec_minb;
+    if (v == 2 && !getenv("BNBP_SPEC_MINB")) {
+        mb = std::max(1, mb - 1);
+        if (const char* e = getenv("BNBP_SPEC_MINB_CHECK")) mb = std::min(16, std::max(1, atoi(e)));
+    }
+    return mb;
+}
+
 // Make variant v of the specialised kernel available (compile or fetch from the cache, load, upload
 // the CPT arena into its constant bank).
 int ensure_spec(bnbp_handle* h, int v)
@@ -272,7 +286,7 @@ int ensure_spec(bnbp_handle* h, int v)
     h->spec_state[v] = -1;
     SpecConfig cfg;
     cfg.fp32 = h->precision == BNBP_FP32;
-    cfg.vec = h->spec_vec; cfg.minb = h->spec_minb; cfg.variant = v; cfg.ahead = h->spec_ahead;
+    cfg.vec = h->spec_vec; cfg.minb = spec_minb_for(h, v); cfg.variant = v; cfg.ahead = h->spec_ahead;
     const std::string src = spec_source(spec_layout(h), cfg);
     std::vector<char> cubin;
     std::string err;
@@ -428,6 +442,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     int orig_set = 0;
     // Compaction pays when the sweep counts spread (alarm37, eps 1e-6: mean 13, max 40 sweeps).  Not with
     // dense nodes (their per-case tables live in a third arena) and not for small batches.
+    const bool trace_compact = getenv("BNBP_TRACE") != nullptr;
+    const auto t_chunk = std::chrono::steady_clock::now();
     const bool compact = eps_mode && h->compact_ok && h->TS == 0 && n >= 16384 && !getenv("BNBP_NO_COMPACT");
 
     SweepArgs<T> sa;
@@ -603,6 +619,10 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             CU_TRY(cudaMemcpyAsync(&h->pinned_poll[2], d_total, 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             const int64_t n_active = h->pinned_poll[2];
+            if (trace_compact)
+                fprintf(stderr, "[bnbp] census after sweep %d: %lld of %lld positions active, %.3f ms since the chunk started\n", t,
+                        (long long)n_active, (long long)n_cur,
+                        std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_chunk).count());
             if (n_active == 0) {
                 stop = true;
             } else if (n_active * 10 <= n_cur * 7 && n_cur >= 8192) {
@@ -1374,7 +1394,7 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
         if (v == 7 && h.precision != BNBP_FP32) continue;     // marginals in double from a float kernel only
         SpecConfig cfg;
         cfg.fp32 = h.precision == BNBP_FP32;
-        cfg.vec = h.spec_vec; cfg.minb = h.spec_minb; cfg.variant = v; cfg.ahead = h.spec_ahead;
+        cfg.vec = h.spec_vec; cfg.minb = spec_minb_for(&h, v); cfg.variant = v; cfg.ahead = h.spec_ahead;
         std::vector<char> cubin;
         std::string err;
         if (!spec_compile(spec_source(spec_layout(&h), cfg), &cubin, nullptr, nullptr, &err)) return fail(BNBP_ERR_CUDA, err);
@@ -1392,7 +1412,7 @@ int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int3
     if (!h.spec_eligible_) return fail(BNBP_ERR_INVALID, "network is not eligible for specialisation: " + h.spec_why);
     SpecConfig cfg;
     cfg.fp32 = h.precision == BNBP_FP32;
-    cfg.vec = h.spec_vec; cfg.minb = h.spec_minb; cfg.variant = variant; cfg.ahead = h.spec_ahead;
+    cfg.vec = h.spec_vec; cfg.minb = spec_minb_for(&h, variant); cfg.variant = variant; cfg.ahead = h.spec_ahead;
     const std::string src = spec_source(spec_layout(&h), cfg);
     if (needed) *needed = (int64_t)src.size() + 1;
     if (buf && cap > 0) {

@@ -354,7 +354,12 @@ def main():
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                 "traffic": traffic, "kernel": "bnbp_spec_sweep" if st["last_specialised"] else "sweep_kernel",
                 "peak_source": peak_src,
-                "algorithmic_bytes_per_case_sweep": 2 * S * tsize, "ms_per_launch": sweep_ms_per_launch}
+                "algorithmic_bytes_per_case_sweep": 2 * S * tsize, "ms_per_launch": sweep_ms_per_launch,
+                "launch_unit": "one sweep over the resident batch (achieved = 2*S*sizeof(T)*cases / ms_per_launch; traffic is "
+                               "per sweep too). A fixed-count run of a specialised network may put its middle sweeps into ONE "
+                               "looping launch (short grids / whole waves): ms_per_launch is then that launch's time / its sweeps",
+                "sweeps_per_step": int(st["last_sweep_launches"]), "kernel_launches_per_step": launches_per_step,
+                "fused_first_last": bool(st.get("last_fused", 0)), "compactions_per_step": int(st.get("last_compactions", 0))}
 
     dense = None
     if st["dense_nodes"] and dense_ms_per_sweep > 0 and not eps_info:
