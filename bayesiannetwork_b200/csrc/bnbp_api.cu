@@ -107,6 +107,7 @@ struct bnbp_handle {
     bool fuse_ok = true;               // cleared when a fused variant failed to build: the unfused launch sequence runs
     // eps mode: compaction of the still-active cases into a second arena (compact_* kernels, bnbp_kernels.cuh)
     DevBuf d_pl2, d_msg2[2], d_evbits2, d_orig[2], d_src_pos, d_tile_count;
+    bool split = false;                // this run: plain sweeps + delta_retire_kernel instead of the freeze/check variants
     bool compact_ok = true;            // cleared when the second arena does not fit
     int64_t last_compactions = 0;
     DevBuf d_evst;                     // [tiles][N][tb] evidence-state bytes of the resident chunk
@@ -316,6 +317,7 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
 {
     h->run_spec = false;
     h->fuse = false;
+    h->split = false;
     const bool want = h->specialize == BNBP_SPEC_ALWAYS ||
                       (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
     if (want) {
@@ -326,13 +328,17 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
         const bool plain = !eps_mode && prm.damping == 0.0;
         // fixed sweep count: the first sweep knows every message is 1 (:44-55) and the last sweep's
         // messages are never read, so neither is moved through HBM (variants 3 and 4)
-        bool need[5] = {plain && prm.max_sweeps != 2, eps_mode && interval > 1 && prm.damping == 0.0,
-                        eps_mode || prm.damping != 0.0, plain && prm.max_sweeps >= 2, plain && prm.max_sweeps >= 2};
+        // eps mode without damping on a batch worth it: the convergence test is a kernel of its own
+        // (delta_retire_kernel) and the sweeps run as the plain variant
+        const bool split = eps_mode && prm.damping == 0.0 && n_cases >= 16384 && h->TS == 0 && !getenv("BNBP_NO_SPLIT");
+        bool need[5] = {(plain && prm.max_sweeps != 2) || split, eps_mode && interval > 1 && prm.damping == 0.0 && !split,
+                        (eps_mode && !split) || prm.damping != 0.0, plain && prm.max_sweeps >= 2, plain && prm.max_sweeps >= 2};
         bool ok = true;
         for (int v = 0; v < 5 && ok; ++v)
             if (need[v] && ensure_spec(h, v) != BNBP_OK) ok = false;
         if (!ok && h->specialize == BNBP_SPEC_ALWAYS) return BNBP_ERR_CUDA;   // message already set
         h->run_spec = ok;
+        h->split = ok && split;
         // fixed sweep count, hard evidence, one case per thread: K0 runs inside the first sweep and K4
         // inside the last (variants 5 and 6/7), so neither the time-0 pi/lambda nor the final ones
         // cross HBM.  Soft evidence rows do not fit a state byte: the unfused sequence handles them.
@@ -445,6 +451,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     const bool trace_compact = getenv("BNBP_TRACE") != nullptr;
     const auto t_chunk = std::chrono::steady_clock::now();
     const bool compact = eps_mode && h->compact_ok && h->TS == 0 && n >= 16384 && !getenv("BNBP_NO_COMPACT");
+    const bool split = h->split && h->run_spec && eps_mode && prm.damping == 0.0;
+    bool have_total = false;                 // split: a delta_retire_kernel has counted the active cases
 
     SweepArgs<T> sa;
     memset(&sa, 0, sizeof sa);
@@ -492,7 +500,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
 
     int t = 0;
     bool prev_tested = false;
-    const int POLL = compact ? 4 : 8;
+    const int POLL = (compact || split) ? 4 : 8;
     int polls_issued = 0;
     bool stop = false;
     while (t < max_sweeps && !stop) {
@@ -568,7 +576,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             if (h->run_spec) {
                 // network-specialised kernel: variant 0 plain, 1 freeze, 2 freeze + check
                 int variant = check ? 2 : (eps_mode ? 1 : 0);
-                if (variant == 0 && max_sweeps >= 2) variant = t == 0 ? 3 : (t == max_sweeps - 1 ? 4 : 0);
+                if (split) variant = 0;
+                else if (variant == 0 && max_sweeps >= 2) variant = t == 0 ? 3 : (t == max_sweeps - 1 ? 4 : 0);
                 if (fuse && variant == 3) variant = 5;
                 if (fuse && variant == 4) variant = (sizeof(T) == 4 && sizeof(OUT) == 8) ? 7 : 6;
                 SpecAux<T> ax;
@@ -597,25 +606,41 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode, check, st);
                 if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
             }
+            if (split && tested) {
+                // the convergence test of this sweep (:105-131,:147), retirement of the cases it stops, census
+                int rc;
+                if ((rc = h->d_tile_count.ensure((size_t)tiles * 8))) return rc;
+                int32_t* const d_total = d_last_active + 2;
+                CU_TRY(cudaMemsetAsync(d_total, 0, 4, st));
+                delta_retire_kernel<T, OUT><<<tiles_cur, h->tb, 0, st>>>(
+                    (const NodeMeta*)h->d_nodes.p, h->N, h->PL, h->M, h->V, pl_p, sa.msg_cur, sa.msg_nxt, (uint8_t*)h->d_status.p,
+                    (T)prm.epsilon, t + 1, n_cur, orig, d_out, d_out_sweeps, d_out_conv, (int32_t*)h->d_tile_count.p, d_total);
+                CU_TRY(cudaGetLastError());
+                h->last_kernel_launches++;
+                have_total = true;
+            }
             prev_tested = tested;
             h->last_sweep_launches += n_inner;      // counted in sweeps: a looped launch stands for n_inner of them
             h->last_kernel_launches++;
             t += n_inner - 1;
         }
-        if (compact && t < max_sweeps && t >= 8) {
+        if ((split && have_total && t < max_sweeps) || (compact && !split && t < max_sweeps && t >= 8)) {
             // census: the freeze rule of the next launch, active cases per tile and in total (one host
-            // round trip per POLL sweeps; the grid that follows is sized by its answer)
+            // round trip per POLL sweeps; the grid that follows is sized by its answer).  In split mode
+            // the last delta_retire_kernel has already counted.
             int rc;
             if ((rc = h->d_tile_count.ensure((size_t)tiles * 8))) return rc;
             int32_t* const d_total = d_last_active + 2;
             int32_t* const d_tile_cnt = (int32_t*)h->d_tile_count.p;
             int32_t* const d_tile_off = d_tile_cnt + tiles;
-            CU_TRY(cudaMemsetAsync(d_total, 0, 4, st));
-            compact_census_kernel<T><<<tiles_cur, h->tb, 0, st>>>((uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p,
-                                                                  delta + (size_t)((t + 2) % 3) * h->cap, prev_tested ? 1 : 0,
-                                                                  (T)prm.epsilon, t, d_tile_cnt, d_total);
-            CU_TRY(cudaGetLastError());
-            h->last_kernel_launches++;
+            if (!split) {
+                CU_TRY(cudaMemsetAsync(d_total, 0, 4, st));
+                compact_census_kernel<T><<<tiles_cur, h->tb, 0, st>>>((uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p,
+                                                                      delta + (size_t)((t + 2) % 3) * h->cap, prev_tested ? 1 : 0,
+                                                                      (T)prm.epsilon, t, d_tile_cnt, d_total);
+                CU_TRY(cudaGetLastError());
+                h->last_kernel_launches++;
+            }
             CU_TRY(cudaMemcpyAsync(&h->pinned_poll[2], d_total, 4, cudaMemcpyDeviceToHost, st));
             CU_TRY(cudaStreamSynchronize(st));
             const int64_t n_active = h->pinned_poll[2];
@@ -625,7 +650,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                         std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_chunk).count());
             if (n_active == 0) {
                 stop = true;
-            } else if (n_active * 10 <= n_cur * 7 && n_cur >= 8192) {
+            } else if (compact && n_active * 10 <= n_cur * 7 && n_cur >= 8192) {
                 const int64_t tiles_new = (n_active + h->tb - 1) / h->tb;
                 const size_t want = (size_t)tiles_new * h->tb;
                 DevBuf* pl_b[2] = {&h->d_pl, &h->d_pl2};
@@ -649,7 +674,8 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 if (fits && (h->d_orig[0].ensure((size_t)h->cap * 4) || h->d_orig[1].ensure((size_t)h->cap * 4) ||
                              h->d_src_pos.ensure((size_t)h->cap * 4)))
                     fits = false;
-                if (fits) {
+                if (fits && split) have_total = false;           // the counts describe the old arena
+                if (fits && !split) {
                     // 1. retire the converged cases: their state is final (:135-147), write their beliefs now
                     bnbp_handle::BeliefPlan* plan = nullptr;
                     if ((rc = belief_plan(h, h->tb, (int)sizeof(OUT), &plan))) return rc;
@@ -660,6 +686,9 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                         h->tb, h->V, plan->stride, n_cur, d_out, (const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
                         d_out_sweeps, d_out_conv, orig, 1);
                     CU_TRY(cudaGetLastError());
+                    h->last_kernel_launches++;
+                }
+                if (fits) {
                     // 2. new position -> old position (stable), 3. gather into the other arena
                     compact_scan_kernel<<<1, 1024, 0, st>>>(d_tile_cnt, d_tile_off, tiles_cur);
                     int32_t* const orig_new = (int32_t*)h->d_orig[orig_set ^ 1].p;
@@ -673,7 +702,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                         (const int32_t*)h->d_src_pos.p, (int32_t)n_active, h->tb, h->PL, h->M, h->W, pl_p, msg_p[t & 1], evb_p,
                         pl_d, md[t & 1], ev_d, (uint8_t*)h->d_status.p, delta, h->cap);
                     CU_TRY(cudaGetLastError());
-                    h->last_kernel_launches += 4;
+                    h->last_kernel_launches += 3;
                     h->last_compactions++;
                     pl_p = pl_d; msg_p[0] = md[0]; msg_p[1] = md[1]; evb_p = ev_d;
                     arena_set = dst;
@@ -684,7 +713,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                     prev_tested = false;                         // the census already froze what the last test found
                 }
             }
-        } else if (eps_mode && !compact && t < max_sweeps) {
+        } else if (eps_mode && !compact && !split && t < max_sweeps) {
             // asynchronous termination poll: keep one batch of launches in flight while the flag
             // of the batch before travels back (speculative launches exit on the device at once)
             const int slot = polls_issued & 1;
@@ -708,7 +737,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
         const int last = total_sweeps - 1;
         finalize_kernel<T><<<(unsigned)(((int64_t)tiles_cur * h->tb + 255) / 256), 256, 0, st>>>(
             (uint8_t*)h->d_status.p, (int32_t*)h->d_sweeps.p, delta + (size_t)(last % 3) * h->cap,
-            prev_tested ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles_cur * h->tb);
+            (prev_tested && !split) ? 1 : 0, (T)prm.epsilon, total_sweeps, (int64_t)tiles_cur * h->tb);
         CU_TRY(cudaGetLastError());
         h->last_kernel_launches++;
     } else {
@@ -738,7 +767,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
             belief_tiled_kernel<T, OUT><<<tiles_cur, h->tb, plan->smem, st>>>(
                 (const NodeMeta*)h->d_nodes.p, (const BeliefGroup*)plan->groups.p, plan->n_groups, pl_p, h->PL,
                 h->tb, h->V, plan->stride, n_cur, d_out, (const uint8_t*)h->d_status.p, (const int32_t*)h->d_sweeps.p,
-                d_out_sweeps, d_out_conv, orig, 0);
+                d_out_sweeps, d_out_conv, orig, split ? 2 : 0);
         } else {
             belief_kernel<T, OUT><<<tiles, h->tb, 0, st>>>((const NodeMeta*)h->d_nodes.p, h->N, (const T*)h->d_pl.p, h->PL, h->tb,
                                                         h->V, n, d_out, (const uint8_t*)h->d_status.p,
@@ -760,7 +789,7 @@ int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
     int blocks = 4;
     if (h->run_spec) {
         const bool plain = !(prm.epsilon > 0.0) && prm.damping == 0.0;
-        const SpecKernel& k = h->spec[plain ? (prm.max_sweeps != 2 ? 0 : 3) : 2];
+        const SpecKernel& k = h->spec[plain ? (prm.max_sweeps != 2 ? 0 : 3) : (h->split ? 0 : 2)];
         if (k.blocks_per_sm > 0) blocks = k.blocks_per_sm;
     }
     if (const char* e = getenv("BNBP_WAVE_BLOCKS")) blocks = std::max(1, atoi(e));

@@ -21,7 +21,7 @@ def jobs():
                 continue
             out.append((net, prec, 0b00100 if eps > 0 else 0b11111001))
     fx = np.load(os.path.join(ROOT, "tests", "golden", "ref_fixtures.npz"), allow_pickle=False)
-    for name in ["pearl_tests", "pearl_nan_fixed6", "resume_tests"]:
+    for name in ["pearl_tests", "pearl_nan_fixed6", "resume_tests"]:   # (0b...1 also serves the split eps path)
         f = load_fixture(fx, name)
         out.append((f["net"], "fp64", 0b11111101))
     from bayesiannetwork_b200 import synth

@@ -159,10 +159,33 @@ def test_eps_mode_compaction_of_active_cases(BP, oracle_mod, monkeypatch, family
     assert bp.stats()["last_compactions"] == 0
     assert np.array_equal(a.sweeps, b.sweeps) and np.array_equal(a.converged, b.converged)
     assert np.array_equal(a.marginals, b.marginals, equal_nan=True)
+    # the specialised family without damping runs plain sweeps + delta_retire_kernel ("split"); the
+    # freeze/check variants of the sweep kernel (BNBP_NO_SPLIT) must give the same bits
+    monkeypatch.setenv("BNBP_NO_SPLIT", "1")
+    c = bp(ev, 1e-6, max_sweeps=200, **kw)
+    assert np.array_equal(a.sweeps, c.sweeps) and np.array_equal(a.converged, c.converged)
+    assert np.array_equal(a.marginals, c.marginals, equal_nan=True)
     om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=200, threads=0, **kw)
     assert np.array_equal(a.sweeps, osw) and np.array_equal(a.converged, ocv)
     assert_close(a.marginals, om, what="compaction " + family, **TOL["fp64"])
     assert a.sweeps.max() > 2 * a.sweeps.min()                 # the spread that makes compaction pay
+
+
+def test_split_eps_path_with_nan_cases(BP, oracle_mod, ref_fixtures):
+    """Impossible evidence (0/0 -> NaN, the reference has no guard) in a batch large enough for the split eps
+    path: the delta ignores NaN like std::max does (:113-116), so such a case stops after its first tested
+    sweep with NaN beliefs -- as the reference does (fixtures pearl_nan*)."""
+    f = load_fixture(ref_fixtures, "pearl_nan_fixed6")
+    net, ev = f["net"], f["ev"]
+    reps = 20000 // ev.n_cases + 1
+    off = np.concatenate([[0], np.cumsum(np.tile(np.diff(ev.ev_off), reps))]).astype(np.int64)
+    big = EvidenceBatch(ev.n_cases * reps, off, np.tile(ev.ev_node, reps), np.tile(ev.ev_state, reps))
+    bp = BP(net, "fp64", specialize="always")
+    res = bp(big, 1e-3, max_sweeps=50)
+    om, osw, ocv = oracle_mod.run_port(net, big, eps=1e-3, max_sweeps=50, threads=0)
+    assert np.isnan(om).any() and not np.isnan(om).all()
+    assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv)
+    assert_close(res.marginals, om, what="nan cases", **TOL["fp64"])
 
 
 def test_eps_mode_compaction_with_sweep_cap_and_fp32(BP, oracle_mod):
