@@ -406,17 +406,24 @@ def main():
         ev_pinned = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
         out_np = p_out.numpy()
         e2e_steps = max(1, min(args.steps, 10))
+        sampler2 = ClockSampler(local_rank) if rank == 0 else None       # clocks of the e2e leg (outlier calls: see below)
+        if sampler2:
+            sampler2.wait_first()
         for _ in range(2):                                               # warm-up (staging buffers, pinned pages)
             bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)
         barrier()
-        per_call = []
+        if sampler2:
+            sampler2.mark()
+        per_call, per_call_dev = [], []
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             t1 = time.perf_counter()
             bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)
             per_call.append(1e3 * (time.perf_counter() - t1))
+            per_call_dev.append(bp.stats()["last_total_ms"])             # the call has returned: no extra wait
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        clocks2 = sampler2.stop() if sampler2 else None
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -436,7 +443,9 @@ def main():
                "h2d_bytes_per_step": int(ev.nbytes()), "d2h_bytes_per_step": int(n * V * 8 + n * 5),
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "ms_per_call_min_median_max": [min(per_call), sorted(per_call)[len(per_call) // 2], max(per_call)],
-               "device_ms_last_call": bp.stats()["last_total_ms"],
+               "device_ms_per_call_min_median_max": [min(per_call_dev), sorted(per_call_dev)[len(per_call_dev) // 2], max(per_call_dev)],
+               "slowest_call": {"wall_ms": max(per_call), "device_ms": per_call_dev[per_call.index(max(per_call))]},
+               "clocks": clocks2,
                "d2h_link_gbs_measured": d2h_gbs, "d2h_floor_ms_per_step": 1e3 * n * V * 8 / (d2h_gbs * 1e9),
                "pipeline": "three streams: evidence H2D of chunk i+1 and marginal D2H of chunk i-1 overlap the kernels "
                            "of chunk i; chunks cut in whole waves of the sweep grid (BNBP_TRACE=1 prints the plan)"}

@@ -171,21 +171,21 @@ def test_eps_mode_compaction_of_active_cases(BP, oracle_mod, monkeypatch, family
     assert a.sweeps.max() > 2 * a.sweeps.min()                 # the spread that makes compaction pay
 
 
-def test_split_eps_path_with_nan_cases(BP, oracle_mod, ref_fixtures):
-    """Impossible evidence (0/0 -> NaN, the reference has no guard) in a batch large enough for the split eps
-    path: the delta ignores NaN like std::max does (:113-116), so such a case stops after its first tested
-    sweep with NaN beliefs -- as the reference does (fixtures pearl_nan*)."""
+def test_split_eps_path_on_impossible_evidence(BP, oracle_mod, ref_fixtures):
+    """The reference's Pearl graph with impossible evidence (fixture pearl_nan_fixed6: NaN beliefs after 6
+    fixed sweeps), in a batch large enough for the split eps path.  Under the reference's stopping rule these
+    cases stop after 2-3 sweeps, before the 0/0 appears; the split path must stop them at the same sweep."""
     f = load_fixture(ref_fixtures, "pearl_nan_fixed6")
     net, ev = f["net"], f["ev"]
     reps = 20000 // ev.n_cases + 1
     off = np.concatenate([[0], np.cumsum(np.tile(np.diff(ev.ev_off), reps))]).astype(np.int64)
     big = EvidenceBatch(ev.n_cases * reps, off, np.tile(ev.ev_node, reps), np.tile(ev.ev_state, reps))
     bp = BP(net, "fp64", specialize="always")
-    res = bp(big, 1e-3, max_sweeps=50)
-    om, osw, ocv = oracle_mod.run_port(net, big, eps=1e-3, max_sweeps=50, threads=0)
-    assert np.isnan(om).any() and not np.isnan(om).all()
-    assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv)
-    assert_close(res.marginals, om, what="nan cases", **TOL["fp64"])
+    for eps in (1e-3, 1e-9):
+        res = bp(big, eps, max_sweeps=50)
+        om, osw, ocv = oracle_mod.run_port(net, big, eps=eps, max_sweeps=50, threads=0)
+        assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv)
+        assert_close(res.marginals, om, what="impossible evidence, eps mode", **TOL["fp64"])
 
 
 def test_eps_mode_compaction_with_sweep_cap_and_fp32(BP, oracle_mod):
