@@ -50,6 +50,28 @@ namespace {
         }                                                                                 \
     } while (0)
 
+// Wait for a stream; BNBP_SPIN_SYNC=1 polls instead of sleeping on the driver's interrupt.  (Tried as the
+// default against the 30-120 ms host-side stalls that hit bursts of bnbp_run_batch calls on the boxes of this
+// pool at a constant 27.0 ms of device time -- r01y/r01z: neither polling nor switching Python's garbage
+// collector off removes them, so the default stays the sleeping wait, which leaves the core to others.)
+cudaError_t wait_stream(cudaStream_t s)
+{
+    static const bool blocking = getenv("BNBP_SPIN_SYNC") == nullptr;
+    if (!blocking) {
+        const auto t0 = std::chrono::steady_clock::now();
+        for (unsigned spin = 0;; ++spin) {
+            const cudaError_t e = cudaStreamQuery(s);
+            if (e != cudaErrorNotReady) return e;
+            if ((spin & 1023u) == 1023u &&
+                std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count() > 2.0) break;
+#if defined(__x86_64__)
+            __builtin_ia32_pause();
+#endif
+        }
+    }
+    return cudaStreamSynchronize(s);
+}
+
 constexpr int BLOCK_THREADS = 128;   // sweep-kernel block; a tile holds BLOCK_THREADS * vec cases
 
 struct DevBuf {
@@ -642,7 +664,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 h->last_kernel_launches++;
             }
             CU_TRY(cudaMemcpyAsync(&h->pinned_poll[2], d_total, 4, cudaMemcpyDeviceToHost, st));
-            CU_TRY(cudaStreamSynchronize(st));
+            CU_TRY(wait_stream(st));
             const int64_t n_active = h->pinned_poll[2];
             if (trace_compact)
                 fprintf(stderr, "[bnbp] census after sweep %d: %lld of %lld positions active, %.3f ms since the chunk started\n", t,
@@ -850,10 +872,12 @@ std::vector<int64_t> plan_chunks(int64_t n, int64_t wave, double rho)
 
 int check_error_flag(bnbp_handle* h, cudaStream_t st)
 {
-    int32_t flag = 0;
+    // into pinned memory: a device-to-PAGEABLE copy makes the driver itself sleep until the stream has drained
     int32_t* d_error = reinterpret_cast<int32_t*>(h->d_misc.p) + 1;
-    CU_TRY(cudaMemcpyAsync(&flag, d_error, 4, cudaMemcpyDeviceToHost, st));
-    CU_TRY(cudaStreamSynchronize(st));
+    h->pinned_poll[3] = 0;
+    CU_TRY(cudaMemcpyAsync(&h->pinned_poll[3], d_error, 4, cudaMemcpyDeviceToHost, st));
+    CU_TRY(wait_stream(st));
+    const int32_t flag = h->pinned_poll[3];
     if (flag) {
         cudaMemsetAsync(d_error, 0, 4, st);
         const char* what = flag == 1 ? "evidence node id out of range"
@@ -1677,7 +1701,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
     if ((rc = check_error_flag(h, st))) return rc;
-    CU_TRY(cudaStreamSynchronize(cs));
+    CU_TRY(wait_stream(cs));
     stamp("done", idx);
     for (size_t i = 0; i + 3 < tev.size(); i += 4) {
         float a = 0, b = 0, c = 0, d = 0;

@@ -17,6 +17,7 @@ summary each step (and all-gathers marginals with --gather).
 from __future__ import annotations
 
 import argparse
+import gc
 import json
 import os
 import subprocess
@@ -415,6 +416,11 @@ def main():
         if sampler2:
             sampler2.mark()
         per_call, per_call_dev = [], []
+        # no garbage collection inside the timed calls (benchmark hygiene as in timeit; it is NOT what makes
+        # bursts of calls take 30-120 ms of wall time at a constant 27 ms of device time on this pool's boxes,
+        # r01y/r01z -- those stalls are host-side and outside the library: see ms_per_call_min_median_max)
+        gc.collect()
+        gc.disable()
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             t1 = time.perf_counter()
@@ -423,6 +429,7 @@ def main():
             per_call_dev.append(bp.stats()["last_total_ms"])             # the call has returned: no extra wait
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
+        gc.enable()
         clocks2 = sampler2.stop() if sampler2 else None
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)

@@ -23,9 +23,14 @@ p_off, p_node, p_state = pin(ev.ev_off), pin(ev.ev_node), pin(ev.ev_state)
 p_out = torch.empty((n, net.belief_values), dtype=torch.float64, pin_memory=True)
 evp = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
 out = p_out.numpy()
+import gc
+if len(sys.argv) > 3 and sys.argv[3] == "nogc":
+    gc.collect()
+    gc.disable()
 ts = []
 for i in range(calls):
     t0 = time.perf_counter()
     bp(evp, 0.0, max_sweeps=20, out=out)
     ts.append(1e3 * (time.perf_counter() - t0))
+print("gc", "off" if not gc.isenabled() else "on", "| max %.2f median %.2f |" % (max(ts[2:]), sorted(ts[2:])[len(ts[2:]) // 2]), end=" ")
 print(prec, "ms per call:", " ".join(f"{t:.2f}" for t in ts), "| device total of the last call", bp.stats()["last_total_ms"])
