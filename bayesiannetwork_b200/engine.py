@@ -111,7 +111,8 @@ class BeliefPropagation:
     # ---- host buffers ---------------------------------------------------------------------------
     def __call__(self, evidence: Optional[EvidenceBatch] = None, epsilon: float = 0.001, *,
                  max_sweeps: int = 0, damping: float = 0.0, check_interval: int = 1,
-                 out: Optional[np.ndarray] = None) -> BPResult:
+                 out: Optional[np.ndarray] = None, out_sweeps: Optional[np.ndarray] = None,
+                 out_converged: Optional[np.ndarray] = None) -> BPResult:
         if evidence is None:
             evidence = EvidenceBatch.empty(1)   # operator()(epsilon) by-pass (:24-28)
         ev = evidence
@@ -119,8 +120,12 @@ class BeliefPropagation:
         if out is None:
             out = np.empty((n, V), dtype=np.float64)
         assert out.dtype == np.float64 and out.size == n * V and out.flags.c_contiguous
-        sweeps = np.empty(n, dtype=np.int32)
-        conv = np.empty(n, dtype=np.uint8)
+        # caller-owned result buffers (all three optional) keep a hot loop free of multi-megabyte
+        # allocations: every fresh array is an mmap + page faults + munmap on the calling thread
+        sweeps = np.empty(n, dtype=np.int32) if out_sweeps is None else out_sweeps
+        conv = np.empty(n, dtype=np.uint8) if out_converged is None else out_converged
+        assert sweeps.dtype == np.int32 and sweeps.size == n and sweeps.flags.c_contiguous
+        assert conv.dtype == np.uint8 and conv.size == n and conv.flags.c_contiguous
         evc = _capi.EvidenceC(n, _vp(ev.ev_off), _vp(ev.ev_node),
                               None if ev.is_soft else _vp(ev.ev_state),
                               _vp(ev.ev_val_off) if ev.is_soft else None,

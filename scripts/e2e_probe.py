@@ -23,6 +23,9 @@ p_off, p_node, p_state = pin(ev.ev_off), pin(ev.ev_node), pin(ev.ev_state)
 p_out = torch.empty((n, net.belief_values), dtype=torch.float64, pin_memory=True)
 evp = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
 out = p_out.numpy()
+reuse = len(sys.argv) > 4 and sys.argv[4] == "reuse"
+sw = np.empty(n, dtype=np.int32) if reuse else None
+cv = np.empty(n, dtype=np.uint8) if reuse else None
 import gc
 if len(sys.argv) > 3 and sys.argv[3] == "nogc":
     gc.collect()
@@ -30,7 +33,7 @@ if len(sys.argv) > 3 and sys.argv[3] == "nogc":
 ts = []
 for i in range(calls):
     t0 = time.perf_counter()
-    bp(evp, 0.0, max_sweeps=20, out=out)
+    bp(evp, 0.0, max_sweeps=20, out=out, out_sweeps=sw, out_converged=cv)
     ts.append(1e3 * (time.perf_counter() - t0))
-print("gc", "off" if not gc.isenabled() else "on", "| max %.2f median %.2f |" % (max(ts[2:]), sorted(ts[2:])[len(ts[2:]) // 2]), end=" ")
+print("reuse" if reuse else "alloc", "gc", "off" if not gc.isenabled() else "on", "| max %.2f median %.2f |" % (max(ts[2:]), sorted(ts[2:])[len(ts[2:]) // 2]), end=" ")
 print(prec, "ms per call:", " ".join(f"{t:.2f}" for t in ts), "| device total of the last call", bp.stats()["last_total_ms"])
