@@ -1553,6 +1553,14 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     const double rho = ((double)h->V * 8.0 / 55e9) /
                        std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / 6.0e12);
     std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave, rho);
+    if (prm->epsilon > 0.0 && plan.size() > 2 && !getenv("BNBP_CHUNKS")) {
+        // eps mode: the host waits inside every chunk (termination census), so chunks do not overlap each
+        // other's kernels, only the copy of the chunk before; two chunks (~60/40 in whole waves) keep the
+        // grids long and expose the copy of the smaller one only (4 chunks: 57.5 ms, r01fin)
+        const int64_t W = ev->n_cases / wave;
+        const int64_t first = std::max<int64_t>(1, (W * 3 + 2) / 5) * wave;
+        plan = {first, ev->n_cases - first};
+    }
     int64_t chunk = *std::max_element(plan.begin(), plan.end());
     if ((rc = ensure_state(h, chunk))) return rc;
     if (h->cap < chunk) {                                 // HBM cannot hold the planned chunk: equal resident chunks
