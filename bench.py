@@ -58,7 +58,7 @@ class ClockSampler:
         self.rows, self.proc, self.thr = [], None, None
         try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "200",
                  "-i", str(gpu_index)], stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thr = threading.Thread(target=self._pump, daemon=True)
             self.thr.start()
@@ -406,15 +406,16 @@ def main():
         p_out = torch.empty((n, V), dtype=torch.float64, pin_memory=True)
         ev_pinned = EvidenceBatch(n, p_off.numpy(), p_node.numpy(), p_state.numpy())
         out_np = p_out.numpy()
+        # caller-owned count buffers too: a fresh 4 MB + 1 MB numpy array per call is an mmap / munmap pair on
+        # the calling thread, and with gigabytes of pinned memory registered the unmap stalls the process for
+        # 30-120 ms on bursts of calls (r01chk: 40 calls with reused buffers 27.96-29.20 ms, with fresh ones up to 130 ms)
+        p_sw = torch.empty(n, dtype=torch.int32, pin_memory=True)
+        p_cv = torch.empty(n, dtype=torch.uint8, pin_memory=True)
+        sw_np, cv_np = p_sw.numpy(), p_cv.numpy()
         e2e_steps = max(1, min(args.steps, 10))
-        sampler2 = ClockSampler(local_rank) if rank == 0 else None       # clocks of the e2e leg (outlier calls: see below)
-        if sampler2:
-            sampler2.wait_first()
         for _ in range(2):                                               # warm-up (staging buffers, pinned pages)
-            bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)
+            bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np, out_sweeps=sw_np, out_converged=cv_np)
         barrier()
-        if sampler2:
-            sampler2.mark()
         per_call, per_call_dev = [], []
         # no garbage collection inside the timed calls (benchmark hygiene as in timeit; it is NOT what makes
         # bursts of calls take 30-120 ms of wall time at a constant 27 ms of device time on this pool's boxes,
@@ -424,13 +425,12 @@ def main():
         t0 = time.perf_counter()
         for _ in range(e2e_steps):
             t1 = time.perf_counter()
-            bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np)
+            bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np, out_sweeps=sw_np, out_converged=cv_np)
             per_call.append(1e3 * (time.perf_counter() - t1))
             per_call_dev.append(bp.stats()["last_total_ms"])             # the call has returned: no extra wait
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         gc.enable()
-        clocks2 = sampler2.stop() if sampler2 else None
         if world > 1:
             t = torch.tensor([dt], dtype=torch.float64, device=dev)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -452,7 +452,7 @@ def main():
                "ms_per_call_min_median_max": [min(per_call), sorted(per_call)[len(per_call) // 2], max(per_call)],
                "device_ms_per_call_min_median_max": [min(per_call_dev), sorted(per_call_dev)[len(per_call_dev) // 2], max(per_call_dev)],
                "slowest_call": {"wall_ms": max(per_call), "device_ms": per_call_dev[per_call.index(max(per_call))]},
-               "clocks": clocks2,
+               "note": "no nvidia-smi sampling during this leg: its NVML queries showed up as 100 ms outlier calls (r01chk2)",
                "d2h_link_gbs_measured": d2h_gbs, "d2h_floor_ms_per_step": 1e3 * n * V * 8 / (d2h_gbs * 1e9),
                "pipeline": "three streams: evidence H2D of chunk i+1 and marginal D2H of chunk i-1 overlap the kernels "
                            "of chunk i; chunks cut in whole waves of the sweep grid (BNBP_TRACE=1 prints the plan)"}
