@@ -370,6 +370,8 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
             else h->fuse_ok = false;
         }
     }
+    if (!h->run_spec)        // the generic family splits the convergence test off the same way (plain sweep + delta_retire_kernel)
+        h->split = prm.epsilon > 0.0 && prm.damping == 0.0 && n_cases >= 16384 && h->TS == 0 && !getenv("BNBP_NO_SPLIT");
     h->tb = BLOCK_THREADS * (h->run_spec ? h->spec_vec : h->vec);
     h->last_specialised = h->run_spec ? 1 : 0;
     return BNBP_OK;
@@ -473,7 +475,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     const bool trace_compact = getenv("BNBP_TRACE") != nullptr;
     const auto t_chunk = std::chrono::steady_clock::now();
     const bool compact = eps_mode && h->compact_ok && h->TS == 0 && n >= 16384 && !getenv("BNBP_NO_COMPACT");
-    const bool split = h->split && h->run_spec && eps_mode && prm.damping == 0.0;
+    const bool split = h->split && eps_mode && prm.damping == 0.0;
     bool have_total = false;                 // split: a delta_retire_kernel has counted the active cases
 
     SweepArgs<T> sa;
@@ -625,7 +627,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 if (!spec_launch(h->spec[variant], (unsigned)tiles_cur, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
                     return fail(BNBP_ERR_CUDA, err);
             } else {
-                cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode, check, st);
+                cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode && !split, check && !split, st);
                 if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
             }
             if (split && tested) {
