@@ -164,7 +164,12 @@ def test_eps_mode_compaction_of_active_cases(BP, oracle_mod, monkeypatch, family
     monkeypatch.setenv("BNBP_NO_SPLIT", "1")
     c = bp(ev, 1e-6, max_sweeps=200, **kw)
     assert np.array_equal(a.sweeps, c.sweeps) and np.array_equal(a.converged, c.converged)
-    assert np.array_equal(a.marginals, c.marginals, equal_nan=True)
+    if family == "always":
+        assert np.array_equal(a.marginals, c.marginals, equal_nan=True)
+    else:
+        # the generic kernel's plain and freeze/check forms are separate template instantiations: nvcc
+        # contracts a few multiply-adds differently, so they agree to rounding, not to the bit
+        assert_close(a.marginals, c.marginals, rtol=1e-12, atol=1e-15, what="generic split vs in-kernel test")
     om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=200, threads=0, **kw)
     assert np.array_equal(a.sweeps, osw) and np.array_equal(a.converged, ocv)
     assert_close(a.marginals, om, what="compaction " + family, **TOL["fp64"])
