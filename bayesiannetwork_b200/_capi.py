@@ -49,7 +49,8 @@ class StatsC(C.Structure):
                 ("dense_flops_per_case_sweep", C.c_double), ("last_dense_launches", C.c_int64),
                 ("last_dense_ms", C.c_double), ("dense_tensor_jobs", C.c_int64),
                 ("dense_tensor_flops_per_case_sweep", C.c_double), ("last_dense_tensor_launches", C.c_int64),
-                ("last_fused", C.c_int64), ("last_compactions", C.c_int64)]
+                ("last_fused", C.c_int64), ("last_compactions", C.c_int64),
+                ("last_host_ms", C.c_double), ("last_host_wait_ms", C.c_double)]
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",

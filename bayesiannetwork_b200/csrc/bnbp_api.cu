@@ -126,6 +126,7 @@ struct bnbp_handle {
     int spec_state[NSPEC] = {0, 0, 0, 0, 0, 0, 0, 0};   // 0 untried, 1 loaded, -1 failed
     bool fuse = false;                 // this run: K0 inside the first sweep, K4 inside the last (variants 5, 6/7)
     int last_fused = 0;
+    double last_host_ms = -1.0, last_host_wait_ms = -1.0;   // wall clock of the last bnbp_run_batch call / of its final waits
     bool fuse_ok = true;               // cleared when a fused variant failed to build: the unfused launch sequence runs
     // eps mode: compaction of the still-active cases into a second arena (compact_* kernels, bnbp_kernels.cuh)
     DevBuf d_pl2, d_msg2[2], d_evbits2, d_orig[2], d_src_pos, d_tile_count;
@@ -1523,6 +1524,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
                    int32_t* out_sweeps, uint8_t* out_converged)
 {
     if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_run_batch: NULL argument");
+    const auto t_entry = std::chrono::steady_clock::now();
     int rc = validate_params(prm);
     if (rc) return rc;
     if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
@@ -1710,8 +1712,10 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     CU_TRY(cudaStreamWaitEvent(st, e_last, 0));
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
+    const auto t_wait = std::chrono::steady_clock::now();
     if ((rc = check_error_flag(h, st))) return rc;
     CU_TRY(wait_stream(cs));
+    h->last_host_wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wait).count();
     stamp("done", idx);
     for (size_t i = 0; i + 3 < tev.size(); i += 4) {
         float a = 0, b = 0, c = 0, d = 0;
@@ -1733,6 +1737,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     } else {
         h->last_case_sweeps = -1;
     }
+    h->last_host_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_entry).count();
     return BNBP_OK;
 }
 
@@ -1929,6 +1934,8 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->last_dense_tensor_launches = h->last_dense_tc_launches;
     out->last_fused = h->last_fused;
     out->last_compactions = h->last_compactions;
+    out->last_host_ms = h->last_host_ms;
+    out->last_host_wait_ms = h->last_host_wait_ms;
     out->last_dense_ms = -1.0;
     out->last_sweep_ms = -1.0;
     out->last_total_ms = -1.0;

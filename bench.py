@@ -416,7 +416,7 @@ def main():
         for _ in range(2):                                               # warm-up (staging buffers, pinned pages)
             bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np, out_sweeps=sw_np, out_converged=cv_np)
         barrier()
-        per_call, per_call_dev = [], []
+        per_call, per_call_dev, per_call_lib = [], [], []
         # no garbage collection inside the timed calls (benchmark hygiene as in timeit; it is NOT what makes
         # bursts of calls take 30-120 ms of wall time at a constant 27 ms of device time on this pool's boxes,
         # r01y/r01z -- those stalls are host-side and outside the library: see ms_per_call_min_median_max)
@@ -427,7 +427,9 @@ def main():
             t1 = time.perf_counter()
             bp(ev_pinned, args.epsilon, max_sweeps=sweeps, out=out_np, out_sweeps=sw_np, out_converged=cv_np)
             per_call.append(1e3 * (time.perf_counter() - t1))
-            per_call_dev.append(bp.stats()["last_total_ms"])             # the call has returned: no extra wait
+            st_call = bp.stats()                                         # the call has returned: no extra wait
+            per_call_dev.append(st_call["last_total_ms"])
+            per_call_lib.append((st_call["last_host_ms"], st_call["last_host_wait_ms"]))
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         gc.enable()
@@ -451,7 +453,9 @@ def main():
                "steps": e2e_steps, "ms_per_step": 1e3 * dt / e2e_steps,
                "ms_per_call_min_median_max": [min(per_call), sorted(per_call)[len(per_call) // 2], max(per_call)],
                "device_ms_per_call_min_median_max": [min(per_call_dev), sorted(per_call_dev)[len(per_call_dev) // 2], max(per_call_dev)],
-               "slowest_call": {"wall_ms": max(per_call), "device_ms": per_call_dev[per_call.index(max(per_call))]},
+               "slowest_call": {"wall_ms": max(per_call), "device_ms": per_call_dev[per_call.index(max(per_call))],
+                                "inside_bnbp_run_batch_ms": per_call_lib[per_call.index(max(per_call))][0],
+                                "of_which_final_stream_waits_ms": per_call_lib[per_call.index(max(per_call))][1]},
                "note": "no nvidia-smi sampling during this leg: its NVML queries showed up as 100 ms outlier calls (r01chk2)",
                "d2h_link_gbs_measured": d2h_gbs, "d2h_floor_ms_per_step": 1e3 * n * V * 8 / (d2h_gbs * 1e9),
                "pipeline": "three streams: evidence H2D of chunk i+1 and marginal D2H of chunk i-1 overlap the kernels "

@@ -149,6 +149,8 @@ typedef struct bnbp_stats {
     int64_t last_fused;              /* 1 if the last run formed the time-0 state inside the first sweep and the
                                         marginals inside the last one (no separate init / belief kernels) */
     int64_t last_compactions;        /* eps mode: how often the still-active cases were gathered into dense tiles */
+    double  last_host_ms;            /* wall clock of the last bnbp_run_batch call, entry to return (-1: none yet)  */
+    double  last_host_wait_ms;       /* of which: the final waits for the streams                                   */
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;
