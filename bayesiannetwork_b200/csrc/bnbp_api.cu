@@ -245,6 +245,10 @@ int ensure_state(bnbp_handle* h, int64_t n_cases)
     const int64_t TBMAX = 512;          // every kernel family's tile width divides this
     int64_t want = (n_cases + TBMAX - 1) / TBMAX * TBMAX;
     const size_t per_case = (size_t)(h->PL + 2 * (size_t)h->M + (size_t)h->TS) * h->tsize + (size_t)h->W * 4 + 3 * h->tsize + 8;
+    // fast path first: cudaMemGetInfo below is an ioctl into the kernel driver, and on a shared host it
+    // waits behind whatever else queries the GPU (monitoring daemons): 20-90 ms on 1 call in ~5 (r01chk4:
+    // the slow host-buffer calls spent their extra time before the first kernel was enqueued)
+    if (want <= h->cap) return h->fuse ? h->d_evst.ensure((size_t)h->cap * h->N) : BNBP_OK;
     int64_t limit = h->max_resident;
     if (limit <= 0) {
         size_t free_b = 0, total_b = 0;
