@@ -829,9 +829,9 @@ int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
 // rho = estimated copy time / compute time of a chunk (an upper bound: the compute estimate is the HBM
 // floor of the sweeps).  Every chunk boundary costs ~20 dependent-launch drains (0.3 ms on alarm37,
 // r01l trace), so the plan is as short as the overlap allows:
-//   compute-bound (rho < 0.9): 4 chunks shrinking by ~rho, so each copy hides behind the next chunk's
+//   compute-bound (rho < 0.9): 5 chunks shrinking by ~rho, so each copy hides behind the next chunk's
 //                 kernels and the exposed tail copy is the smallest chunk;
-//   copy-bound:   a 1-wave and a 2-wave chunk start the copy engine early, the rest goes in 3 chunks.
+//   copy-bound:   a 1-wave and a 2-wave chunk start the copy engine early, the rest goes in 4 chunks.
 std::vector<int64_t> plan_chunks(int64_t n, int64_t wave, double rho)
 {
     std::vector<int64_t> plan;
@@ -840,12 +840,12 @@ std::vector<int64_t> plan_chunks(int64_t n, int64_t wave, double rho)
     std::vector<int64_t> w;
     int64_t rest = W;
     double ratio = std::min(0.8, std::max(0.5, rho));
-    int k = 4;
+    int k = 5;                                         // r01end sweep, alarm37 fp64: 4 chunks 27.6 ms, 5: 26.9, 6: 27.2, 8: 27.4
     if (rho >= 0.9) {
         if (W >= 10) { w = {1, 2}; rest -= 3; }
         else if (W >= 5) { w = {1}; rest -= 1; }
         ratio = 1.0;
-        k = 3;
+        k = 4;                                         // fp32: 3 chunks after the ramp 20.9 ms, 4: 19.4, 5: 19.5
     }
     if (const char* e = getenv("BNBP_CHUNKS")) k = std::max(1, atoi(e));
     k = (int)std::min<int64_t>(k, rest);
