@@ -19,6 +19,7 @@
 
 #include <cassert>
 #include <cstddef>
+#include <initializer_list>
 #include <iterator>
 #include <utility>
 #include <vector>
@@ -92,6 +93,46 @@ public:
     {
         matrix_type out(*this);
         out *= rhs;
+        return out;
+    }
+
+    // ---- additions used by the batched front ends (not in the reference) ------------------------------
+    // a 1 x n row from a list of values: the shape of every evidence / belief matrix on the BP path
+    static matrix_type row(std::initializer_list<double> values)
+    {
+        matrix_type m(1, values.size());
+        std::size_t i = 0;
+        for (double const v : values) m.rows_[0][i++] = v;
+        return m;
+    }
+
+    // row-major copy of all entries: what the flat C ABI (bnbp_evidence::ev_values) takes
+    std::vector<double> flat() const
+    {
+        std::vector<double> out;
+        out.reserve(rows_.size() * width_);
+        for (row_type const& r : rows_) out.insert(out.end(), r.begin(), r.end());
+        return out;
+    }
+
+    bool same_shape(matrix_type const& other) const { return height() == other.height() && width() == other.width(); }
+
+    double sum() const
+    {
+        double total = 0.0;
+        for (row_type const& r : rows_)
+            for (double const cell : r) total += cell;
+        return total;
+    }
+
+    // every entry divided by the plain sum, no zero guard: the normalisation of the BP path
+    // (belief_propagation.hpp:298-311; 0/0 stays NaN exactly as there)
+    matrix_type normalized() const
+    {
+        matrix_type out(*this);
+        double const total = sum();
+        for (row_type& r : out.rows_)
+            for (double& cell : r) cell /= total;
         return out;
     }
 

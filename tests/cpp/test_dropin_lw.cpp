@@ -95,4 +95,9 @@ BOOST_AUTO_TEST_CASE(sampler_make_cpt_counts_on_the_device)
     BOOST_CHECK((b->cpt[{{a, 0}}].second == std::vector<double>{0.75, 0.25}));
     BOOST_CHECK((b->cpt[{{a, 1}}].second == std::vector<double>{0.5, 0.5}));     // never seen: uniform (:147-151)
     std::remove(path);
+    // matrix_type helpers of the batched front ends
+    bn::matrix_type const e = bn::matrix_type::row({0.3, 0.7});
+    BOOST_CHECK(e.height() == 1 && e.width() == 2 && e.flat() == (std::vector<double>{0.3, 0.7}));
+    BOOST_CHECK(std::fabs((e % e).normalized()[0][1] - 0.49 / 0.58) < 1e-15);     // belief of a soft-evidence node
+    BOOST_CHECK(e.same_shape(e.normalized()) && std::fabs(e.sum() - 1.0) < 1e-15);
 }
