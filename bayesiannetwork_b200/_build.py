@@ -19,7 +19,7 @@ SPEC_EMBED = os.path.join(CSRC, "bnbp_spec_embed.inc")   # ... from this generat
 HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_sweep.cuh"),
            os.path.join(CSRC, "bnbp_variants.h"), os.path.join(CSRC, "bnbp_jit.h"), SPEC_SRC,
            os.path.join(CSRC, "bnbp_dense.h"), os.path.join(CSRC, "bnbp_dense.cuh"),
-           os.path.join(CSRC, "bnbp_dense_tc.cuh"),
+           os.path.join(CSRC, "bnbp_dense_tc.cuh"), os.path.join(CSRC, "bnbp_lw.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 # host-only units: rebuilt when the drop-in headers they wrap change
