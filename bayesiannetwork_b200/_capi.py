@@ -54,7 +54,7 @@ class StatsC(C.Structure):
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",
-           "bnbp_run_batch_device", "bnbp_lw_run_batch", "bnbp_estimate_cpt", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source",
+           "bnbp_run_batch_device", "bnbp_check_errors", "bnbp_lw_run_batch", "bnbp_estimate_cpt", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source",
            "bnbp_netfile_parse", "bnbp_netfile_load", "bnbp_netfile_network", "bnbp_netfile_name",
            "bnbp_netfile_node_name", "bnbp_netfile_state_name", "bnbp_netfile_free"]
 
@@ -86,6 +86,8 @@ def load():
     lib.bnbp_run_batch_device.restype = C.c_int
     lib.bnbp_run_batch_device.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.POINTER(RunParamsC),
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bnbp_check_errors.restype = C.c_int
+    lib.bnbp_check_errors.argtypes = [C.c_void_p, C.c_void_p]
     lib.bnbp_lw_run_batch.restype = C.c_int
     lib.bnbp_lw_run_batch.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.c_int64, C.c_uint64, C.c_void_p, C.c_void_p]
     lib.bnbp_estimate_cpt.restype = C.c_int

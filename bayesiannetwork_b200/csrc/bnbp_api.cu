@@ -322,7 +322,14 @@ int ensure_spec(bnbp_handle* h, int v)
     double ms = 0;
     if (!spec_compile(src, &cubin, &cached, &ms, &err)) { h->spec_why = err; return fail(BNBP_ERR_CUDA, err); }
     h->spec_compile_ms += ms;
-    if (!spec_load(cubin, &h->spec[v], &err)) { h->spec_why = err; return fail(BNBP_ERR_CUDA, err); }
+    if (!spec_load(cubin, &h->spec[v], &err)) {
+        // a cached cubin that does not load (another driver / a damaged file) is replaced once
+        if (!cached || !spec_compile(src, &cubin, &cached, &ms, &err, true) || !spec_load(cubin, &h->spec[v], &err)) {
+            h->spec_why = err;
+            return fail(BNBP_ERR_CUDA, err);
+        }
+        h->spec_compile_ms += ms;
+    }
     h->spec[v].from_cache = cached;
     h->spec[v].compile_ms = ms;
     bool ok;
@@ -1334,7 +1341,9 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     if (prop.major < 10)
         return fail(BNBP_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100: kernels are built for sm_100a only");
 
-    std::unique_ptr<bnbp_handle> h(new bnbp_handle());
+    // a failed create releases what it had allocated (device buffers, streams, events)
+    struct Destroy { void operator()(bnbp_handle* p) const { bnbp_destroy(p); } };
+    std::unique_ptr<bnbp_handle, Destroy> h(new bnbp_handle());
     h->device = dev;
     int rc = build_layout(net, opt, h.get());
     if (rc) return rc;
@@ -1501,6 +1510,8 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm, ev->ev_values != nullptr, h->precision != BNBP_FP32))) return rc;
     if ((rc = ensure_state(h, ev->n_cases))) return rc;
+    // a flag left by an earlier (unchecked, asynchronous) run must not fail this one
+    CU_TRY(cudaMemsetAsync(reinterpret_cast<int32_t*>(h->d_misc.p) + 1, 0, 4, st));
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
     bool exact = true;
     for (int64_t c0 = 0; c0 < ev->n_cases; c0 += h->cap) {
@@ -1521,7 +1532,17 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     if (!exact) h->last_case_sweeps = -1;
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
+    // epsilon mode has synchronised with the host already (termination census): report malformed evidence now.
+    // Fixed-count runs stay asynchronous; the caller asks with bnbp_check_errors once it has synchronised.
+    if (prm->epsilon > 0.0) return check_error_flag(h, st);
     return BNBP_OK;
+}
+
+int bnbp_check_errors(bnbp_handle* h, void* stream)
+{
+    if (!h) return fail(BNBP_ERR_INVALID, "bnbp_check_errors: NULL handle");
+    CU_TRY(cudaSetDevice(h->device));
+    return check_error_flag(h, stream ? (cudaStream_t)stream : h->stream);
 }
 
 int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm, double* out_marginals,
@@ -1538,6 +1559,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     const bool soft = ev->ev_values != nullptr;
     if (nnz > 0 && !soft && !ev->ev_state) return fail(BNBP_ERR_INVALID, "neither ev_state nor ev_values given");
     if (soft && !ev->ev_val_off) return fail(BNBP_ERR_INVALID, "ev_val_off is NULL");
+    if (soft && ev->ev_val_off[nnz] < ev->ev_val_off[0]) return fail(BNBP_ERR_INVALID, "ev_val_off not monotone");
     if (ev->n_cases > 0 && (ev->ev_off[0] < 0 || nnz < ev->ev_off[0])) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
     // (the per-case monotonicity check runs chunk by chunk below, while the device works on the chunk before)
     CU_TRY(cudaSetDevice(h->device));
@@ -1631,6 +1653,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         for (int64_t c : plan) fprintf(stderr, " %lld", (long long)c);
         fprintf(stderr, "\n");
     }
+    CU_TRY(cudaMemsetAsync(reinterpret_cast<int32_t*>(h->d_misc.p) + 1, 0, 4, st));
     cudaStream_t cs = h->copy_stream, hs = h->h2d_stream;
     struct Drain {                       // no path leaves this call with copies from/to host memory in flight
         cudaStream_t a, b, c;
@@ -1671,6 +1694,11 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         DevEvidence de{(const int64_t*)h->s_ev_off.p + c0, 0, (const int32_t*)h->s_ev_node.p, nullptr, nullptr, nullptr, 0};
         if (soft) {
             const int64_t va = ev->ev_val_off[a], vb = ev->ev_val_off[b];
+            {   // the offsets become memcpy ranges below: refuse anything not monotone inside [val0, end]
+                bool mono = va >= val0 && vb <= ev->ev_val_off[nnz];
+                for (int64_t e = a; e < b; ++e) mono &= ev->ev_val_off[e + 1] >= ev->ev_val_off[e];
+                if (!mono) return fail(BNBP_ERR_INVALID, "ev_val_off not monotone");
+            }
             CU_TRY(cudaMemcpyAsync((int64_t*)h->s_ev_val_off.p + a, ev->ev_val_off + a, (size_t)(b - a + 1) * 8, cudaMemcpyHostToDevice, hs));
             if (vb > va)
                 CU_TRY(cudaMemcpyAsync((double*)h->s_ev_values.p + (va - val0), ev->ev_values + va, (size_t)(vb - va) * 8, cudaMemcpyHostToDevice, hs));
@@ -1807,6 +1835,7 @@ int bnbp_lw_run_batch(bnbp_handle* h, const bnbp_evidence* ev, int64_t n_samples
     if ((rc = h->d_lw_out.ensure((size_t)std::min(CH, ev->n_cases) * h->V * 8))) return rc;
     if ((rc = h->d_lw_wsum.ensure((size_t)std::min(CH, ev->n_cases) * 8))) return rc;
     int32_t* d_error = reinterpret_cast<int32_t*>(h->d_misc.p) + 1;
+    CU_TRY(cudaMemsetAsync(d_error, 0, 4, st));
     h->last_kernel_launches = 0;
     for (int64_t c0 = 0; c0 < ev->n_cases; c0 += CH) {
         const int64_t n = std::min(CH, ev->n_cases - c0);

@@ -67,7 +67,10 @@ struct SpecKernel {                 // one loaded cubin
 };
 
 // Compile (or fetch from the cache) without touching a GPU.  Returns false and fills err on failure.
-bool spec_compile(const std::string& source, std::vector<char>* cubin, bool* from_cache, double* ms, std::string* err);
+// bypass_cache: compile even when the cache holds an entry (and overwrite it) -- the retry after a cached cubin
+// failed to load.
+bool spec_compile(const std::string& source, std::vector<char>* cubin, bool* from_cache, double* ms, std::string* err,
+                  bool bypass_cache = false);
 
 // Load a cubin into the current context and resolve the kernel + the CPT constant.
 bool spec_load(const std::vector<char>& cubin, SpecKernel* out, std::string* err);

@@ -14,6 +14,7 @@
  *   bnbp_run_batch     <- belief_propagation::operator()(precondition, epsilon)
  *                         belief_propagation.hpp:31-159, for n_cases evidence sets at once
  *   bnbp_run_batch_device  same, evidence / marginals already resident in device memory
+ *   bnbp_check_errors  (evidence validation of the asynchronous device-path call; no reference counterpart)
  *   bnbp_destroy       <- belief_propagation::~belief_propagation()   :21
  *   bnbp_last_error    <- (the reference has no error channel; UB / NaN / endless loop)
  *   bnbp_refresh_cpt   <- the reference reads vertex_t::cpt at call time (graph.hpp:157-161), so
@@ -175,6 +176,14 @@ int  bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_para
 int  bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm,
                            void* out_marginals, int32_t* out_sweeps, uint8_t* out_converged,
                            void* stream);
+
+/* The device-path call above does not wait for the device, so malformed evidence it meets there (node id or
+ * state out of range, soft row of the wrong length: such entries are skipped) cannot fail the call itself
+ * unless epsilon > 0 made it synchronise.  After synchronising `stream`, this returns BNBP_ERR_INVALID with
+ * the reason if the last device-path run skipped evidence, BNBP_OK otherwise.  Every run clears the flag
+ * when it starts, so an unchecked error never fails a later call.  (The reference has no error channel:
+ * evidence on a vertex outside the graph is silently ignored, belief_propagation.hpp:69-73.) */
+int  bnbp_check_errors(bnbp_handle* h, void* stream);
 
 /* Likelihood weighting for a batch of HARD-evidence cases: the independent statistical
  * check of BP marginals on loopy networks.  Replaces likelihood_weighting::operator()(evidence_list,

@@ -39,3 +39,12 @@ def test_no_device_is_an_error_not_a_fallback():
     else:
         raise AssertionError("bnbp_create succeeded without a device")
     assert np.isfinite(1.0)
+
+
+def test_cmake_target_compiles_every_unit_of_the_in_tree_build():
+    """CMakeLists.txt builds the same translation units as bayesiannetwork_b200/_build.py, so a CMake-built
+    libbnbp.so exports the same symbols (round-1 finding: bnbp_netfile.cpp was missing from the CMake target)."""
+    from bayesiannetwork_b200 import _build
+    cm = open(os.path.join(ROOT, "CMakeLists.txt")).read()
+    for src, _, _ in _build._units():
+        assert "${CSRC}/" + os.path.basename(src) in cm, os.path.basename(src)
