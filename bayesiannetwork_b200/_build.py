@@ -16,8 +16,10 @@ OBJDIR = os.path.join(LIBDIR, "obj")
 LIB = os.path.join(LIBDIR, "libbnbp.so")
 SPEC_SRC = os.path.join(CSRC, "bnbp_spec.cuh")           # compiled at run time by NVRTC ...
 SPEC_EMBED = os.path.join(CSRC, "bnbp_spec_embed.inc")   # ... from this generated raw-string copy
+ONCHIP_SRC = os.path.join(CSRC, "bnbp_onchip.cuh")       # the on-chip multi-sweep kernel, appended behind it
+ONCHIP_EMBED = os.path.join(CSRC, "bnbp_onchip_embed.inc")
 HEADERS = [os.path.join(CSRC, "bnbp_kernels.cuh"), os.path.join(CSRC, "bnbp_sweep.cuh"),
-           os.path.join(CSRC, "bnbp_variants.h"), os.path.join(CSRC, "bnbp_jit.h"), SPEC_SRC,
+           os.path.join(CSRC, "bnbp_variants.h"), os.path.join(CSRC, "bnbp_jit.h"), SPEC_SRC, ONCHIP_SRC,
            os.path.join(CSRC, "bnbp_dense.h"), os.path.join(CSRC, "bnbp_dense.cuh"),
            os.path.join(CSRC, "bnbp_dense_tc.cuh"), os.path.join(CSRC, "bnbp_lw.cuh"),
            os.path.join(os.path.dirname(HERE), "include", "bnbp.h")]
@@ -31,13 +33,14 @@ HOST_HEADERS = {"bnbp_netfile.cpp": [os.path.join(INCLUDE, "bayesian", "graph.hp
 
 
 def embed_spec_header() -> None:
-    """bnbp_spec.cuh -> bnbp_spec_embed.inc (a C++ raw string literal #included by bnbp_jit.cu)."""
-    text = open(SPEC_SRC).read()
-    assert ')BNBPSPEC"' not in text
-    out = 'R"BNBPSPEC(' + text + ')BNBPSPEC"\n'
-    if not os.path.exists(SPEC_EMBED) or open(SPEC_EMBED).read() != out:
-        with open(SPEC_EMBED, "w") as f:
-            f.write(out)
+    """bnbp_spec.cuh / bnbp_onchip.cuh -> *_embed.inc (C++ raw string literals #included by bnbp_jit.cu)."""
+    for src, dst in ((SPEC_SRC, SPEC_EMBED), (ONCHIP_SRC, ONCHIP_EMBED)):
+        text = open(src).read()
+        assert ')BNBPSPEC"' not in text
+        out = 'R"BNBPSPEC(' + text + ')BNBPSPEC"\n'
+        if not os.path.exists(dst) or open(dst).read() != out:
+            with open(dst, "w") as f:
+                f.write(out)
 
 
 def sweep_variants():

@@ -25,7 +25,7 @@ class FlatNetworkC(C.Structure):
 class OptionsC(C.Structure):
     _fields_ = [("precision", C.c_int32), ("device", C.c_int32), ("max_resident_cases", C.c_int64),
                 ("specialize", C.c_int32), ("dense_min_cpt", C.c_int32), ("dense_tensor", C.c_int32),
-                ("reserved", C.c_int32 * 5)]
+                ("onchip", C.c_int32), ("reserved", C.c_int32 * 4)]
 
 
 class EvidenceC(C.Structure):
@@ -50,7 +50,9 @@ class StatsC(C.Structure):
                 ("last_dense_ms", C.c_double), ("dense_tensor_jobs", C.c_int64),
                 ("dense_tensor_flops_per_case_sweep", C.c_double), ("last_dense_tensor_launches", C.c_int64),
                 ("last_fused", C.c_int64), ("last_compactions", C.c_int64),
-                ("last_host_ms", C.c_double), ("last_host_wait_ms", C.c_double)]
+                ("last_host_ms", C.c_double), ("last_host_wait_ms", C.c_double),
+                ("last_onchip", C.c_int64), ("onchip_roles", C.c_int64), ("onchip_smem_bytes", C.c_int64),
+                ("onchip_blocks_per_sm", C.c_int64), ("onchip_role_imbalance", C.c_double)]
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",

@@ -136,6 +136,17 @@ struct bnbp_handle {
     DevBuf d_evst;                     // [tiles][N][tb] evidence-state bytes of the resident chunk
     bool run_spec = false;             // kernel family of the current run
     int last_specialised = 0;
+    // on-chip multi-sweep kernel (bnbp_onchip.cuh): index = (check ? 2 : 0) + (marginals in double from a float kernel ? 1 : 0)
+    int onchip = 0;                    // bnbp_options.onchip: 0 auto, 1 always, -1 never
+    bool oc_eligible = false;
+    std::string oc_why;
+    int oc_roles = 4, oc_minb = 1, oc_ahead = 1;
+    size_t oc_smem = 0;
+    SpecKernel oc[4];
+    int oc_state[4] = {0, 0, 0, 0};    // 0 untried, 1 loaded, -1 failed
+    bool run_onchip = false;           // this run: the whole case (init, every sweep, beliefs) in one on-chip kernel
+    int last_onchip = 0;
+    double oc_imbalance = 1.0;         // busiest role / mean role cost of the node partition
     double spec_compile_ms = 0.0;
     // dense contraction path (bnbp_dense.h): nodes whose CPT has >= dense_min entries
     int64_t dense_min = 256;           // < 0: never
@@ -344,6 +355,51 @@ int ensure_spec(bnbp_handle* h, int v)
     return BNBP_OK;
 }
 
+// Same for the on-chip kernel (variants 8 / 9 of the generated source, entry bnbp_onchip_run).
+int ensure_onchip(bnbp_handle* h, int idx)
+{
+    if (h->oc_state[idx] == 1) return BNBP_OK;
+    if (h->oc_state[idx] < 0) return fail(BNBP_ERR_INVALID, "on-chip kernel unavailable: " + h->oc_why);
+    h->oc_state[idx] = -1;
+    SpecConfig cfg;
+    cfg.fp32 = h->precision == BNBP_FP32;
+    cfg.vec = 1; cfg.minb = h->oc_minb; cfg.variant = 8 + (idx >> 1); cfg.ahead = h->oc_ahead;
+    cfg.roles = h->oc_roles; cfg.out_double = (idx & 1) != 0;
+    const std::string src = spec_source(spec_layout(h), cfg);
+    std::vector<char> cubin;
+    std::string err;
+    bool cached = false;
+    double ms = 0;
+    if (!spec_compile(src, &cubin, &cached, &ms, &err)) { h->oc_why = err; return fail(BNBP_ERR_CUDA, err); }
+    h->spec_compile_ms += ms;
+    const int threads = 32 * h->oc_roles;
+    if (!spec_load(cubin, &h->oc[idx], &err, "bnbp_onchip_run", threads, h->oc_smem)) {
+        if (!cached || !spec_compile(src, &cubin, &cached, &ms, &err, true) ||
+            !spec_load(cubin, &h->oc[idx], &err, "bnbp_onchip_run", threads, h->oc_smem)) {
+            h->oc_why = err;
+            return fail(BNBP_ERR_CUDA, err);
+        }
+        h->spec_compile_ms += ms;
+    }
+    h->oc[idx].from_cache = cached;
+    h->oc[idx].compile_ms = ms;
+    bool ok;
+    if (cfg.fp32) {
+        std::vector<float> tmp(h->cpt_host.begin(), h->cpt_host.end());
+        ok = spec_upload_cpt(h->oc[idx], tmp.data(), tmp.size() * 4, &err);
+    } else {
+        ok = spec_upload_cpt(h->oc[idx], h->cpt_host.data(), h->cpt_host.size() * 8, &err);
+    }
+    if (!ok) { spec_unload(&h->oc[idx]); h->oc_why = err; return fail(BNBP_ERR_CUDA, err); }
+    if (h->oc[idx].blocks_per_sm < 1) {
+        spec_unload(&h->oc[idx]);
+        h->oc_why = "the on-chip kernel does not fit an SM (registers / shared memory)";
+        return fail(BNBP_ERR_CUDA, h->oc_why);
+    }
+    h->oc_state[idx] = 1;
+    return BNBP_OK;
+}
+
 // Kernel family of one run.  Decided before the state is initialised because the tile width
 // (cases per thread) belongs to the family.  ALWAYS: failure is an error; AUTO: the generic GPU
 // kernel takes over (still CUDA: there is no CPU path).
@@ -352,6 +408,29 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
     h->run_spec = false;
     h->fuse = false;
     h->split = false;
+    h->run_onchip = false;
+    h->last_onchip = 0;
+    {
+        // the on-chip kernel: the whole case in one launch, state in shared memory (hard evidence; soft rows
+        // take the streaming kernels).  AUTO: eligible networks, batches worth a persistent grid.
+        int mode = h->onchip;
+        if (const char* e = getenv("BNBP_ONCHIP")) mode = atoi(e) > 0 ? 1 : (atoi(e) < 0 || !strcmp(e, "0") ? -1 : 0);
+        const bool want_oc = mode > 0 || (mode == 0 && h->specialize == BNBP_SPEC_AUTO && h->oc_eligible && !soft_evidence && n_cases >= 4096);
+        if (want_oc) {
+            if (!h->oc_eligible) return fail(BNBP_ERR_INVALID, "onchip=ALWAYS but the network is not eligible: " + h->oc_why);
+            if (soft_evidence) return fail(BNBP_ERR_INVALID, "onchip=ALWAYS: soft evidence rows take the streaming kernels");
+            const int idx = ((prm.epsilon > 0.0 || prm.damping != 0.0) ? 2 : 0) + ((h->precision == BNBP_FP32 && out_double) ? 1 : 0);
+            const int rc = ensure_onchip(h, idx);
+            if (rc == BNBP_OK) {
+                h->run_onchip = true;
+                h->last_onchip = 1;
+                h->last_specialised = 1;
+                h->tb = 32;
+                return BNBP_OK;
+            }
+            if (mode > 0) return rc;
+        }
+    }
     const bool want = h->specialize == BNBP_SPEC_ALWAYS ||
                       (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
     if (want) {
@@ -816,6 +895,54 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     return BNBP_OK;
 }
 
+// The whole path for n cases in ONE launch of the on-chip kernel (bnbp_onchip.cuh): init, every sweep, the
+// stopping rule and the beliefs; nothing but evidence in and marginals out touches HBM.
+template <typename T, typename OUT>
+int run_onchip(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_params& prm, OUT* d_out,
+               int32_t* d_out_sweeps, uint8_t* d_out_conv, cudaStream_t st, int64_t* planned_sweeps)
+{
+    const bool eps_mode = prm.epsilon > 0.0;
+    if (!eps_mode && prm.max_sweeps <= 0)
+        return fail(BNBP_ERR_INVALID, "epsilon <= 0 needs a positive max_sweeps (the loop would never end)");
+    if (de.ev_values) return fail(BNBP_ERR_INVALID, "the on-chip kernel takes hard evidence");
+    const int idx = ((eps_mode || prm.damping != 0.0) ? 2 : 0) + (sizeof(OUT) != sizeof(T) ? 1 : 0);
+    const SpecKernel& k = h->oc[idx];
+    if (h->oc_state[idx] != 1) return fail(BNBP_ERR_INVALID, "on-chip kernel not loaded");
+    int32_t* const misc = reinterpret_cast<int32_t*>(h->d_misc.p);
+    unsigned long long* const ticket = reinterpret_cast<unsigned long long*>(misc + 8);
+    CU_TRY(cudaMemsetAsync(ticket, 0, 8, st));
+    OnchipArgs<T> a;
+    a.ev_off = reinterpret_cast<const long long*>(de.ev_off); a.ev_base = de.ev_base;
+    a.ev_node = de.ev_node; a.ev_state = de.ev_state;
+    a.n_cases = n;
+    a.out = d_out; a.out_sweeps = d_out_sweeps; a.out_conv = d_out_conv;
+    a.ticket = ticket; a.error_flag = misc + 1;
+    a.eps = (T)prm.epsilon; a.damping = (T)prm.damping;
+    a.max_sweeps = prm.max_sweeps > 0 ? prm.max_sweeps : (1 << 30);
+    a.interval = prm.check_interval > 0 ? prm.check_interval : 1;
+    int sms = 148;
+    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    const int64_t groups = (n + 31) / 32;
+    const unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)sms * std::max(1, k.blocks_per_sm));
+    if ((int)h->ev_sweep.size() < 2 * (h->ev_sweep_used + 1)) {
+        cudaEvent_t e0, e1;
+        CU_TRY(cudaEventCreate(&e0));
+        CU_TRY(cudaEventCreate(&e1));
+        h->ev_sweep.push_back(e0);
+        h->ev_sweep.push_back(e1);
+    }
+    CU_TRY(cudaEventRecord(h->ev_sweep[2 * h->ev_sweep_used], st));
+    std::string err;
+    if (!onchip_launch(k, blocks, (unsigned)(32 * h->oc_roles), h->oc_smem, st, &a, &err)) return fail(BNBP_ERR_CUDA, err);
+    CU_TRY(cudaEventRecord(h->ev_sweep[2 * h->ev_sweep_used + 1], st));
+    h->ev_sweep_used++;
+    h->last_kernel_launches++;
+    h->last_sweep_launches += eps_mode ? 1 : a.max_sweeps;      // counted in sweeps: the launch runs them all
+    h->last_fused = 1;
+    if (planned_sweeps) *planned_sweeps = eps_mode ? -1 : (int64_t)a.max_sweeps * n;
+    return BNBP_OK;
+}
+
 // Cases one full wave of the sweep grid holds (blocks resident on the 148 SMs x cases per tile).
 // The specialised kernels report their occupancy; the generic family is taken at 4 blocks per SM.
 int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
@@ -823,6 +950,12 @@ int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int blocks = 4;
+    if (h->run_onchip) {
+        // persistent grid: one "wave" = 8 rounds of 32 cases on every resident CTA
+        int nb = 1;
+        for (int i = 0; i < 4; ++i) if (h->oc_state[i] == 1) nb = std::max(nb, h->oc[i].blocks_per_sm);
+        return (int64_t)sms * nb * 32 * 8;
+    }
     if (h->run_spec) {
         const bool plain = !(prm.epsilon > 0.0) && prm.damping == 0.0;
         const SpecKernel& k = h->spec[plain ? (prm.max_sweeps != 2 ? 0 : 3) : (h->split ? 0 : 2)];
@@ -1136,6 +1269,8 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     }
     h->dense_min = (opt && opt->dense_min_cpt != 0) ? opt->dense_min_cpt : 256;
     h->dense_tc = opt ? opt->dense_tensor : 0;
+    h->onchip = opt ? opt->onchip : 0;
+    if (h->onchip < -1 || h->onchip > 1) return fail(BNBP_ERR_INVALID, "bnbp_options.onchip out of range");
     if (const char* ev = getenv("BNBP_DENSE_TC")) h->dense_tc = atoi(ev);      // tuning / test knob: -1 never, 1 every product
     if (const char* ev = getenv("BNBP_DENSE_MMA")) h->dense_mma = atoi(ev) != 0;   // tuning knob: 0 = DFMA products
     if (const char* ev = getenv("BNBP_DENSE_MIN")) h->dense_min = atoll(ev);   // tuning / test knob (< 0: never)
@@ -1305,6 +1440,20 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         }
         if (const char* ev = getenv("BNBP_SPEC_MINB")) h->spec_minb = std::min(16, std::max(1, atoi(ev)));
         if (const char* ev = getenv("BNBP_SPEC_AHEAD")) h->spec_ahead = std::min(4, std::max(0, atoi(ev)));
+        // ---- on-chip kernel: the state of a 32-case group (pi/lambda + both message buffers) must fit the
+        //      shared memory of one CTA
+        constexpr size_t SMEM_OPTIN = 227 * 1024;
+        h->oc_roles = 4;
+        if (const char* ev = getenv("BNBP_OC_ROLES")) h->oc_roles = std::min(16, std::max(1, atoi(ev)));
+        h->oc_ahead = 1;
+        if (const char* ev = getenv("BNBP_OC_AHEAD")) h->oc_ahead = std::min(4, std::max(0, atoi(ev)));
+        h->oc_smem = onchip_smem_bytes(L, h->precision == BNBP_FP32, h->oc_roles);
+        h->oc_eligible = h->spec_eligible_ && h->oc_smem <= SMEM_OPTIN;
+        if (!h->spec_eligible_) h->oc_why = h->spec_why;
+        else if (!h->oc_eligible) h->oc_why = "the state of 32 cases (" + std::to_string(h->oc_smem) + " B) exceeds the shared memory of an SM";
+        h->oc_minb = (int)std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (h->oc_smem + 1024)));
+        if (const char* ev = getenv("BNBP_OC_MINB")) h->oc_minb = std::min(16, std::max(1, atoi(ev)));
+        spec_partition(L, h->oc_roles, &h->oc_imbalance);
     }
     return BNBP_OK;
 }
@@ -1417,6 +1566,7 @@ void bnbp_destroy(bnbp_handle* h)
     if (h->copy_stream) { cudaStreamSynchronize(h->copy_stream); cudaStreamDestroy(h->copy_stream); }
     if (h->h2d_stream) { cudaStreamSynchronize(h->h2d_stream); cudaStreamDestroy(h->h2d_stream); }
     for (int v = 0; v < bnbp_handle::NSPEC; ++v) spec_unload(&h->spec[v]);
+    for (int v = 0; v < 4; ++v) spec_unload(&h->oc[v]);
     for (cudaEvent_t e : h->ev_sweep) cudaEventDestroy(e);
     for (cudaEvent_t e : h->ev_dense) cudaEventDestroy(e);
     for (int i = 0; i < 2; ++i) {
@@ -1449,6 +1599,18 @@ int bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values)
         }
         if (!ok) return fail(BNBP_ERR_CUDA, err);
     }
+    for (int v = 0; v < 4; ++v) {
+        if (h->oc_state[v] != 1) continue;
+        std::string err;
+        bool ok;
+        if (h->precision == BNBP_FP32) {
+            std::vector<float> tmp(h->cpt_host.begin(), h->cpt_host.end());
+            ok = spec_upload_cpt(h->oc[v], tmp.data(), tmp.size() * 4, &err);
+        } else {
+            ok = spec_upload_cpt(h->oc[v], h->cpt_host.data(), h->cpt_host.size() * 8, &err);
+        }
+        if (!ok) return fail(BNBP_ERR_CUDA, err);
+    }
     return h->precision == BNBP_FP32 ? upload_cpt<float>(h, cpt, n_values) : upload_cpt<double>(h, cpt, n_values);
 }
 
@@ -1458,6 +1620,18 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
     int rc = build_layout(net, opt, &h);
     if (rc) return rc;
     if (!h.spec_eligible_) return fail(BNBP_ERR_INVALID, "network is not eligible for specialisation: " + h.spec_why);
+    for (int idx = 0; idx < 4; ++idx) {                           // bits 8..11: the on-chip kernels
+        if (!(variant_mask & (1 << (8 + idx)))) continue;
+        if ((idx & 1) && h.precision != BNBP_FP32) continue;
+        if (!h.oc_eligible) return fail(BNBP_ERR_INVALID, "network is not eligible for the on-chip kernel: " + h.oc_why);
+        SpecConfig cfg;
+        cfg.fp32 = h.precision == BNBP_FP32;
+        cfg.vec = 1; cfg.minb = h.oc_minb; cfg.variant = 8 + (idx >> 1); cfg.ahead = h.oc_ahead;
+        cfg.roles = h.oc_roles; cfg.out_double = (idx & 1) != 0;
+        std::vector<char> cubin;
+        std::string err;
+        if (!spec_compile(spec_source(spec_layout(&h), cfg), &cubin, nullptr, nullptr, &err)) return fail(BNBP_ERR_CUDA, err);
+    }
     for (int v = 0; v < bnbp_handle::NSPEC; ++v) {
         if (!(variant_mask & (1 << v))) continue;
         if (v == 7 && h.precision != BNBP_FP32) continue;     // marginals in double from a float kernel only
@@ -1474,7 +1648,7 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
 int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant, char* buf, int64_t cap,
                      int64_t* needed)
 {
-    if (variant < 0 || variant >= bnbp_handle::NSPEC) return fail(BNBP_ERR_INVALID, "variant must be 0..7");
+    if (variant < 0 || variant > 9) return fail(BNBP_ERR_INVALID, "variant must be 0..9");
     bnbp_handle h;
     int rc = build_layout(net, opt, &h);
     if (rc) return rc;
@@ -1482,6 +1656,10 @@ int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int3
     SpecConfig cfg;
     cfg.fp32 = h.precision == BNBP_FP32;
     cfg.vec = h.spec_vec; cfg.minb = spec_minb_for(&h, variant); cfg.variant = variant; cfg.ahead = h.spec_ahead;
+    if (variant >= 8) {
+        if (!h.oc_eligible) return fail(BNBP_ERR_INVALID, "network is not eligible for the on-chip kernel: " + h.oc_why);
+        cfg.vec = 1; cfg.minb = h.oc_minb; cfg.ahead = h.oc_ahead; cfg.roles = h.oc_roles;
+    }
     const std::string src = spec_source(spec_layout(&h), cfg);
     if (needed) *needed = (int64_t)src.size() + 1;
     if (buf && cap > 0) {
@@ -1509,16 +1687,23 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     h->last_compactions = 0;
     if (ev->n_cases == 0) return BNBP_OK;
     if ((rc = choose_kernels(h, ev->n_cases, *prm, ev->ev_values != nullptr, h->precision != BNBP_FP32))) return rc;
-    if ((rc = ensure_state(h, ev->n_cases))) return rc;
+    if (!h->run_onchip && (rc = ensure_state(h, ev->n_cases))) return rc;
     // a flag left by an earlier (unchecked, asynchronous) run must not fail this one
     CU_TRY(cudaMemsetAsync(reinterpret_cast<int32_t*>(h->d_misc.p) + 1, 0, 4, st));
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
     bool exact = true;
-    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += h->cap) {
-        const int64_t n = std::min<int64_t>(h->cap, ev->n_cases - c0);
+    const int64_t step_cases = h->run_onchip ? ev->n_cases : h->cap;      // on chip: no resident state arena, one launch
+    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += step_cases) {
+        const int64_t n = std::min<int64_t>(step_cases, ev->n_cases - c0);
         DevEvidence de{ev->ev_off + c0, 0, ev->ev_node, ev->ev_state, ev->ev_val_off, ev->ev_values, 0};
         int64_t planned = 0;
-        if (h->precision == BNBP_FP32)
+        if (h->run_onchip)
+            rc = h->precision == BNBP_FP32
+                     ? run_onchip<float, float>(h, n, de, *prm, (float*)out_marginals + (size_t)c0 * h->V,
+                                                out_sweeps ? out_sweeps + c0 : nullptr, out_converged ? out_converged + c0 : nullptr, st, &planned)
+                     : run_onchip<double, double>(h, n, de, *prm, (double*)out_marginals + (size_t)c0 * h->V,
+                                                  out_sweeps ? out_sweeps + c0 : nullptr, out_converged ? out_converged + c0 : nullptr, st, &planned);
+        else if (h->precision == BNBP_FP32)
             rc = run_chunk<float, float>(h, n, de, *prm, (float*)out_marginals + (size_t)c0 * h->V,
                                          out_sweeps ? out_sweeps + c0 : nullptr,
                                          out_converged ? out_converged + c0 : nullptr, st, &planned);
@@ -1580,10 +1765,11 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     const int64_t wave = wave_cases(h, *prm);
     // copy over a ~55 GB/s host link vs the sweeps at the HBM floor (2*S*sizeof(T) bytes per case-sweep)
     const double sweeps_est = prm->epsilon > 0.0 ? (double)std::min(prm->max_sweeps > 0 ? prm->max_sweeps : 20, 20) : (double)prm->max_sweeps;
-    const double rho = ((double)h->V * 8.0 / 55e9) /
-                       std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / 6.0e12);
+    double rho = ((double)h->V * 8.0 / 55e9) /
+                 std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / 6.0e12);
+    if (h->run_onchip) rho = 2.0;                          // the kernel moves ~1 KB per case: the call is bound by the copy
     std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave, rho);
-    if (prm->epsilon > 0.0 && plan.size() > 2 && !getenv("BNBP_CHUNKS")) {
+    if (prm->epsilon > 0.0 && plan.size() > 2 && !getenv("BNBP_CHUNKS") && !h->run_onchip) {
         // eps mode: the host waits inside every chunk (termination census), so chunks do not overlap each
         // other's kernels, only the copy of the chunk before; two chunks (~60/40 in whole waves) keep the
         // grids long and expose the copy of the smaller one only (4 chunks: 57.5 ms, r01fin)
@@ -1592,8 +1778,8 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         plan = {first, ev->n_cases - first};
     }
     int64_t chunk = *std::max_element(plan.begin(), plan.end());
-    if ((rc = ensure_state(h, chunk))) return rc;
-    if (h->cap < chunk) {                                 // HBM cannot hold the planned chunk: equal resident chunks
+    if (!h->run_onchip && (rc = ensure_state(h, chunk))) return rc;
+    if (!h->run_onchip && h->cap < chunk) {               // HBM cannot hold the planned chunk: equal resident chunks
         chunk = h->cap;
         plan.assign((size_t)((ev->n_cases + chunk - 1) / chunk), chunk);
     }
@@ -1715,7 +1901,11 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         if (!whole && idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_chunk[3 * (idx - 2) + 2], 0));   // ring slot is free again
         stamp("enqueue chunk", idx);
         mark(st);
-        if (h->precision == BNBP_FP32)
+        if (h->run_onchip)
+            rc = h->precision == BNBP_FP32
+                     ? run_onchip<float, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr)
+                     : run_onchip<double, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
+        else if (h->precision == BNBP_FP32)
             rc = run_chunk<float, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0,
                                           (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         else
@@ -1967,6 +2157,15 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->last_dense_tensor_launches = h->last_dense_tc_launches;
     out->last_fused = h->last_fused;
     out->last_compactions = h->last_compactions;
+    out->last_onchip = h->last_onchip;
+    out->onchip_roles = h->oc_eligible ? h->oc_roles : 0;
+    out->onchip_smem_bytes = h->oc_eligible ? (int64_t)h->oc_smem : 0;
+    out->onchip_role_imbalance = h->oc_imbalance;
+    {
+        int nb = 0;
+        for (int i = 0; i < 4; ++i) if (h->oc_state[i] == 1) nb = std::max(nb, h->oc[i].blocks_per_sm);
+        out->onchip_blocks_per_sm = nb;
+    }
     out->last_host_ms = h->last_host_ms;
     out->last_host_wait_ms = h->last_host_wait_ms;
     out->last_dense_ms = -1.0;

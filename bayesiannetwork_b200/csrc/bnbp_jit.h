@@ -31,7 +31,18 @@ struct SpecConfig {
     int minb = 1;       // __launch_bounds__ min blocks per SM
     int variant = 0;    // 0 plain, 1 freeze, 2 freeze + check, 3 first, 4 last, 5 first + K0, 6/7 last + K4 (bnbp_spec.cuh)
     int ahead = 1;      // software-pipeline depth of the input loads
+    // on-chip variants (8 plain, 9 check: bnbp_onchip.cuh)
+    int roles = 4;              // warps that share the node walk of a 32-case group
+    bool out_double = false;    // marginals in double from a float kernel (the host-buffer call)
 };
+
+// cost of one node in one sweep as the role partition of the on-chip kernel sees it (multiply-adds + the
+// normalisations it emits), and the longest-processing-time partition itself: owner[x] = role of node x
+double spec_node_cost(const SpecLayout& L, int x);
+std::vector<int> spec_partition(const SpecLayout& L, int roles, double* imbalance = nullptr);
+
+// bytes of dynamic shared memory the on-chip kernel needs for one 32-case group
+size_t onchip_smem_bytes(const SpecLayout& L, bool fp32, int roles);
 
 // Can (and should) this network be specialised?  why != nullptr receives the reason when not.
 bool spec_eligible(const SpecLayout& L, bool fp32, std::string* why);
@@ -72,14 +83,38 @@ struct SpecKernel {                 // one loaded cubin
 bool spec_compile(const std::string& source, std::vector<char>* cubin, bool* from_cache, double* ms, std::string* err,
                   bool bypass_cache = false);
 
-// Load a cubin into the current context and resolve the kernel + the CPT constant.
-bool spec_load(const std::vector<char>& cubin, SpecKernel* out, std::string* err);
+// Load a cubin into the current context and resolve the kernel + the CPT constant.  threads / smem: the launch
+// shape the occupancy is asked for (the on-chip kernel opts in to its dynamic shared memory here).
+bool spec_load(const std::vector<char>& cubin, SpecKernel* out, std::string* err, const char* entry = "bnbp_spec_sweep",
+               int threads = 128, size_t smem = 0);
 void spec_unload(SpecKernel* k);
 bool spec_upload_cpt(const SpecKernel& k, const void* host, size_t bytes, std::string* err);
 
 // <<<tiles, 128, 0, st>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux)
 bool spec_launch(const SpecKernel& k, unsigned tiles, cudaStream_t st, void* pl, const void* cur, void* nxt,
                  const void* evbits, const void* aux, std::string* err);
+
+// mirrors bnbp_spec::OcArgs (device side) for T = double / float
+template <typename T> struct OnchipArgs {
+    const long long* ev_off;
+    long long ev_base;
+    const int* ev_node;
+    const int* ev_state;
+    long long n_cases;
+    void* out;
+    int* out_sweeps;
+    unsigned char* out_conv;
+    unsigned long long* ticket;
+    int* error_flag;
+    T eps;
+    T damping;
+    int max_sweeps;
+    int interval;
+};
+
+// <<<blocks, threads, smem, st>>> bnbp_onchip_run(args)
+bool onchip_launch(const SpecKernel& k, unsigned blocks, unsigned threads, size_t smem, cudaStream_t st, const void* args,
+                   std::string* err);
 
 std::string spec_cache_dir();
 

@@ -17,6 +17,7 @@ from .flat import EvidenceBatch, FlatNetwork
 
 FP64, FP32 = 0, 1
 SPECIALIZE = {"auto": 0, "always": 1, "never": 2}
+ONCHIP = {"auto": 0, "always": 1, "never": -1}
 
 
 def _net_c(net: FlatNetwork):
@@ -82,7 +83,7 @@ class BeliefPropagation:
 
     def __init__(self, net: FlatNetwork, precision: str = "fp64", device: int = -1,
                  max_resident_cases: int = 0, specialize: str = "auto", dense_min_cpt: int = 0,
-                 dense_tensor: int = 0):
+                 dense_tensor: int = 0, onchip: str = "auto"):
         self.net = net
         self.precision = {"fp64": FP64, "fp32": FP32, "f64": FP64, "f32": FP32}[precision]
         lib = _capi.load()
@@ -93,8 +94,10 @@ class BeliefPropagation:
         # 256 entries, < 0 = never); see include/bnbp.h
         # dense_tensor: fp32 handles run large dense products on the tensor cores (tcgen05, 3xTF32);
         # 0 = default, 1 = every dense product, -1 = never
+        # onchip: the on-chip multi-sweep kernel ("auto": eligible networks with specialize="auto" and >= 4096
+        # hard-evidence cases; "always" / "never")
         opt = _capi.OptionsC(self.precision, device, max_resident_cases, SPECIALIZE[specialize], int(dense_min_cpt),
-                             int(dense_tensor))
+                             int(dense_tensor), ONCHIP[onchip])
         _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
 
     def close(self):
@@ -147,6 +150,11 @@ class BeliefPropagation:
         prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval))
         _capi.check(self._lib.bnbp_run_batch_device(self._h, C.byref(evc), C.byref(prm), dp(out), dp(out_sweeps),
                                                     dp(out_converged), C.c_void_p(stream) if stream else None))
+
+    def check_errors(self, stream: int = 0) -> None:
+        """After synchronising with a ``run_device`` call: raise if it skipped malformed evidence
+        (``bnbp_check_errors``; the asynchronous call itself cannot report it)."""
+        _capi.check(self._lib.bnbp_check_errors(self._h, C.c_void_p(stream) if stream else None))
 
     # ---- likelihood weighting (SURVEY 8 f2) ------------------------------------------------------
     def likelihood_weighting(self, evidence: EvidenceBatch, n_samples: int = 10000, seed: int = 1,

@@ -279,6 +279,70 @@ def make_evidence(net: FlatNetwork, n_cases: int, *, exact_k: int | None = None,
     return EvidenceBatch(n_cases, ev_off, ev_node, None, voff, vals)
 
 
+# ---- the same evidence, generated with torch (GPU) ---------------------------------------------------
+def _s64(v: int) -> int:
+    """A 64-bit pattern as the signed value torch.int64 holds."""
+    v &= _M64
+    return v - (1 << 64) if v >= (1 << 63) else v
+
+
+def _lsr(z, k: int):
+    """Logical right shift of int64 tensors (torch's >> is arithmetic)."""
+    return (z >> k) & ((1 << (64 - k)) - 1)
+
+
+def _mix_t(z):
+    z = z ^ _lsr(z, 30)
+    z = z * _s64(0xBF58476D1CE4E5B9)
+    z = z ^ _lsr(z, 27)
+    z = z * _s64(0x94D049BB133111EB)
+    return z ^ _lsr(z, 31)
+
+
+def _counter_t(seed: int, index, draw: int = 0):
+    s0 = _mix_t(index ^ _s64(seed))
+    return _mix_t(s0 + _s64((draw + 1) * _GAMMA))
+
+
+def make_evidence_torch(net: FlatNetwork, n_cases: int, *, p: float = 0.10, seed: int = EVIDENCE_SEED,
+                        case_offset: int = 0, device="cuda", chunk_elems: int = 1 << 25):
+    """``make_evidence(net, n_cases, p=p, ...)`` (hard evidence, every node independently with probability
+    ``p``) computed with torch integer arithmetic on ``device``: bit-identical CSR arrays, returned as
+    tensors (ev_off int64, ev_node int32, ev_state int32) that are already resident where the device path
+    wants them.  numpy needs ~6 s per 8 192 cases of the 10 000-node grid; this is what lets bench.py build
+    the 65 536-case batch of BASELINE config 3 in seconds."""
+    import torch
+    n = net.n_nodes
+    dev = torch.device(device)
+    sign = -(1 << 63)
+    thresh = _s64(int(p * 18446744073709551616.0) & _M64) ^ sign          # unsigned compare = signed compare of x ^ 2^63
+    node_ids = torch.arange(n, dtype=torch.int64, device=dev)
+    card = torch.from_numpy(net.card.astype(np.int64)).to(dev)
+    two64_mod = torch.tensor([(1 << 64) % max(int(r), 1) for r in net.card], dtype=torch.int64, device=dev)
+    step = max(1, chunk_elems // max(n, 1))
+    nodes_out, states_out, counts_out = [], [], []
+    for lo in range(0, n_cases, step):
+        hi = min(n_cases, lo + step)
+        case = torch.arange(case_offset + lo, case_offset + hi, dtype=torch.int64, device=dev)
+        key = case[:, None] * 0x100000001B3 + node_ids[None, :]
+        pick = (_counter_t(seed ^ 0x5EED, key) ^ sign) < thresh
+        counts_out.append(pick.sum(dim=1))
+        rows, cols = torch.nonzero(pick, as_tuple=True)
+        ent_key = case[rows] * 0x9E3779B1 + cols * 0x85EBCA77
+        u = _counter_t(seed ^ 0xABCD, ent_key, draw=0)
+        r = card[cols]
+        st = torch.remainder(u, r)
+        st = torch.where(u < 0, torch.remainder(st + two64_mod[cols], r), st)   # u is an unsigned 64-bit value
+        nodes_out.append(cols.to(torch.int32))
+        states_out.append(st.to(torch.int32))
+    counts = torch.cat(counts_out) if counts_out else torch.zeros(0, dtype=torch.int64, device=dev)
+    ev_off = torch.zeros(n_cases + 1, dtype=torch.int64, device=dev)
+    ev_off[1:] = torch.cumsum(counts, 0)
+    ev_node = torch.cat(nodes_out) if nodes_out else torch.zeros(0, dtype=torch.int32, device=dev)
+    ev_state = torch.cat(states_out) if states_out else torch.zeros(0, dtype=torch.int32, device=dev)
+    return ev_off, ev_node, ev_state
+
+
 WORKLOADS = {
     # name: (network factory, default cases, evidence kwargs, default fixed sweeps)
     "alarm37": (alarm37, 1 << 20, dict(exact_k=4), 20),

@@ -185,6 +185,7 @@ def run_reference_arm(args, rank: int, world: int):
     dt = sum(times)
     value = total_cases * sweeps * args.steps / dt
     kind = "reference" if use_ref else "port"
+    configs = None if args.no_configs else reference_scaled_configs(cores, use_ref)
     sample = (f"{total_cases} cases x {sweeps} sweeps per step ({per_core} per core), "
               f"{'oracle/_ref: unmodified reference headers' if use_ref else 'oracle C port (reference not compiled here)'}")
     line = {
@@ -195,9 +196,202 @@ def run_reference_arm(args, rank: int, world: int):
                    "cases_per_step": total_cases},
         "cpu_baseline": {"value": value, "unit": UNIT, "cores": cores, "kind": kind, "sample": sample},
         "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0,
+        "gpu_launches": 0, "configs": configs,
     }
     print(json.dumps(line), flush=True)
+
+
+def _ref_scaled_worker(args):
+    net, ev, sweeps = args
+    from oracle import oracle
+    return oracle.run_reference(net, ev, eps=0.0, max_sweeps=sweeps)[3]     # seconds inside operator()
+
+
+def reference_scaled_configs(cores: int, use_ref: bool):
+    """the UNMODIFIED reference on scaled instances of configs 3-5 (its cost grows
+    ~N^3 with the node count, so the full sizes cannot be run: 100x100 grid = ~2.5e4 s per sweep per case), one
+    process per core, one case each; full-size figures only as labelled extrapolations."""
+    import multiprocessing as mp
+    if not use_ref:
+        return None
+    scaled = [
+        ("cfg3'", "grid 20x20 (cfg 3 is 100x100)", synth.grid(20), 2,
+         (10000 / 400) ** 3, "N^3 (topology queries dominate: graph.hpp:378-413,466-481)"),
+        ("cfg4'", "random DAG 200 nodes, <= 4 parents, card 2-8 (cfg 4 has 2000)", synth.random_dag(200), 2,
+         (2000 / 200) ** 3, "N^3"),
+        ("cfg5'", "64 nodes, 3 parents, card 8 (cfg 5 has card 32)", synth.high_card(64, card=8, n_parents=3), 3,
+         (32 / 8) ** 4, "CPT entries (x256: same topology, hash-map CPT lookups dominate)"),
+    ]
+    out = []
+    for key, what, net, sweeps, factor, law in scaled:
+        shards = [synth.make_evidence(net, 1, case_offset=i, p=0.10) for i in range(cores)]
+        with mp.get_context("fork").Pool(cores) as pool:
+            t0 = time.perf_counter()
+            secs = pool.map(_ref_scaled_worker, [(net, s, sweeps) for s in shards])
+            wall = time.perf_counter() - t0
+        per_core = sweeps / (sum(secs) / len(secs))
+        out.append({"config": key, "instance": what, "nodes": net.n_nodes, "edges": net.n_edges, "cpt_entries": int(net.cpt.size),
+                    "kind": "reference", "cores": cores, "sample": f"1 case x {sweeps} sweeps per core, {wall:.1f} s",
+                    "case_sweeps_per_s_per_core": per_core, "value": per_core * cores, "unit": UNIT,
+                    "full_size_extrapolation": {"value": per_core * cores / factor, "unit": UNIT, "factor": factor, "law": law,
+                                                "note": "EXTRAPOLATED, not measured: the full-size instance cannot be run"}})
+    return out
+
+
+# ---------------------------------------------------------------------------------------------------
+# BASELINE.json configs 3-5 as short measured entries of the same JSON line ("configs"): value, the roofline
+# that BINDS the config (BASELINE.md section 4: HBM / FMA pipe / tensor pipe), a parity sample against the
+# oracle port and the port's own rate on that sample (the cpu_baseline of the entry).
+#   key, workload, BASELINE total cases, GPUs the config is defined on, precisions, parity sample (N=1, N>1), binding roofline
+EXTRA_CONFIGS = [
+    ("cfg3", "grid100", 1 << 16, 1, ["fp64"], (16, 16), "hbm"),
+    ("cfg4", "dag2000", 1 << 18, 8, ["fp64"], (48, 128), "fma"),
+    ("cfg5", "card32", 1 << 17, 8, ["fp32", "fp64"], (12, 24), "tensor"),
+]
+TOLERANCE = {"fp64": (1e-9, 1e-12), "fp32": (1e-5, 1e-7)}
+FMA_PEAK_TFLOPS = {"fp64": 37.2, "fp32": 74.4}     # nominal: 2 x 148 SMs x 1.965 GHz x (64 | 128) lanes
+FP64_TENSOR_PEAK_TFLOPS = 40.0                     # nominal B200 fp64 tensor (DMMA) rate
+
+
+def walk_flops(net) -> float:
+    """F = sum_X (2k+2) r_X Q_X: one fused CPT pass for pi_X and all k lambda-messages."""
+    k = np.diff(net.parent_off).astype(np.float64)
+    size = np.diff(net.cpt_off).astype(np.float64)
+    return float(((2 * k + 2) * size)[k > 0].sum())
+
+
+def measure_config(key, workload, total_cases, base_gpus, precision, parity_cases, binding, *, torch, dist, dev,
+                   local_rank, rank, world, with_cpu):
+    from bayesiannetwork_b200.engine import BeliefPropagation
+    from bayesiannetwork_b200.flat import EvidenceBatch
+    factory, _, evkw, sweeps = synth.WORKLOADS[workload]
+    net = factory()
+    # N = 1: the share one GPU holds when the config runs on the GPU count BASELINE.json names; N > 1: strong
+    # scaling, the BASELINE total sharded N ways
+    n = total_cases // (world if world > 1 else base_gpus)
+    tdtype = torch.float64 if precision == "fp64" else torch.float32
+    tsize = 8 if precision == "fp64" else 4
+    V, S = net.belief_values, net.state_values
+    t_gen = time.perf_counter()
+    d_off, d_node, d_state = synth.make_evidence_torch(net, n, case_offset=rank * n, device=dev, **evkw)
+    torch.cuda.synchronize()
+    t_gen = time.perf_counter() - t_gen
+    bp = BeliefPropagation(net, precision, device=local_rank)
+    d_out = torch.empty((n, V), dtype=tdtype, device=dev)
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def step():
+        bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=0.0, max_sweeps=sweeps, stream=stream)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    t0 = time.perf_counter()
+    step()                                               # warm-up (allocates the state arena)
+    barrier()
+    warm_s = time.perf_counter() - t0
+    steps = 2 if warm_s < 5.0 else 1
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record()
+    for _ in range(steps):
+        step()
+    e1.record()
+    barrier()
+    ms = e0.elapsed_time(e1)
+    st = bp.stats()
+    dense_ms = max(0.0, st["last_dense_ms"]) if st["dense_nodes"] else 0.0
+    sweep_ms = (st["last_sweep_ms"] - dense_ms) / max(1, st["last_sweep_launches"])
+    dense_ms_per_sweep = dense_ms / max(1, st["last_sweep_launches"])
+    if world > 1:
+        t = torch.tensor([ms, sweep_ms, dense_ms_per_sweep], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms, sweep_ms, dense_ms_per_sweep = (float(x) for x in t)
+    value = world * n * sweeps * steps / (ms * 1e-3)
+    per_gpu = value / world
+    peak, peak_src = measured_peaks()
+    hbm = {"bound": "hbm", "achieved": per_gpu * 2 * S * tsize / 1e9, "peak": peak, "unit": "GB/s", "peak_source": peak_src,
+           "algorithmic_bytes_per_case_sweep": 2 * S * tsize,
+           "note": "whole step (sweep kernel + dense products + init + beliefs) against the HBM copy peak"}
+    hbm["frac"] = hbm["achieved"] / peak
+    kern = {"sweep_kernel_ms_per_sweep": sweep_ms, "dense_ms_per_sweep": dense_ms_per_sweep,
+            "sweep_kernel_hbm_frac": (2.0 * S * tsize * min(n, st["resident_cases"]) / (sweep_ms * 1e-3) / 1e9 / peak) if sweep_ms > 0 else None,
+            "resident_cases": int(st["resident_cases"]), "dense_nodes": int(st["dense_nodes"]),
+            "kernel_launches_per_step": int(st["last_kernel_launches"])}
+    if binding == "hbm":
+        roof = hbm
+    elif binding == "fma":
+        F = walk_flops(net)
+        tf = per_gpu * F / 1e12
+        roof = {"bound": "fma", "achieved": tf, "peak": FMA_PEAK_TFLOPS[precision], "unit": "TFLOP/s",
+                "frac": tf / FMA_PEAK_TFLOPS[precision], "flops_per_case_sweep": F,
+                "peak_source": "nominal CUDA-core FMA peak at 1965 MHz (fp64 64, fp32 128 lanes per SM)",
+                "note": "algorithmic flops F = sum (2k+2) r Q (SURVEY 8d) x case-sweeps/s of the whole step; nodes on the dense "
+                        "path spend 4|CPT| instead of (2k+2)|CPT|, so the executed flops are lower", "hbm_frac": hbm["frac"]}
+    else:
+        dense_flops = st["dense_flops_per_case_sweep"]
+        if precision == "fp32" and st.get("dense_tensor_jobs", 0) and dense_ms_per_sweep > 0:
+            mp = {}
+            try:
+                mp = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+            except Exception:
+                pass
+            tpk = 0.5 * mp["bf16_tflops"] if mp.get("bf16_tflops") else 1100.0
+            issued = 3.0 * st["dense_tensor_flops_per_case_sweep"]
+            ttf = issued * min(n, st["resident_cases"]) / (dense_ms_per_sweep * 1e-3) / 1e12
+            roof = {"bound": "tensor", "achieved": ttf, "peak": tpk, "unit": "TFLOP/s", "frac": ttf / tpk, "kernel": "dense_tc_kernel",
+                    "issued_flops_per_case_sweep": issued, "algorithmic_flops_per_case_sweep": dense_flops,
+                    "note": "tcgen05 kind::tf32, 3xTF32 (hi*hi + hi*lo + lo*hi): issued tf32 flops = 3 x algorithmic, over the time "
+                            "of the dense launches of one sweep",
+                    "peak_source": ("0.5 x measured bf16 (MEASURED_PEAKS.json bf16_tflops)" if mp.get("bf16_tflops")
+                                    else "nominal tf32 dense 1.1 PFLOP/s"), "hbm_frac": hbm["frac"]}
+        else:
+            ttf = dense_flops * min(n, st["resident_cases"]) / max(dense_ms_per_sweep * 1e-3, 1e-12) / 1e12
+            roof = {"bound": "tensor", "achieved": ttf, "peak": FP64_TENSOR_PEAK_TFLOPS, "unit": "TFLOP/s",
+                    "frac": ttf / FP64_TENSOR_PEAK_TFLOPS, "kernel": "dense_gemm_kernel (fp64 mma.sync m8n8k4, DMMA)",
+                    "algorithmic_flops_per_case_sweep": dense_flops, "peak_source": "nominal B200 fp64 tensor rate (40 TFLOP/s)",
+                    "note": "no tensor-core format holds the 1e-9 bound, so the fp64 products run as DMMA", "hbm_frac": hbm["frac"]}
+    entry = {"config": key, "workload": workload, "dtype": "f64" if precision == "fp64" else "f32", "value": value, "unit": UNIT,
+             "n_gpus": world, "scaling": "strong" if world > 1 else f"1/{base_gpus} share of the BASELINE total" if base_gpus > 1 else "full size",
+             "total_cases": n * world, "cases_per_gpu": n, "baseline_total_cases": total_cases, "sweeps": sweeps, "steps": steps,
+             "ms_per_step": ms / steps, "nodes": net.n_nodes, "edges": net.n_edges, "state_values_per_case": S,
+             "roofline": roof, "kernels": kern, "evidence_generation_s": t_gen}
+    # parity (rank 0): evenly spaced cases of this rank's shard against the oracle port, same sweeps
+    if rank == 0:
+        k = min(parity_cases, n)
+        idx = np.unique(np.linspace(0, n - 1, k).astype(np.int64))
+        offs = d_off.cpu().numpy()
+        rows = d_out[torch.from_numpy(idx).to(dev)].double().cpu().numpy()
+        cases = []
+        for c in idx:
+            a, b = int(offs[c]), int(offs[c + 1])
+            cases.append(dict(zip(d_node[a:b].cpu().numpy().tolist(), d_state[a:b].cpu().numpy().tolist())))
+        sample = EvidenceBatch.from_cases(net, cases)
+        cores = cpu_cores()
+        from oracle import oracle
+        if not oracle.have_port():
+            oracle.build()
+        t0 = time.perf_counter()
+        om, _, _ = oracle.run_port(net, sample, eps=0.0, max_sweeps=sweeps, threads=cores)
+        dt = time.perf_counter() - t0
+        rtol, atol = TOLERANCE[precision]
+        err = np.abs(rows - om)
+        bound = rtol * np.maximum(np.abs(rows), np.abs(om)) + atol
+        ratio = float(np.nanmax(err / bound))
+        ok = bool(np.array_equal(np.isnan(rows), np.isnan(om)) and ratio <= 1.0)
+        entry["parity"] = {"cases": int(len(idx)), "checker": "oracle/bp_oracle.c", "rtol": rtol, "atol": atol,
+                           "max_err_over_bound": ratio, "ok": ok}
+        if with_cpu:
+            entry["cpu_baseline"] = {"value": len(idx) * sweeps / dt, "unit": UNIT, "cores": cores, "kind": "port",
+                                     "sample": f"{len(idx)} cases of the workload x {sweeps} sweeps, oracle/bp_oracle.c (OpenMP, {cores} threads), {dt:.1f} s"}
+        if not ok:
+            raise SystemExit(f"bench.py: {key} {precision}: parity sample off (max err/bound {ratio:.3g})")
+    bp.close()
+    del d_out, d_off, d_node, d_state
+    torch.cuda.empty_cache()
+    return entry
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -224,6 +418,9 @@ def main():
     ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
+    ap.add_argument("--no-configs", action="store_true",
+                    help="skip the short measured entries for BASELINE configs 3-5 (the `configs` array of the line)")
+    ap.add_argument("--only-configs", default="", help="comma-separated subset of cfg3,cfg4,cfg5")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "bnbp" else args.warmup
 
@@ -366,12 +563,14 @@ def main():
     if st["dense_nodes"] and dense_ms_per_sweep > 0 and not eps_info:
         # CUDA-core contraction (fp64 parity needs fp64 products): nominal B200 vector peaks
         # 2 x 148 SMs x 1.965 GHz x (64 fp64 | 128 fp32) lanes
-        pk = 37.2 if args.precision == "fp64" else 74.4
+        # fp64 products run as DMMA (tensor pipe); fp32 products without the tcgen05 path are CUDA-core FMAs
+        pk = FP64_TENSOR_PEAK_TFLOPS if args.precision == "fp64" else FMA_PEAK_TFLOPS["fp32"]
         tf = st["dense_flops_per_case_sweep"] * n / (dense_ms_per_sweep * 1e-3) / 1e12
         dense = {"kernel": "dense_gemm_kernel", "nodes": int(st["dense_nodes"]),
                  "flops_per_case_sweep": st["dense_flops_per_case_sweep"], "ms_per_sweep": dense_ms_per_sweep,
                  "achieved": tf, "peak": pk, "unit": "TFLOP/s", "frac": tf / pk,
-                 "peak_source": "nominal CUDA-core FMA peak at 1965 MHz (fp64 64, fp32 128 lanes per SM)",
+                 "peak_source": ("nominal B200 fp64 tensor rate (DMMA)" if args.precision == "fp64"
+                                 else "nominal CUDA-core FMA peak at 1965 MHz (128 fp32 lanes per SM)"),
                  "table_values_per_case": int(st["dense_values_per_case"]),
                  "launches_per_sweep": int(st["last_dense_launches"]) // max(1, int(st["last_sweep_launches"])),
                  "share_of_sweep_time": dense_ms_per_sweep / (dense_ms_per_sweep + sweep_ms_per_launch)}
@@ -387,6 +586,8 @@ def main():
             tpk = 0.5 * mp["bf16_tflops"] if mp.get("bf16_tflops") else 1100.0
             ttf = 3.0 * st["dense_tensor_flops_per_case_sweep"] * n / (dense_ms_per_sweep * 1e-3) / 1e12
             all_tc = int(st["dense_tensor_jobs"]) == 2 * int(st["dense_nodes"])
+            for kdrop in ("achieved", "peak", "frac", "peak_source"):      # a tensor job has no CUDA-core roofline
+                dense.pop(kdrop, None)
             dense.update({"kernel": "dense_tc_kernel" if all_tc else "dense_tc_kernel + dense_gemm_kernel",
                           "tensor_jobs": int(st["dense_tensor_jobs"]),
                           "tensor": {"bound": "tensor", "achieved": ttf, "peak": tpk, "unit": "TFLOP/s", "frac": ttf / tpk,
@@ -474,6 +675,26 @@ def main():
                "sample": f"first {sample_cases} cases of the workload x {sweeps} sweeps, oracle/bp_oracle.c "
                          f"(OpenMP, {cores} threads), {dt:.1f} s"}
 
+    # ---- BASELINE configs 3-5: short measured entries (every rank takes part; rank 0 checks parity) -----
+    configs = None
+    main_workload = args.workload == "alarm37" and not args.network and not args.cases and not eps_info
+    if main_workload and not args.no_configs:
+        bp.close()
+        del d_out, d_off, d_node, d_state, d_sw, d_cv, gathered
+        if e2e is not None:
+            del p_out, p_off, p_node, p_state, p_sw, p_cv, out_np, sw_np, cv_np, ev_pinned
+        gc.collect()
+        torch.cuda.empty_cache()
+        only = [x for x in args.only_configs.split(",") if x]
+        configs = []
+        for key, workload, total, base_gpus, precisions, samples, binding in EXTRA_CONFIGS:
+            if only and key not in only:
+                continue
+            for precision in precisions:
+                configs.append(measure_config(key, workload, total, base_gpus, precision, samples[1 if world > 1 else 0], binding,
+                                              torch=torch, dist=dist, dev=dev, local_rank=local_rank, rank=rank, world=world,
+                                              with_cpu=not args.no_cpu))
+
     if rank == 0:
         line = {
             "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
@@ -491,7 +712,7 @@ def main():
                        "l2": f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
                              f"of per-case state per GPU vs 126 MB"},
             "roofline": roofline, "dense": dense, "cpu_baseline": cpu, "e2e": e2e,
-            "gpu_launches": launches_per_step * args.steps, "clocks": clocks,
+            "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "configs": configs,
         }
         print(json.dumps(line), flush=True)
     if world > 1:

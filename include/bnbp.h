@@ -95,7 +95,12 @@ typedef struct bnbp_options {
                                    accumulators in TMEM, every operand split hi + lo into two tf32 values:
                                    csrc/bnbp_dense_tc.cuh).  0 = default (products with K >= 32, N >= 128),
                                    1 = every dense product, -1 = never (CUDA-core FMA products)             */
-    int32_t reserved[5];
+    int32_t onchip;             /* the ON-CHIP kernel (csrc/bnbp_onchip.cuh): a specialised network whose per-case state fits
+                                   shared memory runs init, every sweep, the stopping rule and the beliefs of a case in ONE
+                                   launch, 32 cases per CTA, the node walk split over 4 warps; HBM sees evidence in and
+                                   marginals out only.  0 = default (eligible networks, specialize == AUTO, hard evidence,
+                                   batches >= 4096 cases), 1 = always (error if impossible), -1 = never (streaming kernels) */
+    int32_t reserved[4];
 } bnbp_options;
 
 /* Evidence for a batch, CSR over cases.  Entry e of case c (ev_off[c] <= e < ev_off[c+1])
@@ -152,6 +157,11 @@ typedef struct bnbp_stats {
     int64_t last_compactions;        /* eps mode: how often the still-active cases were gathered into dense tiles */
     double  last_host_ms;            /* wall clock of the last bnbp_run_batch call, entry to return (-1: none yet)  */
     double  last_host_wait_ms;       /* of which: the final waits for the streams                                   */
+    int64_t last_onchip;             /* 1 if the last run used the on-chip kernel (state in shared memory for all sweeps) */
+    int64_t onchip_roles;            /* warps that share the node walk of a 32-case group (0: network not eligible)   */
+    int64_t onchip_smem_bytes;       /* shared memory of one group: (PL + 2M) * 32 values + reduction scratch          */
+    int64_t onchip_blocks_per_sm;    /* resident groups per SM of the loaded on-chip kernel (0: none loaded yet)        */
+    double  onchip_role_imbalance;   /* busiest role / mean role cost of the node partition (1 = perfectly balanced)    */
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;
@@ -214,11 +224,13 @@ int  bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values);
  * <dir of libbnbp.so>/jitcache), so that bnbp_create/run on the GPU box finds it there.
  * variant_mask: bit 0 plain (fixed sweeps), bit 1 freeze, bit 2 freeze+check (epsilon mode, damping),
  *               bit 3 plain-first (time-0 messages are all 1: not loaded), bit 4 plain-last (messages
- *               of the last sweep are never read: not stored).
+ *               of the last sweep are never read: not stored), bits 5-7 the fused first / last sweeps;
+ *               bits 8-11 the on-chip kernel: 8 fixed sweeps, 9 the same with double marginals from a
+ *               float kernel, 10 / 11 the epsilon / damping flavour of the two.
  * Returns BNBP_ERR_INVALID with the reason if the network is not eligible. */
 int  bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant_mask);
 
-/* The generated CUDA source of one variant (0..4), for inspection and tests.  Writes at most
+/* The generated CUDA source of one variant (0..7 streaming, 8 / 9 on-chip plain / check), for inspection and tests.  Writes at most
  * cap bytes including the terminating NUL and returns the full length via *needed. */
 int  bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int32_t variant,
                       char* buf, int64_t cap, int64_t* needed);

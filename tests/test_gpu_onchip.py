@@ -1,0 +1,215 @@
+"""Parity of the ON-CHIP multi-sweep kernel (bnbp_onchip.cuh: the state of 32 cases in shared memory for all
+sweeps, node walk split over 4 warps, cases handed out by a ticket counter) with the oracle -- needs a B200.
+
+Same bar as the other parity tests: fp64 1e-9 / 1e-12 with equal sweep counts and flags in eps mode, fp32
+1e-5 / 1e-7 at fixed sweep counts.  ``onchip="always"`` makes a missing / failing compile an error."""
+import numpy as np
+import pytest
+
+from bayesiannetwork_b200 import synth
+from bayesiannetwork_b200.flat import EvidenceBatch
+from helpers import assert_close, load_fixture
+
+pytestmark = pytest.mark.gpu
+TOL = {"fp64": dict(rtol=1e-9, atol=1e-12), "fp32": dict(rtol=1e-5, atol=1e-7)}
+
+
+@pytest.fixture(scope="module")
+def BP():
+    from bayesiannetwork_b200.engine import BeliefPropagation
+    return BeliefPropagation
+
+
+def _hub():
+    card = [3] + [2 + (i % 3) for i in range(12)] + [2, 4]
+    parents = [[]] + [[0] for _ in range(12)] + [[], [5, 9]]
+    return synth._assemble(card, parents, 77, "hub12")
+
+
+def _cases():
+    yield "alarm37_fixed", synth.alarm37(), dict(exact_k=4), 0.0, 20
+    yield "alarm37_eps", synth.alarm37(), dict(exact_k=4), 1e-6, 200
+    yield "polytree40", synth.random_polytree(40, card_hi=4, seed=21), dict(p=0.15), 1e-8, 300
+    yield "grid6_loopy", synth.grid(6, seed=4), dict(p=0.1), 1e-7, 400
+    yield "dag45_k4", synth.random_dag(45, 4, 2, 3, seed=7), dict(p=0.1), 0.0, 12
+    yield "hub12_isolated", _hub(), dict(p=0.3), 1e-9, 200
+
+
+@pytest.mark.parametrize("name,net,evkw,eps,cap", list(_cases()), ids=[c[0] for c in _cases()])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_onchip_vs_oracle(BP, oracle_mod, name, net, evkw, eps, cap, precision):
+    if precision == "fp32" and eps > 0:
+        pytest.skip("fp32 parity is asserted at fixed sweep counts")
+    ev = synth.make_evidence(net, 777, seed=17, **evkw)          # ragged: 24 groups of 32 and one of 9
+    om, osw, ocv = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap, threads=0)
+    bp = BP(net, precision, onchip="always")
+    if bp.stats()["onchip_roles"] == 0:
+        pytest.skip("the state of 32 cases of this network does not fit shared memory in this precision")
+    res = bp(ev, eps, max_sweeps=cap)
+    st = bp.stats()
+    assert st["last_onchip"] == 1 and st["onchip_blocks_per_sm"] >= 1
+    assert np.array_equal(res.sweeps, osw), (name, np.nonzero(res.sweeps != osw)[0][:5])
+    assert np.array_equal(res.converged, ocv), name
+    assert_close(res.marginals, om, what=name, **TOL[precision])
+
+
+@pytest.mark.parametrize("name", ["pearl_tests", "pearl_nan", "pearl_nan_fixed6", "resume_tests"])
+def test_onchip_reference_fixtures(BP, ref_fixtures, name):
+    """The reference's own graphs incl. the impossible-evidence (NaN) case, from reference output."""
+    f = load_fixture(ref_fixtures, name)
+    if f["ev"].is_soft:
+        pytest.skip("soft evidence rows take the streaming kernels")
+    bp = BP(f["net"], "fp64", onchip="always")
+    res = bp(f["ev"], f["eps"], max_sweeps=f["max_sweeps"])
+    assert bp.stats()["last_onchip"] == 1
+    assert np.array_equal(res.sweeps, f["sweeps"]), (res.sweeps, f["sweeps"])
+    assert np.array_equal(res.converged, f["converged"])
+    assert_close(res.marginals, f["marginals"], what=name, **TOL["fp64"])
+
+
+def test_onchip_is_the_default_for_large_batches_and_matches_the_streaming_kernels(BP, oracle_mod):
+    """>= 4096 hard-evidence cases of an eligible network take the on-chip kernel by default; the streaming
+    specialised kernels (specialize="always") and the generic kernel give the same beliefs."""
+    net = synth.alarm37()
+    ev = synth.make_evidence(net, 5000, exact_k=4, seed=3)
+    a = BP(net, "fp64")
+    ra = a(ev, 0.0, max_sweeps=20)
+    assert a.stats()["last_onchip"] == 1
+    b = BP(net, "fp64", specialize="always")
+    rb = b(ev, 0.0, max_sweeps=20)
+    assert b.stats()["last_onchip"] == 0 and b.stats()["last_specialised"] == 1
+    c = BP(net, "fp64", specialize="never")
+    rc = c(ev, 0.0, max_sweeps=20)
+    assert c.stats()["last_onchip"] == 0 and c.stats()["last_specialised"] == 0
+    assert_close(ra.marginals, rb.marginals, what="on-chip vs streaming", **TOL["fp64"])
+    assert_close(ra.marginals, rc.marginals, what="on-chip vs generic", **TOL["fp64"])
+    om, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=20, threads=0)
+    assert_close(ra.marginals, om, what="on-chip vs oracle", **TOL["fp64"])
+    # small batches stay on the generic kernel; soft evidence takes the streaming kernels
+    small = ev.slice(0, 100)
+    a(small, 0.0, max_sweeps=5)
+    assert a.stats()["last_onchip"] == 0
+    soft = synth.make_evidence(net, 5000, exact_k=4, seed=3, soft=True)
+    rs = a(soft, 0.0, max_sweeps=6)
+    assert a.stats()["last_onchip"] == 0
+    os_, _, _ = oracle_mod.run_port(net, soft, eps=0.0, max_sweeps=6, threads=0)
+    assert_close(rs.marginals, os_, what="soft evidence", **TOL["fp64"])
+
+
+def test_onchip_eps_mode_extensions_and_refill(BP, oracle_mod):
+    """Sweep counts spread from 3 to 40 on alarm37: lanes retire and take new cases at different sweeps.  Also
+    check_interval and damping (the time-t message comes from the other shared-memory buffer)."""
+    net = synth.alarm37()
+    ev = synth.make_evidence(net, 6001, exact_k=4, seed=11)
+    for kw in (dict(), dict(check_interval=3), dict(damping=0.2), dict(damping=0.1, check_interval=4)):
+        om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-7, max_sweeps=60, threads=0, **kw)
+        bp = BP(net, "fp64", onchip="always")
+        res = bp(ev, 1e-7, max_sweeps=60, **kw)
+        assert bp.stats()["last_onchip"] == 1
+        assert np.array_equal(res.sweeps, osw), (kw, np.nonzero(res.sweeps != osw)[0][:5])
+        assert np.array_equal(res.converged, ocv), kw
+        assert_close(res.marginals, om, what=str(kw), **TOL["fp64"])
+        assert osw.min() < osw.max()
+    # fixed sweep count with damping (the check variant without a stopping rule)
+    om, osw, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=9, threads=0, damping=0.3)
+    res = BP(net, "fp64", onchip="always")(ev, 0.0, max_sweeps=9, damping=0.3)
+    assert np.array_equal(res.sweeps, osw)
+    assert_close(res.marginals, om, what="fixed + damping", **TOL["fp64"])
+
+
+def test_onchip_batch_shapes_device_path_and_errors(BP, oracle_mod):
+    import torch
+    from bayesiannetwork_b200.engine import BnbpError
+    net = synth.alarm37()
+    bp = BP(net, "fp64", onchip="always")
+    for n in (1, 31, 32, 33, 4736, 4737):                        # one lane ... one case more than a full grid of groups
+        ev = synth.make_evidence(net, n, exact_k=4, seed=50 + n)
+        om, osw, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=7, threads=0)
+        res = bp(ev, 0.0, max_sweeps=7)
+        assert np.array_equal(res.sweeps, osw)
+        assert_close(res.marginals, om, what=f"{n} cases", **TOL["fp64"])
+    # no evidence at all, every node observed, a node listed twice (the last entry wins)
+    all_nodes = {i: int(i % net.card[i]) for i in range(net.n_nodes)}
+    ev = EvidenceBatch.from_cases(net, [{}, all_nodes, {0: 1}, {36: 0, 5: 1, 17: 0}])
+    om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=100)
+    res = bp(ev, 1e-6, max_sweeps=100)
+    assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv)
+    assert_close(res.marginals, om, what="edge", **TOL["fp64"])
+    dup = EvidenceBatch(1, np.array([0, 2]), np.array([3, 3], np.int32), np.array([0, 1], np.int32))
+    one = EvidenceBatch(1, np.array([0, 1]), np.array([3], np.int32), np.array([1], np.int32))
+    assert np.array_equal(bp(dup, 0.0, max_sweeps=5).marginals, bp(one, 0.0, max_sweeps=5).marginals)
+    # device path: float marginals from a float handle, device-resident evidence
+    bp32 = BP(net, "fp32", onchip="always")
+    ev = synth.make_evidence(net, 3000, exact_k=4, seed=9)
+    dev = torch.device("cuda", 0)
+    out = torch.empty((3000, net.belief_values), dtype=torch.float32, device=dev)
+    sw = torch.empty(3000, dtype=torch.int32, device=dev)
+    bp32.run_device(3000, torch.from_numpy(ev.ev_off).to(dev), torch.from_numpy(ev.ev_node).to(dev),
+                    torch.from_numpy(ev.ev_state).to(dev), out, epsilon=0.0, max_sweeps=20, out_sweeps=sw)
+    torch.cuda.synchronize()
+    bp32.check_errors()
+    om, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=20, threads=0)
+    assert bp32.stats()["last_onchip"] == 1 and int(sw.min()) == 20 == int(sw.max())
+    assert_close(out.cpu().numpy(), om, what="device path fp32", **TOL["fp32"])
+    # malformed evidence is reported, and the handle stays usable
+    bad = EvidenceBatch(1, np.array([0, 1]), np.array([1], np.int32), np.array([7], np.int32))
+    with pytest.raises(BnbpError):
+        bp(bad, 0.0, max_sweeps=3)
+    bad = EvidenceBatch(1, np.array([0, 1]), np.array([99], np.int32), np.array([0], np.int32))
+    with pytest.raises(BnbpError):
+        bp(bad, 0.0, max_sweeps=3)
+    assert np.isfinite(bp(one, 0.0, max_sweeps=3).marginals).all()
+
+
+def test_onchip_refresh_cpt_and_ineligible_networks(BP, oracle_mod):
+    from bayesiannetwork_b200.engine import BnbpError
+    net = synth.random_dag(20, 3, 2, 4, seed=31)
+    bp = BP(net, onchip="always")
+    ev = synth.make_evidence(net, 200, p=0.2, seed=2)
+    bp(ev, 0.0, max_sweeps=4)
+    cpt = net.cpt[::-1].copy()
+    for x in range(net.n_nodes):
+        r = int(net.card[x])
+        seg = cpt[net.cpt_off[x]:net.cpt_off[x + 1]].reshape(-1, r)
+        seg /= seg.sum(axis=1, keepdims=True)
+    from bayesiannetwork_b200.flat import FlatNetwork
+    net2 = FlatNetwork(net.card, net.parent_off, net.parents, net.cpt_off, cpt, name="refreshed")
+    bp.refresh_cpt(net2.cpt)
+    om, _, _ = oracle_mod.run_port(net2, ev, eps=0.0, max_sweeps=9, threads=0)
+    assert_close(bp(ev, 0.0, max_sweeps=9).marginals, om, what="refresh", **TOL["fp64"])
+    # a network whose state does not fit shared memory is refused with onchip="always" and served by the
+    # streaming / generic kernels by default
+    big = synth.grid(30, seed=2)
+    with pytest.raises(BnbpError):
+        BP(big, onchip="always")(synth.make_evidence(big, 64, p=0.1), 0.0, max_sweeps=3)
+    res = BP(big)(synth.make_evidence(big, 4200, p=0.1), 0.0, max_sweeps=3)
+    assert np.isfinite(res.marginals).all()
+
+
+def test_onchip_full_size_alarm37_properties(BP, oracle_mod):
+    """BASELINE cfg 2 at full size through the on-chip kernel (the default path of bench.py): size-independent
+    properties, shard invariance, and a 256-case sample against the oracle, fixed sweeps and eps mode."""
+    net = synth.alarm37()
+    n = 1 << 20
+    ev = synth.make_evidence(net, n, exact_k=4)
+    bp = BP(net)
+    res = bp(ev, 0.0, max_sweeps=20)
+    assert bp.stats()["last_onchip"] == 1
+    m = res.marginals
+    off = net.belief_off
+    assert np.isfinite(m).all()
+    assert np.abs(np.add.reduceat(m, off[:-1], axis=1) - 1.0).max() < 1e-12
+    rows = np.repeat(np.arange(n), np.diff(ev.ev_off))
+    assert np.array_equal(m[rows, off[ev.ev_node] + ev.ev_state], np.ones(ev.nnz))
+    lo, hi = 300_001, 300_001 + 70_000
+    part = bp(ev.slice(lo, hi), 0.0, max_sweeps=20)
+    assert np.array_equal(part.marginals, m[lo:hi])              # a case's result does not depend on its lane or group
+    idx = np.linspace(0, n - 1, 256).astype(np.int64)
+    sample = EvidenceBatch.from_cases(net, [
+        {int(ev.ev_node[e]): int(ev.ev_state[e]) for e in range(ev.ev_off[c], ev.ev_off[c + 1])} for c in idx])
+    om, _, _ = oracle_mod.run_port(net, sample, eps=0.0, max_sweeps=20, threads=0)
+    assert_close(m[idx], om, what="alarm37 sample", **TOL["fp64"])
+    res = bp(ev, 1e-6, max_sweeps=200)
+    om, osw, ocv = oracle_mod.run_port(net, sample, eps=1e-6, max_sweeps=200, threads=0)
+    assert np.array_equal(res.sweeps[idx], osw) and np.array_equal(res.converged[idx], ocv)
+    assert_close(res.marginals[idx], om, what="alarm37 eps sample", **TOL["fp64"])

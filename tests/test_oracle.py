@@ -120,3 +120,14 @@ def test_live_reference_random_nets(oracle_mod, seed):
             mp, sp, cp = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap)
             assert np.array_equal(sr, sp) and np.array_equal(cr, cp)
             assert_close(mp, mr, rtol=1e-12, atol=1e-15, what=f"seed{seed} soft{soft} eps{eps}")
+
+
+def test_torch_evidence_generator_is_bit_identical_to_numpy():
+    """synth.make_evidence_torch (what bench.py uses for the big batches of configs 3-5) = synth.make_evidence."""
+    from bayesiannetwork_b200 import synth
+    for net in (synth.grid(9), synth.random_dag(120), synth.high_card(6, 32, 3)):
+        for off in (0, 98765):
+            a = synth.make_evidence(net, 300, p=0.1, case_offset=off)
+            o, nd, st = synth.make_evidence_torch(net, 300, p=0.1, case_offset=off, device="cpu", chunk_elems=20000)
+            assert np.array_equal(a.ev_off, o.numpy()) and np.array_equal(a.ev_node, nd.numpy())
+            assert np.array_equal(a.ev_state, st.numpy())
