@@ -35,7 +35,16 @@ class EvidenceC(C.Structure):
 
 class RunParamsC(C.Structure):
     _fields_ = [("epsilon", C.c_double), ("max_sweeps", C.c_int32), ("damping", C.c_double),
-                ("check_interval", C.c_int32), ("reserved", C.c_int32 * 7)]
+                ("check_interval", C.c_int32), ("out_precision", C.c_int32), ("gather", C.c_int32),
+                ("n_query", C.c_int32), ("query_nodes", C.c_void_p), ("reserved", C.c_int32 * 4)]
+
+
+class SummaryC(C.Structure):
+    _fields_ = [("n_cases", C.c_int64), ("case_sweeps", C.c_int64), ("not_converged", C.c_int64),
+                ("max_sweeps", C.c_int64)]
+
+
+COMM_ID_BYTES = 128
 
 
 class StatsC(C.Structure):
@@ -57,6 +66,8 @@ class StatsC(C.Structure):
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",
            "bnbp_run_batch_device", "bnbp_check_errors", "bnbp_lw_run_batch", "bnbp_estimate_cpt", "bnbp_get_stats", "bnbp_refresh_cpt", "bnbp_precompile", "bnbp_spec_source",
+           "bnbp_host_alloc", "bnbp_host_free", "bnbp_create_multi", "bnbp_get_summary", "bnbp_comm_unique_id",
+           "bnbp_comm_init", "bnbp_comm_summary",
            "bnbp_netfile_parse", "bnbp_netfile_load", "bnbp_netfile_network", "bnbp_netfile_name",
            "bnbp_netfile_node_name", "bnbp_netfile_state_name", "bnbp_netfile_free"]
 
@@ -88,6 +99,20 @@ def load():
     lib.bnbp_run_batch_device.restype = C.c_int
     lib.bnbp_run_batch_device.argtypes = [C.c_void_p, C.POINTER(EvidenceC), C.POINTER(RunParamsC),
                                           C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
+    lib.bnbp_host_alloc.restype = C.c_void_p
+    lib.bnbp_host_alloc.argtypes = [C.c_size_t]
+    lib.bnbp_host_free.restype = None
+    lib.bnbp_host_free.argtypes = [C.c_void_p]
+    lib.bnbp_create_multi.restype = C.c_int
+    lib.bnbp_create_multi.argtypes = [C.POINTER(FlatNetworkC), C.POINTER(OptionsC), C.c_void_p, C.c_int32, C.POINTER(C.c_void_p)]
+    lib.bnbp_get_summary.restype = C.c_int
+    lib.bnbp_get_summary.argtypes = [C.c_void_p, C.POINTER(SummaryC)]
+    lib.bnbp_comm_unique_id.restype = C.c_int
+    lib.bnbp_comm_unique_id.argtypes = [C.c_void_p]
+    lib.bnbp_comm_init.restype = C.c_int
+    lib.bnbp_comm_init.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p]
+    lib.bnbp_comm_summary.restype = C.c_int
+    lib.bnbp_comm_summary.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.POINTER(SummaryC), C.c_void_p]
     lib.bnbp_check_errors.restype = C.c_int
     lib.bnbp_check_errors.argtypes = [C.c_void_p, C.c_void_p]
     lib.bnbp_lw_run_batch.restype = C.c_int

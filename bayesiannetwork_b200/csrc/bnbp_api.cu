@@ -10,6 +10,8 @@
 #include "bnbp_dense.h"
 #include "bnbp_dense_tc.cuh"
 
+#include <nccl.h>
+
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
@@ -18,6 +20,7 @@
 #include <map>
 #include <memory>
 #include <string>
+#include <thread>
 #include <vector>
 
 using namespace bnbp;
@@ -204,6 +207,24 @@ struct bnbp_handle {
     // stats of the last run
     int64_t last_case_sweeps = -1, last_sweep_launches = 0, last_kernel_launches = 0;
     bool total_recorded = false;
+    // what leaves the device (bnbp_run_params.n_query / query_nodes)
+    std::vector<int32_t> q_nodes;      // the query the device tables describe (empty: every node)
+    bool q_valid = false;
+    int Vout = 0;                      // values per output row of the current run
+    DevBuf d_belcol;                   // [N] column of node x's marginal in an output row, -1: not written
+    DevBuf d_colmap;                   // [Vout] source column (full-width row) of output column j
+    DevBuf s_full;                     // full-width rows of a chunk (streaming kernels under a query), gathered into the output
+    // host link / memory rates for the chunk planner (measured once per handle, not assumed)
+    double link_gbs = 0.0, hbm_gbs = 0.0;
+    // multi-GPU: the communicator this handle owns, and -- for a group handle -- its members
+    ncclComm_t comm = nullptr;
+    int comm_rank = 0, comm_world = 1;
+    cudaStream_t comm_stream = nullptr;
+    std::vector<cudaEvent_t> ev_comm;  // per gather chunk: computed, gathered
+    DevBuf d_summary;                  // 4 x int64: case sweeps, not converged, max sweeps, cases
+    int64_t* pin_summary = nullptr;    // pinned [4]
+    std::vector<bnbp_handle*> members; // group handle: one member per device (the group itself holds no device state)
+    bnbp_summary last_summary = {0, 0, 0, 0};
 };
 
 namespace {
@@ -916,6 +937,7 @@ int run_onchip(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_
     a.ev_node = de.ev_node; a.ev_state = de.ev_state;
     a.n_cases = n;
     a.out = d_out; a.out_sweeps = d_out_sweeps; a.out_conv = d_out_conv;
+    a.bel_col = (const int*)h->d_belcol.p; a.out_stride = h->Vout;
     a.ticket = ticket; a.error_flag = misc + 1;
     a.eps = (T)prm.epsilon; a.damping = (T)prm.damping;
     a.max_sweeps = prm.max_sweeps > 0 ? prm.max_sweeps : (1 << 30);
@@ -941,6 +963,197 @@ int run_onchip(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_
     h->last_fused = 1;
     if (planned_sweeps) *planned_sweeps = eps_mode ? -1 : (int64_t)a.max_sweeps * n;
     return BNBP_OK;
+}
+
+// ---- what leaves the device ---------------------------------------------------------------------------
+// Row layout of the marginals of this run: every node (the reference's result map, :151-158) or the queried
+// nodes only.  The device tables are rebuilt only when the query changes.
+int query_columns(const bnbp_handle* h, const bnbp_run_params& prm, std::vector<int32_t>* q, std::vector<int32_t>* belcol,
+                  std::vector<int32_t>* colmap)
+{
+    if (prm.n_query < 0) return fail(BNBP_ERR_INVALID, "n_query < 0");
+    if (prm.n_query > 0 && !prm.query_nodes) return fail(BNBP_ERR_INVALID, "query_nodes is NULL");
+    q->assign(prm.query_nodes, prm.query_nodes + prm.n_query);
+    belcol->assign((size_t)h->N, -1);
+    colmap->clear();
+    if (q->empty()) {
+        for (int x = 0; x < h->N; ++x) {
+            (*belcol)[(size_t)x] = h->nodes[x].bel_off;
+            for (int i = 0; i < h->nodes[x].card; ++i) colmap->push_back(h->nodes[x].bel_off + i);
+        }
+        return BNBP_OK;
+    }
+    for (int32_t x : *q) {
+        if (x < 0 || x >= h->N) return fail(BNBP_ERR_INVALID, "query node id out of range");
+        if ((*belcol)[(size_t)x] >= 0) return fail(BNBP_ERR_INVALID, "query node listed twice");
+        (*belcol)[(size_t)x] = (int32_t)colmap->size();
+        for (int i = 0; i < h->nodes[x].card; ++i) colmap->push_back(h->nodes[x].bel_off + i);
+    }
+    return BNBP_OK;
+}
+
+int set_query(bnbp_handle* h, const bnbp_run_params& prm)
+{
+    std::vector<int32_t> q, belcol, colmap;
+    int rc = query_columns(h, prm, &q, &belcol, &colmap);
+    if (rc) return rc;
+    if (h->q_valid && q == h->q_nodes) return BNBP_OK;
+    CU_TRY(cudaDeviceSynchronize());          // an earlier asynchronous run may still read the old tables
+    if ((rc = h->d_belcol.ensure(belcol.size() * 4)) || (rc = h->d_colmap.ensure(std::max<size_t>(16, colmap.size() * 4)))) return rc;
+    CU_TRY(cudaMemcpy(h->d_belcol.p, belcol.data(), belcol.size() * 4, cudaMemcpyHostToDevice));
+    if (!colmap.empty()) CU_TRY(cudaMemcpy(h->d_colmap.p, colmap.data(), colmap.size() * 4, cudaMemcpyHostToDevice));
+    h->q_nodes.swap(q);
+    h->Vout = (int)colmap.size();
+    h->q_valid = true;
+    return BNBP_OK;
+}
+
+template <typename OUT>
+__global__ void gather_columns_kernel(const OUT* __restrict__ src, OUT* __restrict__ dst, int64_t n, int V, int Vout,
+                                      const int32_t* __restrict__ colmap)
+{
+    const int64_t total = n * Vout;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < total; i += (int64_t)gridDim.x * blockDim.x) {
+        const int64_t c = i / Vout;
+        dst[i] = src[c * V + colmap[i - c * Vout]];
+    }
+}
+
+// One chunk through whichever kernel family the run chose; under a query the streaming kernels write full-width
+// rows into a staging buffer and the asked-for columns are gathered into the output (the on-chip kernel writes
+// only those in the first place).
+template <typename T, typename OUT>
+int run_any(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_params& prm, OUT* d_out, int32_t* d_out_sweeps,
+            uint8_t* d_out_conv, cudaStream_t st, int64_t* planned_sweeps)
+{
+    if (h->run_onchip) return run_onchip<T, OUT>(h, n, de, prm, d_out, d_out_sweeps, d_out_conv, st, planned_sweeps);
+    if (h->q_nodes.empty()) return run_chunk<T, OUT>(h, n, de, prm, d_out, d_out_sweeps, d_out_conv, st, planned_sweeps);
+    int rc = h->s_full.ensure((size_t)n * h->V * sizeof(OUT));
+    if (rc) return rc;
+    if ((rc = run_chunk<T, OUT>(h, n, de, prm, (OUT*)h->s_full.p, d_out_sweeps, d_out_conv, st, planned_sweeps))) return rc;
+    const int64_t total = n * h->Vout;
+    if (total > 0) {
+        gather_columns_kernel<OUT><<<(unsigned)std::min<int64_t>((total + 255) / 256, 148 * 16), 256, 0, st>>>(
+            (const OUT*)h->s_full.p, d_out, n, h->V, h->Vout, (const int32_t*)h->d_colmap.p);
+        CU_TRY(cudaGetLastError());
+        h->last_kernel_launches++;
+    }
+    return BNBP_OK;
+}
+
+// ---- rates the chunk planner needs: measured on this handle's device, once --------------------------------
+int measure_rates(bnbp_handle* h)
+{
+    if (h->link_gbs > 0.0) return BNBP_OK;
+    // device-to-host over the link this GPU sits on: 32 MB from device memory into pinned memory, second of two copies
+    const size_t bytes = 32u << 20;
+    void* dev = nullptr;
+    void* host = nullptr;
+    CU_TRY(cudaMalloc(&dev, bytes));
+    if (cudaMallocHost(&host, bytes) != cudaSuccess) { cudaFree(dev); cudaGetLastError(); h->link_gbs = 25.0; }
+    else {
+        cudaEvent_t e0, e1;
+        cudaEventCreate(&e0);
+        cudaEventCreate(&e1);
+        cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->copy_stream);
+        cudaEventRecord(e0, h->copy_stream);
+        cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, h->copy_stream);
+        cudaEventRecord(e1, h->copy_stream);
+        float ms = 0.f;
+        if (cudaEventSynchronize(e1) == cudaSuccess && cudaEventElapsedTime(&ms, e0, e1) == cudaSuccess && ms > 0.f)
+            h->link_gbs = (double)bytes / (ms * 1e-3) / 1e9;
+        else
+            h->link_gbs = 25.0;
+        cudaEventDestroy(e0);
+        cudaEventDestroy(e1);
+        cudaFreeHost(host);
+        cudaFree(dev);
+        cudaGetLastError();
+    }
+    // HBM: 0.8 of the interface rate the device reports (memory clock x bus width, double data rate)
+    int khz = 0, bits = 0;
+    cudaDeviceGetAttribute(&khz, cudaDevAttrMemoryClockRate, h->device);
+    cudaDeviceGetAttribute(&bits, cudaDevAttrGlobalMemoryBusWidth, h->device);
+    h->hbm_gbs = khz > 0 && bits > 0 ? 0.8 * 2.0 * (double)khz * 1e3 * (double)bits / 8.0 / 1e9 : 4000.0;
+    cudaGetLastError();
+    return BNBP_OK;
+}
+
+// ---- multi-GPU: summary of a shard on the device, all-reduced over the handle's communicator ----------------
+__global__ void summary_kernel(const int32_t* __restrict__ sweeps, const uint8_t* __restrict__ conv, int64_t n,
+                               unsigned long long* __restrict__ out)
+{
+    unsigned long long s = 0, nc = 0, mx = 0, cnt = 0;
+    for (int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (int64_t)gridDim.x * blockDim.x) {
+        const unsigned long long v = (unsigned long long)sweeps[i];
+        s += v;
+        nc += conv[i] ? 0u : 1u;
+        mx = v > mx ? v : mx;
+        ++cnt;
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        s += __shfl_xor_sync(0xffffffffu, s, o);
+        nc += __shfl_xor_sync(0xffffffffu, nc, o);
+        cnt += __shfl_xor_sync(0xffffffffu, cnt, o);
+        const unsigned long long m2 = __shfl_xor_sync(0xffffffffu, mx, o);
+        mx = m2 > mx ? m2 : mx;
+    }
+    if ((threadIdx.x & 31) == 0) {
+        atomicAdd(&out[0], s);
+        atomicAdd(&out[1], nc);
+        atomicAdd(&out[2], cnt);
+        atomicMax(&out[4], mx);
+    }
+}
+
+int comm_resources(bnbp_handle* h)
+{
+    if (h->comm_stream) return BNBP_OK;
+    CU_TRY(cudaSetDevice(h->device));
+    CU_TRY(cudaStreamCreateWithFlags(&h->comm_stream, cudaStreamNonBlocking));
+    int rc = h->d_summary.ensure(8 * 8);
+    if (rc) return rc;
+    CU_TRY(cudaMallocHost((void**)&h->pin_summary, 8 * 8));
+    return BNBP_OK;
+}
+
+#define NCCL_TRY(expr)                                                                              \
+    do {                                                                                            \
+        ncclResult_t r__ = (expr);                                                                  \
+        if (r__ != ncclSuccess) return fail(BNBP_ERR_CUDA, std::string(#expr) + ": " + ncclGetErrorString(r__)); \
+    } while (0)
+
+// enqueue: local reduction of (sweeps, converged) of n cases, then the two all-reduces (sum / max); the totals land
+// in h->pin_summary once `st` has drained
+int enqueue_summary(bnbp_handle* h, const int32_t* d_sweeps, const uint8_t* d_conv, int64_t n, cudaStream_t st)
+{
+    unsigned long long* d = (unsigned long long*)h->d_summary.p;
+    CU_TRY(cudaMemsetAsync(d, 0, 8 * 8, st));
+    if (n > 0) {
+        summary_kernel<<<(unsigned)std::min<int64_t>((n + 255) / 256, 148 * 8), 256, 0, st>>>(d_sweeps, d_conv, n, d);
+        CU_TRY(cudaGetLastError());
+    }
+    if (h->comm && h->comm_world > 1) {
+        NCCL_TRY(ncclAllReduce(d, d, 4, ncclUint64, ncclSum, h->comm, st));
+        NCCL_TRY(ncclAllReduce(d + 4, d + 4, 1, ncclUint64, ncclMax, h->comm, st));
+    }
+    CU_TRY(cudaMemcpyAsync(h->pin_summary, d, 8 * 8, cudaMemcpyDeviceToHost, st));
+    return BNBP_OK;
+}
+
+void read_summary(const bnbp_handle* h, bnbp_summary* out)
+{
+    out->case_sweeps = h->pin_summary[0];
+    out->not_converged = h->pin_summary[1];
+    out->n_cases = h->pin_summary[2];
+    out->max_sweeps = h->pin_summary[4];
+}
+
+void shard_range(int64_t n, int g, int G, int64_t* lo, int64_t* hi)
+{
+    const int64_t base = n / G, rem = n % G;
+    *lo = g * base + std::min<int64_t>(g, rem);
+    *hi = *lo + base + (g < rem ? 1 : 0);
 }
 
 // Cases one full wave of the sweep grid holds (blocks resident on the 148 SMs x cases per tile).
@@ -1458,6 +1671,59 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
     return BNBP_OK;
 }
 
+// bnbp_run_batch on a group handle (bnbp_create_multi): contiguous case ranges, one host thread per device, every
+// device copies its rows straight into the caller's buffers; then the convergence summary is all-reduced over the
+// group's communicator (one grouped NCCL call from this thread).
+int run_group(bnbp_handle* g, const bnbp_evidence* ev, const bnbp_run_params* prm, void* out_marginals, int32_t* out_sweeps,
+              uint8_t* out_converged)
+{
+    if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
+    if (ev->n_cases > 0 && !ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
+    const int G = (int)g->members.size();
+    std::vector<int32_t> q, belcol, colmap;
+    int rc = query_columns(g, *prm, &q, &belcol, &colmap);
+    if (rc) return rc;
+    const size_t row_bytes = colmap.size() * (prm->out_precision == BNBP_OUT_FP32 ? 4 : 8);
+    std::vector<int> rcs((size_t)G, BNBP_OK);
+    std::vector<std::string> errs((size_t)G);
+    std::vector<int64_t> lo((size_t)G), hi((size_t)G);
+    for (int i = 0; i < G; ++i) shard_range(ev->n_cases, i, G, &lo[(size_t)i], &hi[(size_t)i]);
+    auto work = [&](int i) {
+        bnbp_evidence e = *ev;
+        e.n_cases = hi[(size_t)i] - lo[(size_t)i];
+        e.ev_off = ev->ev_off ? ev->ev_off + lo[(size_t)i] : nullptr;
+        rcs[(size_t)i] = bnbp_run_batch(g->members[(size_t)i], &e, prm, (char*)out_marginals + (size_t)lo[(size_t)i] * row_bytes,
+                                        out_sweeps ? out_sweeps + lo[(size_t)i] : nullptr,
+                                        out_converged ? out_converged + lo[(size_t)i] : nullptr);
+        if (rcs[(size_t)i]) errs[(size_t)i] = bnbp_last_error();      // the error channel is thread-local
+    };
+    std::vector<std::thread> threads;
+    for (int i = 1; i < G; ++i) threads.emplace_back(work, i);
+    work(0);
+    for (std::thread& t : threads) t.join();
+    for (int i = 0; i < G; ++i)
+        if (rcs[(size_t)i]) return fail(rcs[(size_t)i], "device " + std::to_string(g->members[(size_t)i]->device) + ": " + errs[(size_t)i]);
+    // summary: per-case counts are still on each device (whole-shard staging of bnbp_run_batch)
+    NCCL_TRY(ncclGroupStart());
+    for (int i = 0; i < G; ++i) {
+        bnbp_handle* m = g->members[(size_t)i];
+        CU_TRY(cudaSetDevice(m->device));
+        const int64_t n = hi[(size_t)i] - lo[(size_t)i];
+        if ((rc = enqueue_summary(m, (const int32_t*)m->s_out_sweeps.p, (const uint8_t*)m->s_out_conv.p, n, m->stream))) {
+            ncclGroupEnd();
+            return rc;
+        }
+    }
+    NCCL_TRY(ncclGroupEnd());
+    for (int i = 0; i < G; ++i) {
+        CU_TRY(cudaSetDevice(g->members[(size_t)i]->device));
+        CU_TRY(wait_stream(g->members[(size_t)i]->stream));
+    }
+    read_summary(g->members[0], &g->last_summary);
+    g->last_case_sweeps = g->last_summary.case_sweeps;
+    return BNBP_OK;
+}
+
 } // namespace
 
 // =================================================================================================
@@ -1552,7 +1818,17 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
 void bnbp_destroy(bnbp_handle* h)
 {
     if (!h) return;
+    if (!h->members.empty()) {            // a group handle owns its members; it holds no device state itself
+        for (bnbp_handle* m : h->members) bnbp_destroy(m);
+        delete h;
+        return;
+    }
     cudaSetDevice(h->device);
+    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
+    for (cudaEvent_t e : h->ev_comm) cudaEventDestroy(e);
+    if (h->pin_summary) cudaFreeHost(h->pin_summary);
+    for (DevBuf* b : {&h->d_belcol, &h->d_colmap, &h->s_full, &h->d_summary}) b->release();
     if (h->stream) cudaStreamSynchronize(h->stream);
     for (DevBuf* b : {&h->d_nodes, &h->d_e_card, &h->d_e_lam_out, &h->d_c_pi_out, &h->d_cpt, &h->d_pl_init, &h->d_pl,
                       &h->d_msg[0], &h->d_msg[1], &h->d_evbits, &h->d_delta, &h->d_status, &h->d_sweeps, &h->d_misc,
@@ -1583,6 +1859,13 @@ int bnbp_refresh_cpt(bnbp_handle* h, const double* cpt, int64_t n_values)
 {
     if (!h || !cpt) return fail(BNBP_ERR_INVALID, "bnbp_refresh_cpt: NULL argument");
     if (n_values != h->cpt_values) return fail(BNBP_ERR_INVALID, "bnbp_refresh_cpt: CPT size changed (topology edits need a new handle)");
+    if (!h->members.empty()) {
+        for (bnbp_handle* m : h->members) {
+            const int rc = bnbp_refresh_cpt(m, cpt, n_values);
+            if (rc) return rc;
+        }
+        return BNBP_OK;
+    }
     CU_TRY(cudaSetDevice(h->device));
     CU_TRY(cudaDeviceSynchronize());          // runs may have been enqueued on caller streams
     h->cpt_host.assign(cpt, cpt + n_values);
@@ -1686,33 +1969,64 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     h->ev_dense_used = 0;
     h->last_compactions = 0;
     if (ev->n_cases == 0) return BNBP_OK;
+    if (!h->members.empty()) return fail(BNBP_ERR_INVALID, "bnbp_run_batch_device: a group handle takes host buffers (bnbp_run_batch); the device path belongs to one device");
+    if ((rc = set_query(h, *prm))) return rc;
     if ((rc = choose_kernels(h, ev->n_cases, *prm, ev->ev_values != nullptr, h->precision != BNBP_FP32))) return rc;
     if (!h->run_onchip && (rc = ensure_state(h, ev->n_cases))) return rc;
     // a flag left by an earlier (unchecked, asynchronous) run must not fail this one
     CU_TRY(cudaMemsetAsync(reinterpret_cast<int32_t*>(h->d_misc.p) + 1, 0, 4, st));
     CU_TRY(cudaEventRecord(h->ev_total[0], st));
     bool exact = true;
-    const int64_t step_cases = h->run_onchip ? ev->n_cases : h->cap;      // on chip: no resident state arena, one launch
-    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += step_cases) {
+    const size_t row_bytes = (size_t)h->Vout * h->tsize;
+    // gather: out_marginals is [world][n_cases][row]; this rank's kernels write straight into its slot
+    // and every chunk travels to the peers behind the kernels of the next chunk
+    const bool gather = prm->gather != 0;
+    if (gather && (!h->comm || h->comm_world < 1)) return fail(BNBP_ERR_INVALID, "gather needs a communicator (bnbp_comm_init)");
+    const bool exchange = gather && h->comm_world > 1;
+    char* const base = (char*)out_marginals;
+    char* const mine = base + (gather ? (size_t)h->comm_rank * (size_t)ev->n_cases * row_bytes : 0);
+    int64_t step_cases = h->run_onchip ? ev->n_cases : h->cap;            // on chip: no resident state arena, one launch
+    if (exchange) {
+        // 4 chunks of >= 8 MB each when the batch allows it (launch latency of the collective vs overlap)
+        const int64_t min_cases = std::max<int64_t>(32, (int64_t)((8u << 20) / std::max<size_t>(1, row_bytes)));
+        int64_t per = std::max(min_cases, (ev->n_cases + 3) / 4);
+        per = (per + 31) / 32 * 32;
+        step_cases = std::min(step_cases, per);
+    }
+    int n_chunk = 0;
+    for (int64_t c0 = 0; c0 < ev->n_cases; c0 += step_cases, ++n_chunk) {
         const int64_t n = std::min<int64_t>(step_cases, ev->n_cases - c0);
         DevEvidence de{ev->ev_off + c0, 0, ev->ev_node, ev->ev_state, ev->ev_val_off, ev->ev_values, 0};
         int64_t planned = 0;
-        if (h->run_onchip)
-            rc = h->precision == BNBP_FP32
-                     ? run_onchip<float, float>(h, n, de, *prm, (float*)out_marginals + (size_t)c0 * h->V,
-                                                out_sweeps ? out_sweeps + c0 : nullptr, out_converged ? out_converged + c0 : nullptr, st, &planned)
-                     : run_onchip<double, double>(h, n, de, *prm, (double*)out_marginals + (size_t)c0 * h->V,
-                                                  out_sweeps ? out_sweeps + c0 : nullptr, out_converged ? out_converged + c0 : nullptr, st, &planned);
-        else if (h->precision == BNBP_FP32)
-            rc = run_chunk<float, float>(h, n, de, *prm, (float*)out_marginals + (size_t)c0 * h->V,
-                                         out_sweeps ? out_sweeps + c0 : nullptr,
-                                         out_converged ? out_converged + c0 : nullptr, st, &planned);
+        char* const dst = mine + (size_t)c0 * row_bytes;
+        if (h->precision == BNBP_FP32)
+            rc = run_any<float, float>(h, n, de, *prm, (float*)dst, out_sweeps ? out_sweeps + c0 : nullptr,
+                                       out_converged ? out_converged + c0 : nullptr, st, &planned);
         else
-            rc = run_chunk<double, double>(h, n, de, *prm, (double*)out_marginals + (size_t)c0 * h->V,
-                                           out_sweeps ? out_sweeps + c0 : nullptr,
-                                           out_converged ? out_converged + c0 : nullptr, st, &planned);
+            rc = run_any<double, double>(h, n, de, *prm, (double*)dst, out_sweeps ? out_sweeps + c0 : nullptr,
+                                         out_converged ? out_converged + c0 : nullptr, st, &planned);
         if (rc) return rc;
         if (planned < 0) exact = false; else h->last_case_sweeps += planned;
+        if (exchange) {
+            while ((int)h->ev_comm.size() < n_chunk + 2) {
+                cudaEvent_t e;
+                CU_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+                h->ev_comm.push_back(e);
+            }
+            CU_TRY(cudaEventRecord(h->ev_comm[(size_t)n_chunk + 1], st));
+            CU_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_comm[(size_t)n_chunk + 1], 0));
+            NCCL_TRY(ncclGroupStart());
+            for (int r = 0; r < h->comm_world; ++r) {
+                char* const slot = base + ((size_t)r * (size_t)ev->n_cases + (size_t)c0) * row_bytes;
+                NCCL_TRY(ncclBroadcast(slot, slot, (size_t)n * h->Vout, h->tsize == 4 ? ncclFloat : ncclDouble, r, h->comm, h->comm_stream));
+            }
+            NCCL_TRY(ncclGroupEnd());
+        }
+    }
+    if (exchange) {
+        // whatever follows on `st` sees every rank's rows
+        CU_TRY(cudaEventRecord(h->ev_comm[0], h->comm_stream));
+        CU_TRY(cudaStreamWaitEvent(st, h->ev_comm[0], 0));
     }
     if (!exact) h->last_case_sweeps = -1;
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
@@ -1726,17 +2040,24 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
 int bnbp_check_errors(bnbp_handle* h, void* stream)
 {
     if (!h) return fail(BNBP_ERR_INVALID, "bnbp_check_errors: NULL handle");
+    if (!h->members.empty()) return fail(BNBP_ERR_INVALID, "bnbp_check_errors: a group handle has no device path");
     CU_TRY(cudaSetDevice(h->device));
     return check_error_flag(h, stream ? (cudaStream_t)stream : h->stream);
 }
 
-int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm, double* out_marginals,
+int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm, void* out_marginals_v,
                    int32_t* out_sweeps, uint8_t* out_converged)
 {
-    if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_run_batch: NULL argument");
+    if (!h || !ev || !out_marginals_v) return fail(BNBP_ERR_INVALID, "bnbp_run_batch: NULL argument");
     const auto t_entry = std::chrono::steady_clock::now();
     int rc = validate_params(prm);
     if (rc) return rc;
+    if (!h->members.empty()) return run_group(h, ev, prm, out_marginals_v, out_sweeps, out_converged);
+    const bool out_f32 = prm->out_precision == BNBP_OUT_FP32;
+    if (out_f32 && h->precision != BNBP_FP32)
+        return fail(BNBP_ERR_INVALID, "out_precision FP32 needs an fp32 handle (an fp64 handle returns the reference's doubles)");
+    if (prm->out_precision < BNBP_OUT_DEFAULT || prm->out_precision > BNBP_OUT_FP32) return fail(BNBP_ERR_INVALID, "out_precision out of range");
+    char* const out_marginals = (char*)out_marginals_v;
     if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
     if (ev->n_cases > 0 && !ev->ev_off) return fail(BNBP_ERR_INVALID, "ev_off is NULL");
     const int64_t nnz = ev->n_cases ? ev->ev_off[ev->n_cases] : 0;
@@ -1755,7 +2076,9 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->ev_dense_used = 0;
     h->last_compactions = 0;
     if (ev->n_cases == 0) return BNBP_OK;
-    if ((rc = choose_kernels(h, ev->n_cases, *prm, soft, true))) return rc;
+    if ((rc = set_query(h, *prm))) return rc;
+    if ((rc = choose_kernels(h, ev->n_cases, *prm, soft, !out_f32))) return rc;
+    if ((rc = measure_rates(h))) return rc;
     // Chunk pipeline on three streams: evidence of chunk i+1 goes up (h2d_stream) and the marginals of
     // chunk i-1 come down (copy_stream) while init/sweeps/beliefs of chunk i run.  Marginals are 8*V
     // bytes per case, so the copy is of the same order as the kernels.  plan_chunks() cuts the batch
@@ -1763,10 +2086,12 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     // first so the copy engine starts early, then chunks shrinking by 0.7 down to one wave so the
     // exposed tail copy is short.
     const int64_t wave = wave_cases(h, *prm);
-    // copy over a ~55 GB/s host link vs the sweeps at the HBM floor (2*S*sizeof(T) bytes per case-sweep)
+    // copy over the host link vs the sweeps at the HBM floor (2*S*sizeof(T) bytes per case-sweep); both rates
+    // are measured on this handle's device (measure_rates), not assumed
     const double sweeps_est = prm->epsilon > 0.0 ? (double)std::min(prm->max_sweeps > 0 ? prm->max_sweeps : 20, 20) : (double)prm->max_sweeps;
-    double rho = ((double)h->V * 8.0 / 55e9) /
-                 std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / 6.0e12);
+    const size_t out_elem = out_f32 ? 4 : 8;
+    double rho = ((double)h->Vout * (double)out_elem / (h->link_gbs * 1e9)) /
+                 std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / (h->hbm_gbs * 1e9));
     if (h->run_onchip) rho = 2.0;                          // the kernel moves ~1 KB per case: the call is bound by the copy
     std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave, rho);
     if (prm->epsilon > 0.0 && plan.size() > 2 && !getenv("BNBP_CHUNKS") && !h->run_onchip) {
@@ -1785,7 +2110,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     }
     // Output staging: the whole batch when HBM has the room (no chunk ever waits for a slot),
     // else a ring of two chunk-sized slots.
-    const size_t row_bytes = (size_t)h->V * 8;
+    const size_t row_bytes = (size_t)h->Vout * out_elem;
     bool whole = (size_t)ev->n_cases * row_bytes <= h->s_out_all.bytes;
     if (!whole && !getenv("BNBP_STAGING_RING")) {
         size_t free_b = 0, total_b = 0;
@@ -1897,26 +2222,22 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         }
         CU_TRY(cudaEventRecord(e_up, hs));
         CU_TRY(cudaStreamWaitEvent(st, e_up, 0));
-        double* slot = whole ? (double*)h->s_out_all.p + (size_t)c0 * h->V : (double*)h->s_out[idx & 1].p;
+        char* slot = whole ? (char*)h->s_out_all.p + (size_t)c0 * row_bytes : (char*)h->s_out[idx & 1].p;
         if (!whole && idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_chunk[3 * (idx - 2) + 2], 0));   // ring slot is free again
         stamp("enqueue chunk", idx);
         mark(st);
-        if (h->run_onchip)
-            rc = h->precision == BNBP_FP32
-                     ? run_onchip<float, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr)
-                     : run_onchip<double, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
+        if (h->precision == BNBP_FP32 && out_f32)
+            rc = run_any<float, float>(h, n, de, *prm, (float*)slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         else if (h->precision == BNBP_FP32)
-            rc = run_chunk<float, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0,
-                                          (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
+            rc = run_any<float, double>(h, n, de, *prm, (double*)slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         else
-            rc = run_chunk<double, double>(h, n, de, *prm, slot, (int32_t*)h->s_out_sweeps.p + c0,
-                                           (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
+            rc = run_any<double, double>(h, n, de, *prm, (double*)slot, (int32_t*)h->s_out_sweeps.p + c0, (uint8_t*)h->s_out_conv.p + c0, st, nullptr);
         if (rc) return rc;
         mark(st);
         CU_TRY(cudaEventRecord(e_done, st));
         CU_TRY(cudaStreamWaitEvent(cs, e_done, 0));
         mark(cs);
-        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * h->V, slot, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, cs));
+        CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * row_bytes, slot, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, cs));
         mark(cs);
         // per-case counts: into the library's pinned staging (the caller's arrays are usually pageable, and
         // a pageable D2H would block this thread until the chunk is done)
@@ -1967,6 +2288,7 @@ int bnbp_lw_run_batch(bnbp_handle* h, const bnbp_evidence* ev, int64_t n_samples
                       double* out_weight_sum)
 {
     if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_lw_run_batch: NULL argument");
+    if (!h->members.empty()) h = h->members[0];               // likelihood weighting is the cross-check: one device
     if (n_samples < 1) return fail(BNBP_ERR_INVALID, "bnbp_lw_run_batch: n_samples < 1");
     if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
     if (ev->ev_values) return fail(BNBP_ERR_INVALID, "likelihood weighting takes hard evidence (vertex -> state, likelihood_weighting.hpp:15)");
@@ -2135,6 +2457,11 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
 {
     if (!hc || !out) return fail(BNBP_ERR_INVALID, "bnbp_get_stats: NULL argument");
     bnbp_handle* h = const_cast<bnbp_handle*>(hc);
+    if (!h->members.empty()) {            // group: the statistics of the first member, sweeps summed over the group
+        const int rc = bnbp_get_stats(h->members[0], out);
+        if (rc == BNBP_OK) out->last_case_sweeps = h->last_case_sweeps;
+        return rc;
+    }
     memset(out, 0, sizeof *out);
     out->state_values_per_case = (int64_t)h->PL + h->M;
     out->msg_values_per_case = h->M;
@@ -2193,6 +2520,117 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
         }
         cudaGetLastError();
     }
+    return BNBP_OK;
+}
+
+void* bnbp_host_alloc(size_t bytes)
+{
+    void* p = nullptr;
+    if (cudaHostAlloc(&p, std::max<size_t>(bytes, 1), cudaHostAllocPortable) != cudaSuccess) {
+        cudaGetLastError();
+        fail(BNBP_ERR_NOMEM, "bnbp_host_alloc: cudaHostAlloc failed");
+        return nullptr;
+    }
+    return p;
+}
+
+void bnbp_host_free(void* p)
+{
+    if (p) cudaFreeHost(p);
+}
+
+int bnbp_create_multi(const bnbp_flat_network* net, const bnbp_options* opt, const int32_t* devices, int32_t n_devices,
+                      bnbp_handle** out)
+{
+    if (!net || !out) return fail(BNBP_ERR_INVALID, "bnbp_create_multi: NULL argument");
+    *out = nullptr;
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) {
+        cudaGetLastError();
+        return fail(BNBP_ERR_NO_DEVICE, "no CUDA device: libbnbp has no CPU fallback");
+    }
+    std::vector<int> devs;
+    if (n_devices <= 0) n_devices = ndev;
+    for (int i = 0; i < n_devices; ++i) devs.push_back(devices ? devices[i] : i);
+    for (size_t i = 0; i < devs.size(); ++i) {
+        if (devs[i] < 0 || devs[i] >= ndev) return fail(BNBP_ERR_INVALID, "bnbp_create_multi: device ordinal out of range");
+        for (size_t j = 0; j < i; ++j)
+            if (devs[j] == devs[i]) return fail(BNBP_ERR_INVALID, "bnbp_create_multi: a device is listed twice");
+    }
+    struct Destroy { void operator()(bnbp_handle* p) const { bnbp_destroy(p); } };
+    std::unique_ptr<bnbp_handle, Destroy> g(new bnbp_handle());
+    int rc = build_layout(net, opt, g.get());              // host-side layout only: row widths, validation
+    if (rc) return rc;
+    g->device = devs[0];
+    for (int d : devs) {
+        bnbp_options o;
+        memset(&o, 0, sizeof o);
+        if (opt) o = *opt;
+        o.device = d;
+        bnbp_handle* m = nullptr;
+        if ((rc = bnbp_create(net, &o, &m))) return rc;
+        g->members.push_back(m);
+        if ((rc = comm_resources(m))) return rc;
+    }
+    std::vector<ncclComm_t> comms(devs.size(), nullptr);
+    NCCL_TRY(ncclCommInitAll(comms.data(), (int)devs.size(), devs.data()));
+    for (size_t i = 0; i < devs.size(); ++i) {
+        g->members[i]->comm = comms[i];
+        g->members[i]->comm_rank = (int)i;
+        g->members[i]->comm_world = (int)devs.size();
+    }
+    *out = g.release();
+    return BNBP_OK;
+}
+
+int bnbp_get_summary(const bnbp_handle* h, bnbp_summary* out)
+{
+    if (!h || !out) return fail(BNBP_ERR_INVALID, "bnbp_get_summary: NULL argument");
+    *out = h->last_summary;
+    return BNBP_OK;
+}
+
+int bnbp_comm_unique_id(void* id_out)
+{
+    if (!id_out) return fail(BNBP_ERR_INVALID, "bnbp_comm_unique_id: NULL argument");
+    static_assert(sizeof(ncclUniqueId) <= BNBP_COMM_ID_BYTES, "ncclUniqueId larger than BNBP_COMM_ID_BYTES");
+    ncclUniqueId id;
+    NCCL_TRY(ncclGetUniqueId(&id));
+    memset(id_out, 0, BNBP_COMM_ID_BYTES);
+    memcpy(id_out, &id, sizeof id);
+    return BNBP_OK;
+}
+
+int bnbp_comm_init(bnbp_handle* h, int32_t world, int32_t rank, const void* id_in)
+{
+    if (!h || !id_in) return fail(BNBP_ERR_INVALID, "bnbp_comm_init: NULL argument");
+    if (!h->members.empty()) return fail(BNBP_ERR_INVALID, "bnbp_comm_init: a group handle already owns its communicator");
+    if (world < 1 || rank < 0 || rank >= world) return fail(BNBP_ERR_INVALID, "bnbp_comm_init: rank / world out of range");
+    if (h->comm) return fail(BNBP_ERR_INVALID, "bnbp_comm_init: the handle already has a communicator");
+    int rc = comm_resources(h);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(h->device));
+    ncclUniqueId id;
+    memcpy(&id, id_in, sizeof id);
+    NCCL_TRY(ncclCommInitRank(&h->comm, world, id, rank));
+    h->comm_world = world;
+    h->comm_rank = rank;
+    return BNBP_OK;
+}
+
+int bnbp_comm_summary(bnbp_handle* h, const int32_t* d_sweeps, const uint8_t* d_converged, int64_t n_cases, bnbp_summary* out,
+                      void* stream)
+{
+    if (!h || !out || (n_cases > 0 && (!d_sweeps || !d_converged))) return fail(BNBP_ERR_INVALID, "bnbp_comm_summary: NULL argument");
+    if (!h->members.empty()) return fail(BNBP_ERR_INVALID, "bnbp_comm_summary: use bnbp_get_summary on a group handle");
+    int rc = comm_resources(h);
+    if (rc) return rc;
+    CU_TRY(cudaSetDevice(h->device));
+    cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
+    if ((rc = enqueue_summary(h, d_sweeps, d_converged, n_cases, st))) return rc;
+    CU_TRY(wait_stream(st));
+    read_summary(h, out);
+    h->last_summary = *out;
     return BNBP_OK;
 }
 

@@ -102,6 +102,8 @@ template <typename T> struct OnchipArgs {
     const int* ev_state;
     long long n_cases;
     void* out;
+    const int* bel_col;
+    long long out_stride;
     int* out_sweeps;
     unsigned char* out_conv;
     unsigned long long* ticket;

@@ -39,7 +39,9 @@ struct OcArgs {                         // mirrors OnchipArgs in bnbp_jit.h
     const int* ev_node;
     const int* ev_state;
     long long n_cases;
-    OUT* out;                           // [n_cases][BNBP_V] case-major marginals
+    OUT* out;                           // [n_cases][out_stride] case-major marginals
+    const int* bel_col;                 // [N] column of node x's marginal in an output row, -1: not asked for
+    long long out_stride;               // values per output row (sum r_X, or of the queried nodes only)
     int* out_sweeps;                    // [n_cases] or null
     unsigned char* out_conv;            // [n_cases] or null
     unsigned long long* ticket;         // next case to hand out (zero at launch)
@@ -75,8 +77,11 @@ template <class N> __device__ __forceinline__ void oc_init_node(T* pl, T* cur, c
 }
 
 // BEL = normalize(pi .* lambda) (:151-158, matrix.hpp:73-93), same explicit fma / rounded product as K4
-template <class N> __device__ __forceinline__ void oc_belief_node(const T* pl, OUT* row, const bool emit)
+template <class N> __device__ __forceinline__ void oc_belief_node(const T* pl, OUT* row_all, const int* __restrict__ bel_col, bool emit)
 {
+    const int col = bel_col[N::X];
+    emit = emit && col >= 0;
+    OUT* const row = row_all + (col >= 0 ? col : 0) - N::BEL;
     T p[N::R], l[N::R];
 #pragma unroll
     for (int x = 0; x < N::R; ++x) { p[x] = pl[(N::PL + x) * 32]; l[x] = pl[(N::PL + N::R + x) * 32]; }
@@ -207,9 +212,9 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
         const bool done = active && (conv || sw >= a.max_sweeps);
         if (__ballot_sync(0xffffffffu, done)) {
             // the reference returns right after this commit: beliefs of the state as it is now (:151-158)
-            OUT* const row = a.out + (done ? cid : 0) * (long long)BNBP_V;
+            OUT* const row = a.out + (done ? cid : 0) * a.out_stride;
             switch (role) {
-#define BNBP_OC_BEL(NN) oc_belief_node<NN>(c.pl, row, done);
+#define BNBP_OC_BEL(NN) oc_belief_node<NN>(c.pl, row, a.bel_col, done);
 #define BNBP_OC_CASE(R) case R: { BNBP_NODES_##R(BNBP_OC_BEL) } break;
                 BNBP_ROLE_LIST(BNBP_OC_CASE)
 #undef BNBP_OC_CASE

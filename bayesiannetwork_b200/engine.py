@@ -7,7 +7,7 @@ from __future__ import annotations
 
 import ctypes as C
 from dataclasses import dataclass
-from typing import Optional
+from typing import Optional, Sequence
 
 import numpy as np
 
@@ -83,7 +83,7 @@ class BeliefPropagation:
 
     def __init__(self, net: FlatNetwork, precision: str = "fp64", device: int = -1,
                  max_resident_cases: int = 0, specialize: str = "auto", dense_min_cpt: int = 0,
-                 dense_tensor: int = 0, onchip: str = "auto"):
+                 dense_tensor: int = 0, onchip: str = "auto", devices: Optional[Sequence[int]] = None):
         self.net = net
         self.precision = {"fp64": FP64, "fp32": FP32, "f64": FP64, "f32": FP32}[precision]
         lib = _capi.load()
@@ -98,7 +98,15 @@ class BeliefPropagation:
         # hard-evidence cases; "always" / "never")
         opt = _capi.OptionsC(self.precision, device, max_resident_cases, SPECIALIZE[specialize], int(dense_min_cpt),
                              int(dense_tensor), ONCHIP[onchip])
-        _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
+        # devices: several GPUs of this box behind one handle (bnbp_create_multi): a call shards its cases over them
+        # ([] = every visible device); host-buffer calls only
+        self.devices = None if devices is None else [int(d) for d in devices]
+        if self.devices is None:
+            _capi.check(lib.bnbp_create(C.byref(fn), C.byref(opt), C.byref(self._h)))
+        else:
+            arr = np.asarray(self.devices, dtype=np.int32)
+            _capi.check(lib.bnbp_create_multi(C.byref(fn), C.byref(opt), _vp(arr) if arr.size else None, int(arr.size),
+                                              C.byref(self._h)))
 
     def close(self):
         if getattr(self, "_h", None) is not None and self._h:
@@ -115,14 +123,20 @@ class BeliefPropagation:
     def __call__(self, evidence: Optional[EvidenceBatch] = None, epsilon: float = 0.001, *,
                  max_sweeps: int = 0, damping: float = 0.0, check_interval: int = 1,
                  out: Optional[np.ndarray] = None, out_sweeps: Optional[np.ndarray] = None,
-                 out_converged: Optional[np.ndarray] = None) -> BPResult:
+                 out_converged: Optional[np.ndarray] = None, query_nodes: Optional[Sequence[int]] = None,
+                 out_dtype=np.float64) -> BPResult:
+        """``query_nodes``: only these nodes' marginals are returned (columns in the given order);
+        ``out_dtype=np.float32`` (fp32 handles): float marginals, half the device-to-host copy."""
         if evidence is None:
             evidence = EvidenceBatch.empty(1)   # operator()(epsilon) by-pass (:24-28)
         ev = evidence
-        n, V = ev.n_cases, self.net.belief_values
+        q = None if query_nodes is None else np.ascontiguousarray(query_nodes, dtype=np.int32)
+        n = ev.n_cases
+        V = self.net.belief_values if q is None or q.size == 0 else int(self.net.card[q].sum())
+        out_dtype = np.dtype(out_dtype)
         if out is None:
-            out = np.empty((n, V), dtype=np.float64)
-        assert out.dtype == np.float64 and out.size == n * V and out.flags.c_contiguous
+            out = np.empty((n, V), dtype=out_dtype)
+        assert out.dtype == out_dtype and out.size == n * V and out.flags.c_contiguous
         # caller-owned result buffers (all three optional) keep a hot loop free of multi-megabyte
         # allocations: every fresh array is an mmap + page faults + munmap on the calling thread
         sweeps = np.empty(n, dtype=np.int32) if out_sweeps is None else out_sweeps
@@ -133,23 +147,57 @@ class BeliefPropagation:
                               None if ev.is_soft else _vp(ev.ev_state),
                               _vp(ev.ev_val_off) if ev.is_soft else None,
                               _vp(ev.ev_values) if ev.is_soft else None)
-        prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval))
+        prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval),
+                               2 if out_dtype == np.float32 else 0, 0, 0 if q is None else int(q.size), _vp(q))
         _capi.check(self._lib.bnbp_run_batch(self._h, C.byref(evc), C.byref(prm), _vp(out), _vp(sweeps), _vp(conv)))
         return BPResult(out.reshape(n, V), sweeps, conv)
 
     # ---- device-resident buffers (torch tensors on the handle's device) --------------------------
     def run_device(self, n_cases: int, ev_off, ev_node, ev_state, out, *, ev_val_off=None, ev_values=None,
                    epsilon: float = 0.0, max_sweeps: int = 20, damping: float = 0.0, check_interval: int = 1,
-                   out_sweeps=None, out_converged=None, stream: int = 0) -> None:
+                   out_sweeps=None, out_converged=None, stream: int = 0, gather: bool = False,
+                   query_nodes: Optional[Sequence[int]] = None) -> None:
         """All tensor arguments are CUDA tensors (int64 / int32 / float64 offsets and values as in
         ``bnbp_evidence``); ``out`` has the handle's precision, shape [n_cases, sum r_X].
         Work is enqueued on ``stream`` (a raw cudaStream_t, e.g. torch.cuda.current_stream().cuda_stream)."""
         def dp(t):
             return None if t is None else int(t.data_ptr())
         evc = _capi.EvidenceC(int(n_cases), dp(ev_off), dp(ev_node), dp(ev_state), dp(ev_val_off), dp(ev_values))
-        prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval))
+        q = None if query_nodes is None else np.ascontiguousarray(query_nodes, dtype=np.int32)
+        # gather: ``out`` is [world * n_cases, row] on every rank (comm_init first); this rank's rows are written in
+        # place and exchanged over NCCL inside the call
+        prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval), 0,
+                               1 if gather else 0, 0 if q is None else int(q.size), _vp(q))
         _capi.check(self._lib.bnbp_run_batch_device(self._h, C.byref(evc), C.byref(prm), dp(out), dp(out_sweeps),
                                                     dp(out_converged), C.c_void_p(stream) if stream else None))
+
+    # ---- several processes, one GPU each: the communicator lives in the library (SURVEY 8e) --------
+    @staticmethod
+    def comm_unique_id() -> bytes:
+        buf = C.create_string_buffer(_capi.COMM_ID_BYTES)
+        _capi.check(_capi.load().bnbp_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, world: int, rank: int, unique_id: bytes) -> None:
+        """Join the NCCL communicator rank 0 drew with ``comm_unique_id`` (ship the 128 bytes with the
+        launcher's own means, e.g. a ``torch.distributed`` broadcast)."""
+        assert len(unique_id) == _capi.COMM_ID_BYTES
+        buf = C.create_string_buffer(unique_id, _capi.COMM_ID_BYTES)
+        _capi.check(self._lib.bnbp_comm_init(self._h, int(world), int(rank), buf))
+
+    def comm_summary(self, d_sweeps, d_converged, n_cases: int, stream: int = 0) -> dict:
+        """All-reduce (in the library, NCCL) of the per-case counts the last ``run_device`` left in the two CUDA
+        tensors: totals over every rank."""
+        sm = _capi.SummaryC()
+        _capi.check(self._lib.bnbp_comm_summary(self._h, int(d_sweeps.data_ptr()), int(d_converged.data_ptr()), int(n_cases),
+                                                C.byref(sm), C.c_void_p(stream) if stream else None))
+        return {k: int(getattr(sm, k)) for k, _ in sm._fields_}
+
+    def summary(self) -> dict:
+        """Group handle (``devices=...``): totals of the last call over all devices (``bnbp_get_summary``)."""
+        sm = _capi.SummaryC()
+        _capi.check(self._lib.bnbp_get_summary(self._h, C.byref(sm)))
+        return {k: int(getattr(sm, k)) for k, _ in sm._fields_}
 
     def check_errors(self, stream: int = 0) -> None:
         """After synchronising with a ``run_device`` call: raise if it skipped malformed evidence

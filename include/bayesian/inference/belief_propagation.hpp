@@ -28,12 +28,17 @@
 //                                                               (likelihood_weighting.hpp:15,28)
 //   run_flat(bnbp_evidence const&, options)                     zero-copy CSR evidence in, flat
 //                                                               marginals out (10^5-10^6 cases)
+//   options::devices                                            several GPUs of the box behind one object: cases shard
+//                                                               by contiguous ranges, NCCL inside libbnbp
+//   options::query / float_marginals                            run_flat: only the asked-for vertices / floats leave the
+//                                                               device; results land in page-locked memory (pinned_buffer)
 //   loopy_belief_propagation                                    alias (the north-star name)
 #ifndef BNB200_BAYESIAN_INFERENCE_BELIEF_PROPAGATION_HPP
 #define BNB200_BAYESIAN_INFERENCE_BELIEF_PROPAGATION_HPP
 
 #include <cstddef>
 #include <cstdint>
+#include <new>
 #include <stdexcept>
 #include <string>
 #include <unordered_map>
@@ -45,6 +50,47 @@
 
 namespace bn {
 namespace inference {
+
+// Result storage of the flat call: page-locked host memory from libbnbp (bnbp_host_alloc), so the device-to-host
+// copy of the marginals runs at the link rate and overlaps the kernels; a std::vector would be pageable (the copy
+// goes through a driver bounce buffer at a fraction of the rate and blocks the calling thread) and zero-filled
+// first (for 1M alarm37 cases a 0.9 GB memset).  The contents after resize() are unspecified.
+template <class T> class pinned_buffer {
+public:
+    pinned_buffer() : data_(nullptr), size_(0), cap_(0) {}
+    ~pinned_buffer() { bnbp_host_free(data_); }
+    pinned_buffer(pinned_buffer&& o) : data_(o.data_), size_(o.size_), cap_(o.cap_) { o.data_ = nullptr; o.size_ = o.cap_ = 0; }
+    pinned_buffer& operator=(pinned_buffer&& o)
+    {
+        if (this != &o) { bnbp_host_free(data_); data_ = o.data_; size_ = o.size_; cap_ = o.cap_; o.data_ = nullptr; o.size_ = o.cap_ = 0; }
+        return *this;
+    }
+    pinned_buffer(pinned_buffer const&) = delete;
+    pinned_buffer& operator=(pinned_buffer const&) = delete;
+    void resize(std::size_t n)                         // contents are NOT preserved
+    {
+        if (n > cap_) {
+            bnbp_host_free(data_);
+            data_ = static_cast<T*>(bnbp_host_alloc(n * sizeof(T)));
+            if (!data_) { size_ = cap_ = 0; throw std::bad_alloc(); }
+            cap_ = n;
+        }
+        size_ = n;
+    }
+    T* data() { return data_; }
+    T const* data() const { return data_; }
+    std::size_t size() const { return size_; }
+    bool empty() const { return size_ == 0; }
+    T& operator[](std::size_t i) { return data_[i]; }
+    T const& operator[](std::size_t i) const { return data_[i]; }
+    T* begin() { return data_; }
+    T* end() { return data_ + size_; }
+    T const* begin() const { return data_; }
+    T const* end() const { return data_ + size_; }
+private:
+    T* data_;
+    std::size_t size_, cap_;
+};
 
 class belief_propagation {
 public:
@@ -61,15 +107,25 @@ public:
         int precision = BNBP_FP64;   // the reference computes in double
         int device = -1;             // CUDA device ordinal, -1 = current
         int specialize = BNBP_SPEC_AUTO;
+        // several GPUs of this box: a call shards its cases over these ordinals by contiguous ranges,
+        // one host thread and stream set per device; {-1} = every visible device; empty = `device` alone.
+        // Results do not depend on the sharding (bit for bit).
+        std::vector<int> devices;
+        // run_flat only -- what leaves the device (the map-returning overloads always return every vertex in double):
+        std::vector<vertex_type> query;   // non-empty: only these vertices' marginals, in this order
+        bool float_marginals = false;     // fp32 handles: marginals_f32 is filled instead of marginals (half the copy)
     };
 
     struct flat_result {
         std::size_t n_cases = 0;
-        std::size_t values_per_case = 0;           // sum of selectable_num over vertex_list()
-        std::vector<std::size_t> offset;           // offset of vertex i inside one case's row
-        std::vector<double> marginals;             // [n_cases][values_per_case]
-        std::vector<std::int32_t> sweeps;          // sweeps executed per case
-        std::vector<std::uint8_t> converged;       // 1 if the case met delta < epsilon
+        std::size_t values_per_case = 0;           // sum of selectable_num over the vertices of a row
+        std::vector<std::size_t> vertex;           // vertex_list() index of the i-th vertex of a row (all, or the query)
+        std::vector<std::size_t> offset;           // offset of that vertex inside one case's row
+        pinned_buffer<double> marginals;           // [n_cases][values_per_case] (empty if float_marginals)
+        pinned_buffer<float> marginals_f32;        // [n_cases][values_per_case] (only if float_marginals)
+        pinned_buffer<std::int32_t> sweeps;        // sweeps executed per case
+        pinned_buffer<std::uint8_t> converged;     // 1 if the case met delta < epsilon
+        bnbp_summary summary = bnbp_summary();     // totals over all devices (devices.size() > 1: all-reduced over NCCL)
     };
 
     explicit belief_propagation(graph_t const& graph) : graph_(graph) {}
@@ -123,7 +179,7 @@ public:
         ev.ev_state = nullptr;
         ev.ev_val_off = ev_val_off.data();
         ev.ev_values = ev_values.empty() ? &zero_ : ev_values.data();   // non-NULL selects soft evidence
-        return unpack(run_synced(ev, opt));
+        return unpack(run_synced(ev, every_vertex_in_double(opt)));
     }
 
     std::vector<return_type> operator()(std::vector<condition_t> const& cases, options const& opt)
@@ -148,7 +204,7 @@ public:
         ev.ev_state = ev_state.data();
         ev.ev_val_off = nullptr;
         ev.ev_values = nullptr;
-        return unpack(run_synced(ev, opt));
+        return unpack(run_synced(ev, every_vertex_in_double(opt)));
     }
 
     // One hard-evidence case in the condition_t form (vertex -> state)
@@ -189,7 +245,7 @@ private:
     {
         flat_network now = flatten(graph_);
         bool const same_handle = handle_ && opt.precision == precision_ && opt.device == device_ &&
-                                 opt.specialize == specialize_ && now.same_topology(flat_);
+                                 opt.specialize == specialize_ && opt.devices == devices_ && now.same_topology(flat_);
         if (same_handle) {
             if (now.cpt != flat_.cpt) {
                 if (bnbp_refresh_cpt(handle_, now.cpt.data(), static_cast<std::int64_t>(now.cpt.size())) != BNBP_OK)
@@ -211,23 +267,44 @@ private:
         bo.precision = opt.precision;
         bo.device = opt.device;
         bo.specialize = opt.specialize;
-        if (bnbp_create(&net, &bo, &handle_) != BNBP_OK) {
+        int rc;
+        if (opt.devices.empty()) {
+            rc = bnbp_create(&net, &bo, &handle_);
+        } else {
+            std::vector<std::int32_t> list(opt.devices.begin(), opt.devices.end());
+            bool const all = list.size() == 1 && list[0] < 0;
+            rc = bnbp_create_multi(&net, &bo, all ? nullptr : list.data(), all ? 0 : static_cast<std::int32_t>(list.size()), &handle_);
+        }
+        if (rc != BNBP_OK) {
             handle_ = nullptr;
-            throw std::runtime_error(last_error("bnbp_create"));
+            throw std::runtime_error(last_error(opt.devices.empty() ? "bnbp_create" : "bnbp_create_multi"));
         }
         precision_ = opt.precision;
         device_ = opt.device;
         specialize_ = opt.specialize;
+        devices_ = opt.devices;
     }
 
     flat_result run_synced(bnbp_evidence const& ev, options const& opt)
     {
         flat_result out;
         out.n_cases = static_cast<std::size_t>(ev.n_cases);
-        out.offset.resize(flat_.card.size() + 1, 0);
-        for (std::size_t i = 0; i < flat_.card.size(); ++i) out.offset[i + 1] = out.offset[i] + static_cast<std::size_t>(flat_.card[i]);
+        std::vector<std::int32_t> query;
+        for (vertex_type const& v : opt.query) {
+            std::size_t index = 0;
+            if (!graph_.find_index(v, index)) throw std::invalid_argument("belief_propagation: query vertex is not in the graph");
+            query.push_back(static_cast<std::int32_t>(index));
+            out.vertex.push_back(index);
+        }
+        if (query.empty())
+            for (std::size_t i = 0; i < flat_.card.size(); ++i) out.vertex.push_back(i);
+        out.offset.resize(out.vertex.size() + 1, 0);
+        for (std::size_t i = 0; i < out.vertex.size(); ++i)
+            out.offset[i + 1] = out.offset[i] + static_cast<std::size_t>(flat_.card[out.vertex[i]]);
         out.values_per_case = out.offset.back();
-        out.marginals.resize(out.n_cases * out.values_per_case);
+        void* dst;
+        if (opt.float_marginals) { out.marginals_f32.resize(out.n_cases * out.values_per_case); dst = out.marginals_f32.data(); }
+        else { out.marginals.resize(out.n_cases * out.values_per_case); dst = out.marginals.data(); }
         out.sweeps.resize(out.n_cases);
         out.converged.resize(out.n_cases);
         bnbp_run_params prm = bnbp_run_params();
@@ -235,9 +312,21 @@ private:
         prm.max_sweeps = opt.max_sweeps;
         prm.damping = opt.damping;
         prm.check_interval = opt.check_interval;
-        if (bnbp_run_batch(handle_, &ev, &prm, out.marginals.data(), out.sweeps.data(), out.converged.data()) != BNBP_OK)
+        prm.out_precision = opt.float_marginals ? BNBP_OUT_FP32 : BNBP_OUT_DEFAULT;
+        prm.n_query = static_cast<std::int32_t>(query.size());
+        prm.query_nodes = query.empty() ? nullptr : query.data();
+        if (bnbp_run_batch(handle_, &ev, &prm, dst, out.sweeps.data(), out.converged.data()) != BNBP_OK)
             throw std::runtime_error(last_error("bnbp_run_batch"));
+        if (!opt.devices.empty()) bnbp_get_summary(handle_, &out.summary);
         return out;
+    }
+
+    // the map-returning overloads keep the reference's result shape: every vertex, double
+    static options every_vertex_in_double(options opt)
+    {
+        opt.query.clear();
+        opt.float_marginals = false;
+        return opt;
     }
 
     std::vector<return_type> unpack(flat_result const& flat) const
@@ -260,6 +349,7 @@ private:
     flat_network flat_;              // what the device arena currently holds
     bnbp_handle* handle_ = nullptr;
     int precision_ = BNBP_FP64, device_ = -1, specialize_ = BNBP_SPEC_AUTO;
+    std::vector<int> devices_;
     double zero_ = 0.0;
 };
 

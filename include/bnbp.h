@@ -14,6 +14,9 @@
  *   bnbp_run_batch     <- belief_propagation::operator()(precondition, epsilon)
  *                         belief_propagation.hpp:31-159, for n_cases evidence sets at once
  *   bnbp_run_batch_device  same, evidence / marginals already resident in device memory
+ *   bnbp_create_multi / bnbp_comm_* / bnbp_get_summary  (new: SURVEY 8e, cases sharded over the GPUs of a box;
+ *                         the reference runs one evidence set on one core)
+ *   bnbp_host_alloc/free  (new: page-locked result buffers for bnbp_run_batch)
  *   bnbp_check_errors  (evidence validation of the asynchronous device-path call; no reference counterpart)
  *   bnbp_destroy       <- belief_propagation::~belief_propagation()   :21
  *   bnbp_last_error    <- (the reference has no error channel; UB / NaN / endless loop)
@@ -40,7 +43,7 @@
 extern "C" {
 #endif
 
-#define BNBP_VERSION 1
+#define BNBP_VERSION 2
 
 /* status codes */
 enum {
@@ -119,14 +122,37 @@ typedef struct bnbp_evidence {
     const double*  ev_values;   /* [ev_val_off[nnz]] or NULL */
 } bnbp_evidence;
 
+enum { BNBP_OUT_DEFAULT = 0, BNBP_OUT_FP64 = 1, BNBP_OUT_FP32 = 2 };
+
 typedef struct bnbp_run_params {
     double  epsilon;        /* stop a case when its delta < epsilon (reference default 0.001).
                                epsilon <= 0 disables the test (fixed sweep count, no old-message reads) */
     int32_t max_sweeps;     /* cap per case; <= 0 means 1<<30 (the reference has no cap)                */
     double  damping;        /* 0 = reference behaviour; msg = (1-d)*new + d*old otherwise (extension)   */
     int32_t check_interval; /* test convergence every n-th sweep; 1 = reference semantics                */
-    int32_t reserved[7];
+    /* ---- what leaves the device (all 0 / NULL = the reference's "every node, in double") ------------------
+     * The marginals are 8 * sum r_X bytes per case; on a host link of ~50 GB/s that copy, not the kernels,
+     * bounds bnbp_run_batch (alarm37: 840 B per case, 881 MB per 1M cases). */
+    int32_t out_precision;  /* bnbp_run_batch: BNBP_OUT_DEFAULT / BNBP_OUT_FP64 = out_marginals is double*;
+                               BNBP_OUT_FP32 (fp32 handles only) = out_marginals is float*: half the copy.
+                               bnbp_run_batch_device always writes the handle's precision.               */
+    int32_t gather;         /* bnbp_run_batch_device on a handle with a communicator (bnbp_comm_init): out_marginals
+                               is the gathered buffer [world][n_cases][row]; the rank's kernels write straight into
+                               its slot and the slots travel over NCCL chunk by chunk behind the kernels of the next
+                               chunk.  Every rank must pass the same n_cases.                           */
+    int32_t n_query;        /* > 0: only the marginals of query_nodes[0..n_query) are written, in that order: a row
+                               is sum card[query_nodes[i]] values instead of sum r_X (0 = every node)   */
+    const int32_t* query_nodes;   /* host array, read during the call                                   */
+    int32_t reserved[4];
 } bnbp_run_params;
+
+/* Convergence summary of a sharded run (the only collective besides the gather). */
+typedef struct bnbp_summary {
+    int64_t n_cases;        /* over all ranks / devices */
+    int64_t case_sweeps;    /* sum of sweeps executed   */
+    int64_t not_converged;  /* cases whose last tested delta was not < epsilon (all of them when epsilon <= 0) */
+    int64_t max_sweeps;     /* most sweeps any case ran */
+} bnbp_summary;
 
 typedef struct bnbp_stats {
     int64_t state_values_per_case;   /* S = 2*sum r_X + 2*sum_{U->X} r_U                        */
@@ -177,7 +203,40 @@ void bnbp_destroy(bnbp_handle* h);
  *   out_sweeps    [n_cases] sweeps executed per case (may be NULL)
  *   out_converged [n_cases] 1 if the case's last tested delta < epsilon (may be NULL)   */
 int  bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_params* prm,
-                    double* out_marginals, int32_t* out_sweeps, uint8_t* out_converged);
+                    void* out_marginals, int32_t* out_sweeps, uint8_t* out_converged);
+
+/* Page-locked host memory for the buffers of bnbp_run_batch: a pageable destination makes every device-to-host
+ * copy go through a driver bounce buffer (~7 GB/s instead of the link rate) and blocks the calling thread.
+ * The drop-in headers allocate their flat results here.  The memory is not zero-filled. */
+void* bnbp_host_alloc(size_t bytes);
+void  bnbp_host_free(void* p);
+
+/* ---- several GPUs of one box -----------------------------------------------------------------
+ * Evidence cases are independent (belief_propagation.hpp keeps all state per call, :162-172), so a batch shards
+ * by contiguous case ranges with the network replicated; NCCL carries the two exchanges the path has: the
+ * convergence summary (all-reduce) and, on request, the gather of the marginals.  libbnbp owns the communicators.
+ *
+ * One process, several devices: bnbp_create_multi returns a GROUP handle (one member handle, host thread and
+ * stream set per device, an NCCL communicator over them).  bnbp_run_batch on it cuts the caller's CSR evidence
+ * into contiguous ranges (range g = [g*n/G, (g+1)*n/G) up to one case), every device copies its marginals
+ * straight into its rows of the caller's buffers, and the summary is all-reduced in the library
+ * (bnbp_get_summary).  devices == NULL: ordinals 0..n_devices-1; n_devices <= 0: every visible device.
+ * Results are bit-identical to a one-device handle: a case's arithmetic does not depend on where it runs.
+ *
+ * One process per device (torchrun, MPI): every rank creates an ordinary handle, rank 0 draws an id with
+ * bnbp_comm_unique_id and ships it to the others by whatever means the launcher has, all call bnbp_comm_init;
+ * bnbp_run_batch_device with bnbp_run_params.gather then leaves ALL marginals on every rank, and
+ * bnbp_comm_summary all-reduces the per-case counts of the last run. */
+int  bnbp_create_multi(const bnbp_flat_network* net, const bnbp_options* opt, const int32_t* devices, int32_t n_devices,
+                       bnbp_handle** out);
+int  bnbp_get_summary(const bnbp_handle* h, bnbp_summary* out);      /* of the last bnbp_run_batch of a group handle */
+#define BNBP_COMM_ID_BYTES 128
+int  bnbp_comm_unique_id(void* id_out);                              /* BNBP_COMM_ID_BYTES bytes */
+int  bnbp_comm_init(bnbp_handle* h, int32_t world, int32_t rank, const void* id);
+/* d_sweeps / d_converged: the DEVICE arrays the last bnbp_run_batch_device of this rank filled (n_cases entries).
+ * Synchronises `stream`; *out (host) holds the totals over all ranks. */
+int  bnbp_comm_summary(bnbp_handle* h, const int32_t* d_sweeps, const uint8_t* d_converged, int64_t n_cases,
+                       bnbp_summary* out, void* stream);
 
 /* Same, but every pointer inside *ev and every out_* pointer is a DEVICE pointer on the
  * handle's device; out_marginals has the handle's precision (double or float).  The work is

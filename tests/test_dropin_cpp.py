@@ -72,3 +72,11 @@ def test_own_cpp_lw_and_sampler_tests_on_the_gpu_backend():
     """likelihood_weighting.hpp / sampler.hpp drop-ins through the reference's call shapes."""
     out = _run(os.path.join(OWN_BIN, "test_dropin_lw"))
     assert out.count("[  ok  ]") == 2, out
+
+
+@pytest.mark.gpu
+def test_cpp_dropin_over_every_gpu_of_the_box_query_and_float_marginals():
+    """options::devices (bnbp_create_multi: shards + NCCL summary inside libbnbp) equals one device bit for bit;
+    run_flat with query vertices / float marginals (tests/cpp/test_multi_gpu.cpp)."""
+    out = _run(os.path.join(OWN_BIN, "test_multi_gpu"))
+    assert out.count("[  ok  ]") == 2, out
