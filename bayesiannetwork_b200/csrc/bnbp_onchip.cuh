@@ -2,31 +2,37 @@
 //
 // The streaming kernel of bnbp_spec.cuh moves the whole state of a case (S = PL + M values: alarm37 442) through
 // HBM on every sweep and sits on the HBM roofline; the arithmetic units idle (fp64 pipe 18 %, issue 16 %,
-// profiles/r01c).  A case's state is small (alarm37 fp64: PL + 2M = 674 values = 5.4 KB with both message
-// buffers), so here it never leaves the SM between the first and the last sweep of the case
-// (belief_propagation.hpp:31-159 for one case = init :33-73, `sweeps` iterations of :75-148, beliefs :151-158,
-// all inside ONE kernel):
+// profiles/r01c).  A case's state is small (alarm37 fp64: 442 values = 3.5 KB), so here it never leaves the SM
+// between the first and the last sweep of the case (belief_propagation.hpp:31-159 for one case = init :33-73,
+// `sweeps` iterations of :75-148, beliefs :151-158, all inside ONE kernel):
 //
 //   * a GROUP of 32 cases lives in the shared memory of one CTA, slot-major `state[slot][32]` (a warp-wide
-//     access to one slot is 32 consecutive values: conflict-free); pi/lambda in place, two message buffers
-//     (the Jacobi commit :135-143 is the buffer swap);
+//     access to one slot is 32 consecutive values: conflict-free): pi/lambda and ONE message buffer;
 //   * the group is walked by BNBP_ROLES warps: lane = case, warp = a fixed subset of the nodes (longest-
 //     processing-time partition of the per-node cost, made by the network compiler).  Every warp runs the
 //     fully unrolled straight-line code of ITS nodes (the node arithmetic of bnbp_spec.cuh, CPT entries as
 //     constant-bank operands), so the 4 schedulers of the SM work on different nodes of the same 32 cases;
-//     all four updates read time-t state only (:75-101), so ONE __syncthreads per sweep orders them;
+//   * a sweep has two phases.  A: every warp reads the inbox of its nodes (the time-t messages addressed to them)
+//     into registers; barrier; B: it computes its nodes and overwrites the inboxes of their neighbours with the
+//     time-(t+1) messages; barrier.  All four updates read time-t state only (:75-101), so this IS the Jacobi
+//     commit (:135-143) without a second message buffer -- which is what lets TWO groups share an SM in fp64
+//     (113 KB each): the warps of the two groups that own the same nodes run the same instructions, and the kernel
+//     is bound by instruction fetch (r02a: one warp per scheduler walking 29 KB of straight-line code of its own
+//     stalls 6 cycles per issue on `no_instruction`, L1.5 I-cache = 32 KB);
+//   * pi_X / lambda_X are kept unnormalised and the reciprocals skip the slow path (bnbp_spec.cuh: emit_node,
+//     rcp_norm): 40 % fewer instructions per sweep;
 //   * the convergence test (:105-131,:147) is free: each warp reduces |new - old| over the messages it emits in
-//     registers (the old value is one shared-memory load away), the per-case maximum over the warps goes
+//     registers (the old value is the word it is about to overwrite), the per-case maximum over the warps goes
 //     through 4 x 32 shared-memory words at the sweep barrier;
-//   * a lane whose case has stopped (delta < epsilon, or the sweep cap) writes its marginals, takes the next
-//     case from a global ticket counter, loads its evidence and starts over at sweep 0 while the other lanes
-//     carry on: in epsilon mode no lane waits for the slowest case of its group (the kernel is persistent:
-//     grid = resident CTAs, not cases / 32);
+//   * a lane whose case has stopped (delta < epsilon, or the sweep cap) is frozen; once 8 lanes of the group wait
+//     (or nothing else runs) they write their marginals, take the next cases from a global ticket counter, load
+//     their evidence and start over at sweep 0 while the other lanes carry on: in epsilon mode no lane waits for
+//     the slowest case of its group (the kernel is persistent: grid = resident CTAs, not cases / 32);
 //   * HBM sees the evidence of a case once (CSR entries) and its marginals once: ~0.9 KB per case instead of
 //     2 * S * sizeof(T) * sweeps = 141 KB for 20 fp64 sweeps of alarm37.
 //
 // Generator macros in addition to those of bnbp_spec.cuh: BNBP_ROLES, and per role r
-//   BNBP_WALK_r   the software-pipelined BNBP_DECL / BNBP_LOAD / BNBP_COMP sequence of the role's nodes
+//   BNBP_WALK_r   BNBP_DECL(all) BNBP_LOADM(all) BNBP_SYNC BNBP_COMP(all): the two phases of the role's nodes
 //   BNBP_NODES_r(OP)   OP(Ni) for every node of the role
 // plus the constant tables bnbp_owner[N] (role that owns a node), bnbp_ploff[N], bnbp_cardn[N].
 #if BNBP_VARIANT >= 8
@@ -54,8 +60,10 @@ struct OcArgs {                         // mirrors OnchipArgs in bnbp_jit.h
 
 constexpr int ROLES = BNBP_ROLES;
 constexpr int OC_THREADS = 32 * ROLES;
-// shared memory: [PL][32] pi/lambda | [M][32] messages (buffer 0) | [M][32] (buffer 1) | partial deltas | tickets
-constexpr long long OC_STATE = ((long long)BNBP_PL + 2ll * BNBP_M) * 32;
+constexpr int RETIRE_BATCH = 8;         // frozen lanes a group collects before it writes marginals and refills
+// shared memory: [PL][32] pi/lambda | [M][32] messages | partial deltas [2][ROLES][32] | tickets [32]
+
+__device__ __forceinline__ void oc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(OC_THREADS) : "memory"); }
 
 // time-0 state of one node (:33-65): pi = lambda = 1, a root's pi = its raw prior row (:58-64); every message the
 // node is about to READ (its inbox in the current buffer) = 1 (:44-55)
@@ -88,9 +96,10 @@ template <class N> __device__ __forceinline__ void oc_belief_node(const T* pl, O
     T s = T(0);
 #pragma unroll
     for (int x = 0; x < N::R; ++x) s = fma(p[x], l[x], s);
+    const T inv = rcp_norm(s);
     if (emit) {
 #pragma unroll
-        for (int x = 0; x < N::R; ++x) row[N::BEL + x] = (OUT)(mul_rn(p[x], l[x]) / s);
+        for (int x = 0; x < N::R; ++x) row[N::BEL + x] = (OUT)(mul_rn(p[x], l[x]) * inv);
     }
 }
 
@@ -102,25 +111,23 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
     using namespace bnbp_spec;
     extern __shared__ __align__(16) unsigned char oc_smem[];
     T* const s_pl = reinterpret_cast<T*>(oc_smem);
-    T* const s_msg0 = s_pl + (long long)BNBP_PL * 32;
-    T* const s_msg1 = s_msg0 + (long long)BNBP_M * 32;
-    T* const s_delta = s_msg1 + (long long)BNBP_M * 32;                       // [2][ROLES][32]
+    T* const s_msg = s_pl + (long long)BNBP_PL * 32;
+    T* const s_delta = s_msg + (long long)BNBP_M * 32;                        // [2][ROLES][32]
     long long* const s_case = reinterpret_cast<long long*>(s_delta + 2 * ROLES * 32);   // [32]
 
     const int lane = threadIdx.x & 31;
     const int role = threadIdx.x >> 5;
     const bool eps_mode = a.eps > T(0);
 
-    Ctx c;
-    c.damping = a.damping;
-    c.evst = nullptr;
-    c.tile = nullptr;
-    c.pl = s_pl + lane;
+    unsigned evl[BNBP_W];               // observed-node bits of this lane's case (kept apart from Ctx: the evidence loop
+                                        // indexes it dynamically, and a Ctx on the stack would lose the address space of
+                                        // its shared-memory pointers: generic LD / ST instead of LDS / STS)
     long long cid = -1;                 // the case this lane works on (-1: needs one, -2: none left)
     int sw = 0;                         // sweeps its case has run
-    int parity = 0;                     // message buffer the next sweep reads
+    bool fin = false, fconv = false;    // the case has stopped (frozen until the group retires a batch) / it met delta < eps
+    int flip = 0;                       // which half of s_delta this sweep writes
 #pragma unroll
-    for (int w = 0; w < BNBP_W; ++w) c.evw[w][0] = 0u;
+    for (int w = 0; w < BNBP_W; ++w) evl[w] = 0u;
 
     for (;;) {
         // ---- hand out cases to the lanes that have none (every warp takes the same decisions) --------------
@@ -133,17 +140,16 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
                 const long long mine = (long long)base + __popc(need_mask & ((1u << lane) - 1u));
                 if (cid == -1) s_case[lane] = mine < a.n_cases ? mine : -2;
             }
-            __syncthreads();
+            oc_barrier();
             const bool need = cid == -1;
-            if (need) { cid = s_case[lane]; sw = 0; }
+            if (need) { cid = s_case[lane]; sw = 0; fin = false; fconv = false; }
             const bool fresh = need && cid >= 0;
-            T* const cur0 = (parity ? s_msg1 : s_msg0) + lane;
             if (fresh) {
 #pragma unroll
-                for (int w = 0; w < BNBP_W; ++w) c.evw[w][0] = 0u;
+                for (int w = 0; w < BNBP_W; ++w) evl[w] = 0u;
             }
             switch (role) {
-#define BNBP_OC_INIT(NN) oc_init_node<NN>(c.pl, cur0, fresh);
+#define BNBP_OC_INIT(NN) oc_init_node<NN>(s_pl + lane, s_msg + lane, fresh);
 #define BNBP_OC_CASE(R) case R: { BNBP_NODES_##R(BNBP_OC_INIT) } break;
                 BNBP_ROLE_LIST(BNBP_OC_CASE)
 #undef BNBP_OC_CASE
@@ -159,11 +165,9 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
                     const int st = a.ev_state[e];
                     const int r = bnbp_cardn[node];
                     if (st < 0 || st >= r) { *a.error_flag = 3; continue; }
-#pragma unroll
-                    for (int w = 0; w < BNBP_W; ++w)
-                        if ((node >> 5) == w) c.evw[w][0] |= 1u << (node & 31);
+                    evl[node >> 5] |= 1u << (node & 31);
                     if (bnbp_owner[node] == role) {
-                        T* const row = c.pl + (long long)bnbp_ploff[node] * 32;
+                        T* const row = s_pl + lane + (long long)bnbp_ploff[node] * 32;
                         for (int x = 0; x < r; ++x) {
                             const T hot = x == st ? T(1) : T(0);
                             row[x * 32] = hot;
@@ -173,48 +177,61 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
                 }
             }
             if (__ballot_sync(0xffffffffu, cid >= 0) == 0u) break;      // no case left in this group
+            // (the inbox words written above are read by this warp only; no barrier needed before phase A)
         }
 
         // ---- one sweep (:75-101) for the 32 cases of the group, this warp's nodes --------------------------
-        c.cur = (parity ? s_msg1 : s_msg0) + lane;
-        c.nxt = (parity ? s_msg0 : s_msg1) + lane;
-        c.act[0] = cid >= 0;
+        Ctx c;
+        c.damping = a.damping;
+        c.evst = nullptr;
+        c.tile = nullptr;
+        c.pl = s_pl + lane;
+        c.cur = s_msg + lane;           // one message buffer: inboxes are read before the sweep barrier, written after it
+        c.nxt = s_msg + lane;
+#pragma unroll
+        for (int w = 0; w < BNBP_W; ++w) c.evw[w][0] = evl[w];
+        c.act[0] = cid >= 0 && !fin;
         c.dmax[0] = Floor<T>::v();
         switch (role) {
 #define BNBP_DECL(NN) In<NN> in_##NN;
-#define BNBP_LOAD(NN) load_node<NN>(c, in_##NN);
-#define BNBP_COMP(NN) compute_node<NN>(c, in_##NN);
+#define BNBP_LOADM(NN) load_msgs<NN>(c, in_##NN);
+#define BNBP_SYNC oc_barrier();
+#define BNBP_COMP(NN) load_pl<NN>(c, in_##NN); compute_node<NN>(c, in_##NN);
 #define BNBP_OC_CASE(R) case R: { BNBP_WALK_##R } break;
             BNBP_ROLE_LIST(BNBP_OC_CASE)
 #undef BNBP_OC_CASE
 #undef BNBP_DECL
-#undef BNBP_LOAD
+#undef BNBP_LOADM
+#undef BNBP_SYNC
 #undef BNBP_COMP
         }
-        T* const dpart = s_delta + (long long)(parity * ROLES) * 32;
+        T* const dpart = s_delta + (long long)(flip * ROLES) * 32;
         if constexpr (CHECK) dpart[role * 32 + lane] = c.dmax[0];
-        __syncthreads();                                   // commit (:135-143): every time-(t+1) value is written
-        parity ^= 1;
-        const bool active = cid >= 0;
+        oc_barrier();                                      // commit (:135-143): every time-(t+1) value is written
+        flip ^= 1;
+        const bool active = c.act[0];
         if (active) ++sw;
 
         // ---- stopping rule (:105-131,:147) per case -----------------------------------------------------------
-        bool conv = false;
         if constexpr (CHECK) {
             if (eps_mode) {
                 const bool tested = (sw % a.interval) == 0 || sw >= a.max_sweeps;
                 T d = Floor<T>::v();
 #pragma unroll
                 for (int r = 0; r < ROLES; ++r) d = fmax(d, dpart[r * 32 + lane]);
-                conv = active && tested && d < a.eps;
+                if (active && tested && d < a.eps) { fin = true; fconv = true; }
             }
         }
-        const bool done = active && (conv || sw >= a.max_sweeps);
-        if (__ballot_sync(0xffffffffu, done)) {
-            // the reference returns right after this commit: beliefs of the state as it is now (:151-158)
+        if (active && sw >= a.max_sweeps) fin = true;
+        // a stopped case is frozen (the reference returns right after this commit, :147-158); its marginals are written
+        // when the group has a batch of them, or nothing else to do
+        const unsigned fin_mask = __ballot_sync(0xffffffffu, fin && cid >= 0);
+        const unsigned run_mask = __ballot_sync(0xffffffffu, cid >= 0 && !fin);
+        if (fin_mask && (__popc(fin_mask) >= RETIRE_BATCH || run_mask == 0u)) {
+            const bool done = fin && cid >= 0;
             OUT* const row = a.out + (done ? cid : 0) * a.out_stride;
             switch (role) {
-#define BNBP_OC_BEL(NN) oc_belief_node<NN>(c.pl, row, a.bel_col, done);
+#define BNBP_OC_BEL(NN) oc_belief_node<NN>(s_pl + lane, row, a.bel_col, done);
 #define BNBP_OC_CASE(R) case R: { BNBP_NODES_##R(BNBP_OC_BEL) } break;
                 BNBP_ROLE_LIST(BNBP_OC_CASE)
 #undef BNBP_OC_CASE
@@ -222,9 +239,9 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
             }
             if (role == 0 && done) {
                 if (a.out_sweeps) a.out_sweeps[cid] = sw;
-                if (a.out_conv) a.out_conv[cid] = conv ? 1 : 0;
+                if (a.out_conv) a.out_conv[cid] = fconv ? 1 : 0;
             }
-            if (done) cid = -1;
+            if (done) { cid = -1; fin = false; }
         }
     }
 }

@@ -47,6 +47,31 @@ def measured_peaks():
     return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def kernel_source_hash() -> str:
+    """Hash of the CUDA sources of the sweep kernels: a traffic figure measured under ncu is only quoted for the
+    kernel text it was measured on (profiles/update_traffic.py writes it, bench.py refuses a stale one)."""
+    import hashlib
+    h = hashlib.sha1()
+    for name in ("bnbp_spec.cuh", "bnbp_onchip.cuh", "bnbp_sweep.cuh", "bnbp_kernels.cuh"):
+        with open(os.path.join(ROOT, "bayesiannetwork_b200", "csrc", name), "rb") as f:
+            h.update(f.read())
+    return h.hexdigest()[:16]
+
+
+def measured_traffic(key: str):
+    """(bytes per sweep | None, note) from profiles/traffic.json."""
+    try:
+        tj = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))
+    except Exception:
+        return None, "profiles/traffic.json missing"
+    ent = tj.get("entries", {}).get(key)
+    if not ent:
+        return None, f"no ncu capture recorded for {key}"
+    if ent.get("source_hash") != kernel_source_hash():
+        return None, f"stale: {ent.get('from')} was captured on other kernel sources (hash {ent.get('source_hash')})"
+    return float(ent["dram_bytes_per_sweep"]), f"ncu --set full, dram__bytes_read.sum + dram__bytes_write.sum per sweep, {ent.get('from')}"
+
+
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
     Q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
@@ -415,7 +440,11 @@ def main():
                     help="CPT entries from which a node takes the dense contraction path (0 = library default, -1 = never)")
     ap.add_argument("--dense-tensor", type=int, default=0,
                     help="fp32: dense products on the tensor cores (0 = library default, 1 = every product, -1 = never)")
-    ap.add_argument("--gather", action="store_true", help="NCCL all-gather of marginals inside each step")
+    ap.add_argument("--no-gather", action="store_true",
+                    help="N > 1: skip the gather of the marginals (default: every rank ends a step with ALL marginals, "
+                         "exchanged over NCCL inside bnbp_run_batch_device)")
+    ap.add_argument("--onchip", default="auto", choices=["auto", "always", "never"],
+                    help="the on-chip multi-sweep kernel (state in shared memory for all sweeps)")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu", action="store_true")
     ap.add_argument("--no-configs", action="store_true",
@@ -435,7 +464,6 @@ def main():
     import torch
     import torch.distributed as dist
     from bayesiannetwork_b200.engine import BeliefPropagation
-    from bayesiannetwork_b200 import dist as bdist
 
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device -- the bnbp path has no CPU fallback")
@@ -453,31 +481,38 @@ def main():
     tdtype = torch.float64 if args.precision == "fp64" else torch.float32
     tsize = 8 if args.precision == "fp64" else 4
     bp = BeliefPropagation(net, args.precision, device=local_rank, specialize=args.specialize,
-                           dense_min_cpt=args.dense_min, dense_tensor=args.dense_tensor)
+                           dense_min_cpt=args.dense_min, dense_tensor=args.dense_tensor, onchip=args.onchip)
+    gather = world > 1 and not args.no_gather
+    if world > 1:
+        # the communicator lives in libbnbp: rank 0 draws the id, torch.distributed only ships its 128 bytes
+        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        if rank == 0:
+            uid.copy_(torch.frombuffer(bytearray(BeliefPropagation.comm_unique_id()), dtype=torch.uint8))
+        dist.broadcast(uid, 0)
+        bp.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
     d_node = torch.from_numpy(ev.ev_node).to(dev)
     d_state = torch.from_numpy(ev.ev_state).to(dev)
-    d_out = torch.empty((n, V), dtype=tdtype, device=dev)
+    # with the gather every rank holds [world * n, V]; its own kernels write rows [rank * n, (rank + 1) * n) in place
+    gathered = torch.empty((world * n, V), dtype=tdtype, device=dev) if gather else None
+    d_out = gathered[rank * n:(rank + 1) * n] if gather else torch.empty((n, V), dtype=tdtype, device=dev)
     d_sw = torch.empty(n, dtype=torch.int32, device=dev)
     d_cv = torch.empty(n, dtype=torch.uint8, device=dev)
-    summary = torch.zeros(2, dtype=torch.int64, device=dev)
-    gathered = torch.empty((world * n, V), dtype=tdtype, device=dev) if (args.gather and world > 1) else None
+    summaries = []
     # a dedicated (non-default) stream: the library enqueues on it and the CUDA events below see it
     tstream = torch.cuda.Stream(device=dev)
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 
     def step():
-        bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=args.epsilon, max_sweeps=sweeps,
-                      out_sweeps=d_sw, out_converged=d_cv, stream=stream)
+        # the only collectives of the path, both inside libbnbp (NCCL): the gather of the marginals, chunk by chunk
+        # behind the kernels of the next chunk, and the all-reduce of the convergence summary
+        bp.run_device(n, d_off, d_node, d_state, gathered if gather else d_out, epsilon=args.epsilon, max_sweeps=sweeps,
+                      out_sweeps=d_sw, out_converged=d_cv, stream=stream, gather=gather)
         if world > 1:
-            # the only collectives of the path: global sweep count + all-converged flag (and,
-            # on request, the marginals)
-            bdist.reduce_summary(d_sw, d_cv, summary)
-            if gathered is not None:
-                dist.all_gather_into_tensor(gathered, d_out)
+            summaries.append(bp.comm_summary(d_sw, d_cv, n, stream=stream))
 
     def barrier():
         if world > 1:
@@ -515,6 +550,28 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms, sweep_ms_per_launch, dense_ms_per_sweep = float(t[0]), float(t[1]), float(t[2])
     clocks = sampler.stop() if sampler else None
+    multi_gpu = None
+    if world > 1:
+        # the N-rank sharded run equals a 1-rank run: rank 0 recomputes, on its own GPU, the first cases of EVERY rank's
+        # shard (evidence is a function of the case index) and compares them with the rows the gather delivered
+        multi_gpu = {"summary_all_reduce": summaries[-1] if summaries else None, "collectives": "ncclAllReduce (summary) + grouped ncclBroadcast "
+                     "per rank and chunk (gather), issued by libbnbp on its own stream", "gathered_bytes_per_step": int(world * n * V * tsize) if gather else 0}
+        if gather and rank == 0 and not args.network:
+            k = min(256, n)
+            evkw = synth.WORKLOADS[args.workload][2]
+            worst, same = 0.0, True
+            chk = torch.empty((k, V), dtype=tdtype, device=dev)
+            for r in range(world):
+                e_r = synth.make_evidence(net, k, case_offset=r * n, **evkw)
+                bp.run_device(k, torch.from_numpy(e_r.ev_off).to(dev), torch.from_numpy(e_r.ev_node).to(dev),
+                              torch.from_numpy(e_r.ev_state).to(dev), chk, epsilon=args.epsilon, max_sweeps=sweeps, stream=stream)
+                torch.cuda.synchronize()
+                got = gathered[r * n:r * n + k]
+                same = same and bool(torch.equal(got, chk))
+                worst = max(worst, float((got - chk).abs().max()))
+            multi_gpu["n_rank_equals_1_rank"] = {"cases_per_rank_checked": k, "bitwise_equal": same, "max_abs_diff": worst}
+            if not same:
+                raise SystemExit(f"bench.py: gathered marginals differ from a 1-rank run (max abs diff {worst:g})")
     eps_info = None
     if args.epsilon > 0:
         # time-to-solution mode: count the sweeps each case actually executed (same every step)
@@ -540,17 +597,11 @@ def main():
     if eps_info:                                     # frozen cases move no data: average over the launches
         bytes_per_launch = 2.0 * S * tsize * eps_info["case_sweeps_per_step"] / world / max(1, st["last_sweep_launches"])
     achieved = bytes_per_launch / (sweep_ms_per_launch * 1e-3) / 1e9
-    traffic = None
-    tpath = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(tpath):
-        try:
-            tj = json.load(open(tpath))
-            key = f"{args.workload}:{args.precision}:{n}"
-            traffic = tj.get(key)
-        except Exception:
-            traffic = None
+    onchip = bool(st.get("last_onchip", 0))
+    kernel = "bnbp_onchip_run" if onchip else ("bnbp_spec_sweep" if st["last_specialised"] else "sweep_kernel")
+    traffic, traffic_note = measured_traffic(f"{args.workload}:{args.precision}:{kernel}")
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                "traffic": traffic, "kernel": "bnbp_spec_sweep" if st["last_specialised"] else "sweep_kernel",
+                "traffic": traffic, "traffic_note": traffic_note, "kernel": kernel,
                 "peak_source": peak_src,
                 "algorithmic_bytes_per_case_sweep": 2 * S * tsize, "ms_per_launch": sweep_ms_per_launch,
                 "launch_unit": "one sweep over the resident batch (achieved = 2*S*sizeof(T)*cases / ms_per_launch; traffic is "
@@ -558,6 +609,23 @@ def main():
                                "looping launch (short grids / whole waves): ms_per_launch is then that launch's time / its sweeps",
                 "sweeps_per_step": int(st["last_sweep_launches"]), "kernel_launches_per_step": launches_per_step,
                 "fused_first_last": bool(st.get("last_fused", 0)), "compactions_per_step": int(st.get("last_compactions", 0))}
+    if onchip:
+        # the state of a case stays in shared memory for all its sweeps: the ALGORITHMIC bytes (2*S*sizeof(T) per
+        # case-sweep) never cross HBM, so `achieved` may exceed the HBM peak (SURVEY 8d / BASELINE.md 4 say to
+        # report it as such); what binds the kernel is instruction issue / the fp64 pipe
+        F = walk_flops(net)
+        fpk = FMA_PEAK_TFLOPS[args.precision]
+        rate = value / world
+        roofline.update({
+            "state_on_chip": True,
+            "note": "on-chip kernel: frac is against the STREAMING roofline (what a kernel that moves the state through HBM every "
+                    "sweep can reach at most); > 1 means faster than any streaming kernel. One launch runs init, every sweep and the "
+                    "beliefs of the whole batch; ms_per_launch = launch time / sweeps",
+            "hbm_bytes_moved_per_case": int(ev.nbytes() / max(1, n) + V * tsize + 5),
+            "fma": {"bound": "fma", "achieved": rate * F / 1e12, "peak": fpk, "unit": "TFLOP/s", "frac": rate * F / 1e12 / fpk,
+                    "flops_per_case_sweep": F, "note": "algorithmic flops F = sum (2k+2) r Q (SURVEY 8d) against the nominal CUDA-core FMA peak"},
+            "groups_per_sm": int(st.get("onchip_blocks_per_sm", 0)), "warps_per_group": int(st.get("onchip_roles", 0)),
+            "shared_memory_per_group": int(st.get("onchip_smem_bytes", 0)), "role_imbalance": st.get("onchip_role_imbalance")})
 
     dense = None
     if st["dense_nodes"] and dense_ms_per_sweep > 0 and not eps_info:
@@ -662,6 +730,64 @@ def main():
                "pipeline": "three streams: evidence H2D of chunk i+1 and marginal D2H of chunk i-1 overlap the kernels "
                            "of chunk i; chunks cut in whole waves of the sweep grid (BNBP_TRACE=1 prints the plan)"}
 
+    # ---- e2e variants: the host link bounds the call, so what matters is what has to cross it ---------------
+    if e2e is not None and not eps_info:
+        def timed_calls(handle, calls, **kw):
+            for _ in range(2):
+                handle(ev_pinned, args.epsilon, max_sweeps=sweeps, out_sweeps=sw_np, out_converged=cv_np, **kw)
+            barrier()
+            gc.disable()
+            t0 = time.perf_counter()
+            for _ in range(calls):
+                handle(ev_pinned, args.epsilon, max_sweeps=sweeps, out_sweeps=sw_np, out_converged=cv_np, **kw)
+            dtv = time.perf_counter() - t0
+            gc.enable()
+            if world > 1:
+                t = torch.tensor([dtv], dtype=torch.float64, device=dev)
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+                dtv = float(t[0])
+            return dtv
+        variants = []
+        calls = 5
+        q = np.unique(np.linspace(0, net.n_nodes - 1, min(8, net.n_nodes)).astype(np.int32))
+        Vq = int(net.card[q].sum())
+        p_q = torch.empty((n, Vq), dtype=torch.float64, pin_memory=True)
+        dtv = timed_calls(bp, calls, out=p_q.numpy(), query_nodes=q)
+        variants.append({"what": f"{len(q)} query nodes of {net.n_nodes} (bnbp_run_params.query_nodes): only their marginals leave the device",
+                         "dtype": "f64" if args.precision == "fp64" else "f32", "value": world * n * sweeps * calls / dtv, "unit": UNIT,
+                         "ms_per_step": 1e3 * dtv / calls, "d2h_bytes_per_step": int(n * Vq * 8 + n * 5)})
+        del p_q
+        bp32 = bp if args.precision == "fp32" else BeliefPropagation(net, "fp32", device=local_rank, specialize=args.specialize, onchip=args.onchip)
+        p_f = torch.empty((n, V), dtype=torch.float32, pin_memory=True)
+        dtv = timed_calls(bp32, calls, out=p_f.numpy(), out_dtype=np.float32)
+        variants.append({"what": "fp32 handle, float marginals (bnbp_run_params.out_precision = BNBP_OUT_FP32): half the device-to-host copy",
+                         "dtype": "f32", "value": world * n * sweeps * calls / dtv, "unit": UNIT, "ms_per_step": 1e3 * dtv / calls,
+                         "d2h_bytes_per_step": int(n * V * 4 + n * 5)})
+        del p_f
+        if bp32 is not bp:
+            bp32.close()
+        e2e["variants"] = variants
+
+    # ---- the same boundary from C++: bn::inference::belief_propagation::run_flat (tests/cpp/e2e_timing.cpp) -----
+    if e2e is not None and not eps_info and rank == 0 and world == 1:
+        exe = os.path.join(ROOT, "tests", "cpp", "_build", "e2e_timing")
+        if os.path.exists(exe):
+            import tempfile
+            with tempfile.NamedTemporaryFile(suffix=".bnbp", delete=False) as f:
+                np.array([net.n_nodes, net.n_edges, net.cpt.size, n, ev.nnz, sweeps], dtype=np.int64).tofile(f)
+                for arr in (net.card, net.parent_off, net.parents, net.cpt_off, net.cpt, ev.ev_off, ev.ev_node, ev.ev_state):
+                    arr.tofile(f)
+                path = f.name
+            try:
+                r = subprocess.run([exe, path, "5", "2", args.precision, "0", "0"], capture_output=True, text=True, timeout=600)
+                e2e["e2e_cxx"] = json.loads(r.stdout.strip().splitlines()[-1]) if r.returncode == 0 else {"error": r.stderr[-500:]}
+            except Exception as ex:      # the C++ leg is a report, not the measurement: never fail the bench line on it
+                e2e["e2e_cxx"] = {"error": str(ex)}
+            finally:
+                os.unlink(path)
+        else:
+            e2e["e2e_cxx"] = {"error": "tests/cpp/_build/e2e_timing not built"}
+
     # ---- CPU baseline beside it (rank 0, N == 1 only): the oracle port on all host cores ---------------
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu and not eps_info:
@@ -680,7 +806,8 @@ def main():
     main_workload = args.workload == "alarm37" and not args.network and not args.cases and not eps_info
     if main_workload and not args.no_configs:
         bp.close()
-        del d_out, d_off, d_node, d_state, d_sw, d_cv, gathered
+        del d_out, d_off, d_node, d_state, d_sw, d_cv
+        gathered = None
         if e2e is not None:
             del p_out, p_off, p_node, p_state, p_sw, p_cv, out_np, sw_np, cv_np, ev_pinned
         gc.collect()
@@ -706,11 +833,14 @@ def main():
                        "state_values_per_case": S,
                        "schedule": ("synchronous, stop per case at delta < epsilon (reference rule)" if eps_info
                                     else "synchronous, fixed sweeps, no damping"), "eps_mode": eps_info,
-                       "sharding": f"cases x{world}", "gather": bool(gathered is not None),
-                       "kernel_family": "network-specialised (NVRTC sm_100a)" if st["last_specialised"] else "generic",
+                       "sharding": f"cases x{world}", "gather": gather, "multi_gpu": multi_gpu,
+                       "kernel_family": ("on-chip multi-sweep (NVRTC sm_100a, state in shared memory)" if onchip else
+                                         "network-specialised (NVRTC sm_100a)" if st["last_specialised"] else "generic"),
                        "cases_per_tile": int(st["cases_per_tile"]),
-                       "l2": f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
-                             f"of per-case state per GPU vs 126 MB"},
+                       "l2": (f"on-chip kernel: no state in HBM; evidence in + marginals out = {(ev.nbytes() + n * V * tsize) / 1e9:.2f} GB per step vs 126 MB of L2"
+                              if onchip else
+                              f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
+                              f"of per-case state per GPU vs 126 MB")},
             "roofline": roofline, "dense": dense, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "configs": configs,
         }
