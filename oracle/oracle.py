@@ -180,3 +180,47 @@ def reference_dsc_flatten(text: str):
     lib.bnref_dsc_flatten(raw, C.byref(n), C.byref(e), C.byref(v), _ptr(card, C.c_int32), _ptr(poff, C.c_int32),
                           _ptr(par, C.c_int32), _ptr(coff, C.c_int64), _ptr(cpt, C.c_double))
     return card, poff, par[:e.value], coff, cpt[:v.value]
+
+
+REF_SAMPLER_SO = os.path.join(HERE, "_ref", "libbnref_sampler.so")
+
+
+def have_reference_sampler() -> bool:
+    return os.path.exists(REF_SAMPLER_SO)
+
+
+def _sampler_lib():
+    if REF_SAMPLER_SO not in _ref:
+        _ref[REF_SAMPLER_SO] = C.CDLL(REF_SAMPLER_SO)
+    return _ref[REF_SAMPLER_SO]
+
+
+def reference_make_cpt(net, samples, multiplicity=None):
+    """The reference's own sampler::load_sample(table) + sampler::make_cpt (sampler.hpp:29-163, compiled in place
+    over the Boost stand-ins of tests/cpp/boost).  Returns the CPT arena in the layout of include/bnbp.h."""
+    lib = _sampler_lib()
+    samples = np.ascontiguousarray(samples, dtype=np.int32)
+    mult = None if multiplicity is None else np.ascontiguousarray(multiplicity, dtype=np.int64)
+    out = np.empty(int(net.cpt_off[-1]), dtype=np.float64)
+    lib.bnref_make_cpt.restype = C.c_int
+    rc = lib.bnref_make_cpt(C.c_int32(net.n_nodes), _ptr(net.card, C.c_int32), _ptr(net.parent_off, C.c_int32),
+                            _ptr(net.parents, C.c_int32), _ptr(net.cpt_off, C.c_int64), _ptr(samples, C.c_int32),
+                            _ptr(mult, C.c_int64), C.c_int64(samples.shape[0]), _ptr(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"bnref_make_cpt failed ({rc})")
+    return out
+
+
+def reference_make_cpt_from_file(net, path):
+    """The reference's own sample-file reader (sampler.hpp:42-76: 'count v1 .. vN' per line) + make_cpt.
+    Returns (cpt, sampling_size)."""
+    lib = _sampler_lib()
+    out = np.empty(int(net.cpt_off[-1]), dtype=np.float64)
+    size = C.c_int64(0)
+    lib.bnref_make_cpt_from_file.restype = C.c_int
+    rc = lib.bnref_make_cpt_from_file(C.c_int32(net.n_nodes), _ptr(net.card, C.c_int32), _ptr(net.parent_off, C.c_int32),
+                                      _ptr(net.parents, C.c_int32), _ptr(net.cpt_off, C.c_int64), path.encode(),
+                                      C.byref(size), _ptr(out, C.c_double))
+    if rc != 0:
+        raise RuntimeError(f"bnref_make_cpt_from_file failed ({rc})")
+    return out, int(size.value)

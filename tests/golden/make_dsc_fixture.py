@@ -19,6 +19,9 @@ if __name__ == "__main__":
         "pearl": netfile.dump_dsc(synth.pearl_network()),
         "alarm37_reversed": netfile.dump_dsc(synth.alarm37(), order="reversed"),
         "dag30": netfile.dump_dsc(synth.random_dag(30, seed=11)),
+        # the public ASIA network (tests/golden/asia.bif, a third-party BIF file), read by the BIF loader, written as
+        # DSC: the reference's own DSC loader must give back what the BIF loader read (pins the BIF loader by proxy)
+        "asia_from_bif": netfile.dump_dsc(netfile.load(os.path.join(ROOT, "tests", "golden", "asia.bif")).net),
     }
     out = {}
     for name, text in cases.items():

@@ -6,6 +6,7 @@ seeds from std::random_device) and against hand-computed CPT tables.
 GPU part (``-m gpu``): the CUDA kernels behind bnbp_lw_run_batch / bnbp_estimate_cpt against those
 restatements -- draw for draw (same counter-based variates) and count for count."""
 import itertools
+import os
 
 import numpy as np
 import pytest
@@ -13,6 +14,8 @@ import pytest
 from bayesiannetwork_b200 import synth
 from bayesiannetwork_b200.flat import EvidenceBatch, FlatNetwork
 from helpers import assert_close
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
 def exact_posteriors(net: FlatNetwork, ev: EvidenceBatch) -> np.ndarray:
@@ -197,3 +200,52 @@ def test_gpu_estimate_cpt_then_infer(BP, oracle_mod):
     s[5, 3] = 77
     with pytest.raises(BnbpError):
         estimate_cpt(net, s)
+
+
+# ---- f3 pinned against the reference's own sampler.hpp (compiled in place over Boost stand-ins) -----------------
+SAMPLER_FIXTURES = ["pearl", "alarm37", "dag25_card5"]
+
+
+def _sampler_fixture(name):
+    fx = np.load(os.path.join(ROOT, "tests", "golden", "sampler_fixture.npz"), allow_pickle=False)
+    p = name + "/"
+    net = FlatNetwork(fx[p + "card"], fx[p + "parent_off"], fx[p + "parents"], fx[p + "cpt_off"],
+                      np.zeros(int(fx[p + "cpt_off"][-1])), name=name)
+    return net, fx[p + "samples"], fx[p + "mult"], fx[p + "cpt"]
+
+
+@pytest.mark.parametrize("name", SAMPLER_FIXTURES)
+def test_make_cpt_port_equals_reference_golden(oracle_mod, name):
+    """oracle/bp_oracle.c::bp_oracle_make_cpt == the reference's sampler::make_cpt (sampler.hpp:81-163), from the
+    committed output of the reference binary: counts are integers and count / total is one correctly rounded
+    division in both, so the rows agree bit for bit (bar 1e-15)."""
+    net, s, mult, want = _sampler_fixture(name)
+    got = oracle_mod.port_make_cpt(net, s, mult)
+    assert np.abs(got - want).max() <= 1e-15 and np.array_equal(got, want)
+    assert (want.reshape(-1) == 0).sum() >= 0 and np.isfinite(want).all()
+
+
+def test_make_cpt_port_equals_live_reference_and_its_file_reader(oracle_mod, tmp_path):
+    """Where the reference could be compiled (this container): live differential run incl. the reference's own
+    sample-file reader (sampler.hpp:42-76) on a file with runs of blanks (token_compress_on)."""
+    if not oracle_mod.have_reference_sampler():
+        pytest.skip("oracle/_ref/libbnref_sampler.so not built (needs /root/reference)")
+    net = synth.random_dag(18, 3, 2, 4, seed=9)
+    s = np.unique(ancestral_samples(net, 5000, seed=3), axis=0)
+    mult = (np.arange(s.shape[0]) % 5 + 1).astype(np.int64)
+    want = oracle_mod.reference_make_cpt(net, s, mult)
+    assert np.array_equal(oracle_mod.port_make_cpt(net, s, mult), want)
+    path = tmp_path / "samples.txt"
+    path.write_text("".join(f"{int(m)}  " + " ".join(str(int(v)) for v in row) + "\n" for row, m in zip(s, mult)))
+    from_file, size = oracle_mod.reference_make_cpt_from_file(net, str(path))
+    assert size == int(mult.sum()) and np.array_equal(from_file, want)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("name", SAMPLER_FIXTURES)
+def test_gpu_estimate_cpt_equals_reference_golden(name):
+    """bnbp_estimate_cpt (cpt_count_kernel + cpt_normalize_kernel) against the reference binary's output."""
+    from bayesiannetwork_b200.engine import estimate_cpt
+    net, s, mult, want = _sampler_fixture(name)
+    got = estimate_cpt(net, s, mult)
+    assert np.abs(got - want).max() <= 1e-15 and np.array_equal(got, want)
