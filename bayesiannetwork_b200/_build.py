@@ -116,7 +116,7 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
             os.remove(os.path.join(OBJDIR, f))
     if todo or not os.path.exists(LIB):
         cmd = [nvcc, "-shared", "-cudart", "static", "-gencode", "arch=compute_100a,code=sm_100a",
-               "-o", LIB, *objs, "-ldl", "-lnccl"]      # NCCL: the communicators libbnbp owns
+               "-o", LIB, *objs, "-ldl"]      # NCCL (the communicators libbnbp owns) is bound at first use: bnbp_api.cu
         subprocess.run(cmd, check=True, env=_env())
     return LIB
 

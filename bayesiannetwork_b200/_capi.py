@@ -36,7 +36,7 @@ class EvidenceC(C.Structure):
 class RunParamsC(C.Structure):
     _fields_ = [("epsilon", C.c_double), ("max_sweeps", C.c_int32), ("damping", C.c_double),
                 ("check_interval", C.c_int32), ("out_precision", C.c_int32), ("gather", C.c_int32),
-                ("n_query", C.c_int32), ("query_nodes", C.c_void_p), ("reserved", C.c_int32 * 4)]
+                ("n_query", C.c_int32), ("query_nodes", C.c_void_p), ("semiring", C.c_int32), ("reserved", C.c_int32 * 3)]
 
 
 class SummaryC(C.Structure):

@@ -11,6 +11,7 @@
 #include "bnbp_dense_tc.cuh"
 
 #include <nccl.h>
+#include <nvtx3/nvToolsExt.h>      // header-only; ranges cost nothing unless a profiler is attached
 
 #include <algorithm>
 #include <cmath>
@@ -24,6 +25,55 @@
 #include <vector>
 
 using namespace bnbp;
+
+#include <dlfcn.h>
+#include <mutex>
+
+// NCCL is bound at FIRST USE of a communicator, not at link time.  libbnbp is loaded into processes that bring their
+// own NCCL (PyTorch bundles a newer libnccl.so.2 than the system's): a link-time dependency makes the loader map the
+// SYSTEM library first, and a later `import torch` then fails on the symbols only the newer one has (r02b: undefined
+// symbol ncclDevCommCreate).  dlopen("libnccl.so.2") returns the copy the process already holds when there is one.
+namespace bnbp_nccl {
+struct Api {
+    void* so = nullptr;
+    std::string load_error;
+    decltype(&::ncclAllReduce) AllReduce = nullptr;
+    decltype(&::ncclBroadcast) Broadcast = nullptr;
+    decltype(&::ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&::ncclCommInitAll) CommInitAll = nullptr;
+    decltype(&::ncclCommInitRank) CommInitRank = nullptr;
+    decltype(&::ncclGetErrorString) GetErrorString = nullptr;
+    decltype(&::ncclGetUniqueId) GetUniqueId = nullptr;
+    decltype(&::ncclGroupStart) GroupStart = nullptr;
+    decltype(&::ncclGroupEnd) GroupEnd = nullptr;
+};
+static Api& api()
+{
+    static Api a;
+    static std::once_flag once;
+    std::call_once(once, [] {
+        for (const char* nm : {"libnccl.so.2", "libnccl.so"}) {
+            a.so = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+            if (a.so) break;
+        }
+        if (!a.so) { a.load_error = std::string("libnccl.so.2 not found: ") + dlerror(); return; }
+#define BNBP_NCCL_SYM(field, name)                                                  \
+    a.field = reinterpret_cast<decltype(a.field)>(dlsym(a.so, name));               \
+    if (!a.field) { a.load_error = std::string("libnccl lacks ") + name; return; }
+        BNBP_NCCL_SYM(AllReduce, "ncclAllReduce")
+        BNBP_NCCL_SYM(Broadcast, "ncclBroadcast")
+        BNBP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        BNBP_NCCL_SYM(CommInitAll, "ncclCommInitAll")
+        BNBP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
+        BNBP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
+        BNBP_NCCL_SYM(GetUniqueId, "ncclGetUniqueId")
+        BNBP_NCCL_SYM(GroupStart, "ncclGroupStart")
+        BNBP_NCCL_SYM(GroupEnd, "ncclGroupEnd")
+#undef BNBP_NCCL_SYM
+    });
+    return a;
+}
+} // namespace bnbp_nccl
 
 namespace {
 
@@ -74,6 +124,14 @@ cudaError_t wait_stream(cudaStream_t s)
     }
     return cudaStreamSynchronize(s);
 }
+
+// NVTX range over a scope: the phases of a call show up by name on an nsys / ncu timeline
+struct NvtxRange {
+    explicit NvtxRange(const char* name) { nvtxRangePushA(name); }
+    ~NvtxRange() { nvtxRangePop(); }
+    NvtxRange(const NvtxRange&) = delete;
+    NvtxRange& operator=(const NvtxRange&) = delete;
+};
 
 constexpr int BLOCK_THREADS = 128;   // sweep-kernel block; a tile holds BLOCK_THREADS * vec cases
 
@@ -239,10 +297,10 @@ int pick_rmax(int maxcard)
 // ---- launch dispatch ----------------------------------------------------------------------------
 template <typename T>
 cudaError_t launch_sweep(const bnbp_handle* h, const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze,
-                         bool check, cudaStream_t st)
+                         bool check, cudaStream_t st, bool maxp = false)
 {
 #define BNBP_X(TT, V, R, K) \
-    if (h->vec == V && h->rmax == R && h->knet == K) return launch_sweep_vr<TT, V, R, K>(a, grid, smem, freeze, check, st);
+    if (h->vec == V && h->rmax == R && h->knet == K) return launch_sweep_vr<TT, V, R, K>(a, grid, smem, freeze, check, st, maxp);
     BNBP_SWEEP_VARIANTS(BNBP_X, T)
 #undef BNBP_X
     return cudaErrorInvalidConfiguration;
@@ -431,12 +489,25 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
     h->split = false;
     h->run_onchip = false;
     h->last_onchip = 0;
+    if (prm.semiring == BNBP_MAX_PRODUCT) {
+        // opt-in extension: the generic kernel's max flavour (one kernel per network shape class); matrix products
+        // cannot take a maximum, so handles whose large CPTs sit on the dense contraction path refuse it
+        if (h->TS > 0) return fail(BNBP_ERR_INVALID, "max-product: create the handle with dense_min_cpt = -1 (the dense contraction path sums)");
+        h->tb = BLOCK_THREADS * h->vec;
+        h->last_specialised = 0;
+        return BNBP_OK;
+    }
     {
         // the on-chip kernel: the whole case in one launch, state in shared memory (hard evidence; soft rows
         // take the streaming kernels).  AUTO: eligible networks, batches worth a persistent grid.
         int mode = h->onchip;
         if (const char* e = getenv("BNBP_ONCHIP")) mode = atoi(e) > 0 ? 1 : (atoi(e) < 0 || !strcmp(e, "0") ? -1 : 0);
-        const bool want_oc = mode > 0 || (mode == 0 && h->specialize == BNBP_SPEC_AUTO && h->oc_eligible && !soft_evidence && n_cases >= 4096);
+        // AUTO takes it for fixed sweep counts only: in epsilon mode its check flavour (10 k instructions of straight-line
+        // code per sweep, a retire / refill path every few sweeps) runs at 302 M executed case-sweeps/s on alarm37 against
+        // 357-381 M for the streaming kernels with the split convergence test (r02b vs r01fin)
+        const bool plain_run = !(prm.epsilon > 0.0) && prm.damping == 0.0;
+        const bool want_oc = mode > 0 || (mode == 0 && h->specialize == BNBP_SPEC_AUTO && h->oc_eligible && !soft_evidence &&
+                                          n_cases >= 4096 && plain_run);
         if (want_oc) {
             if (!h->oc_eligible) return fail(BNBP_ERR_INVALID, "onchip=ALWAYS but the network is not eligible: " + h->oc_why);
             if (soft_evidence) return fail(BNBP_ERR_INVALID, "onchip=ALWAYS: soft evidence rows take the streaming kernels");
@@ -529,6 +600,7 @@ template <typename T, typename OUT>
 int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_params& prm, OUT* d_out,
               int32_t* d_out_sweeps, uint8_t* d_out_conv, cudaStream_t st, int64_t* planned_sweeps)
 {
+    NvtxRange nvtx_chunk("bnbp: chunk (init, sweeps, beliefs) streaming kernels");
     const int tiles = (int)((n + h->tb - 1) / h->tb);
     int32_t* d_last_active = reinterpret_cast<int32_t*>(h->d_misc.p);
     int32_t* d_error = d_last_active + 1;
@@ -612,6 +684,10 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.last_active = d_last_active;
     sa.eps = (T)prm.epsilon;
     sa.damping = (T)prm.damping;
+    {
+        static const int prefetch = getenv("BNBP_PREFETCH") ? atoi(getenv("BNBP_PREFETCH")) : 1;   // tuning knob (A/B runs)
+        sa.prefetch = prefetch;
+    }
     T* delta = (T*)h->d_delta.p;
     const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * sizeof(T);
     dim3 grid(tiles, n_chunks);
@@ -739,7 +815,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 if (!spec_launch(h->spec[variant], (unsigned)tiles_cur, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
                     return fail(BNBP_ERR_CUDA, err);
             } else {
-                cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode && !split, check && !split, st);
+                cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode && !split, check && !split, st, prm.semiring == BNBP_MAX_PRODUCT);
                 if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("sweep launch: ") + cudaGetErrorString(e));
             }
             if (split && tested) {
@@ -922,6 +998,7 @@ template <typename T, typename OUT>
 int run_onchip(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_params& prm, OUT* d_out,
                int32_t* d_out_sweeps, uint8_t* d_out_conv, cudaStream_t st, int64_t* planned_sweeps)
 {
+    NvtxRange nvtx_chunk("bnbp: chunk, on-chip kernel (init, every sweep, beliefs in one launch)");
     const bool eps_mode = prm.epsilon > 0.0;
     if (!eps_mode && prm.max_sweeps <= 0)
         return fail(BNBP_ERR_INVALID, "epsilon <= 0 needs a positive max_sweeps (the loop would never end)");
@@ -1119,9 +1196,11 @@ int comm_resources(bnbp_handle* h)
 
 #define NCCL_TRY(expr)                                                                              \
     do {                                                                                            \
+        if (!bnbp_nccl::api().load_error.empty()) return fail(BNBP_ERR_CUDA, bnbp_nccl::api().load_error); \
         ncclResult_t r__ = (expr);                                                                  \
-        if (r__ != ncclSuccess) return fail(BNBP_ERR_CUDA, std::string(#expr) + ": " + ncclGetErrorString(r__)); \
+        if (r__ != ncclSuccess) return fail(BNBP_ERR_CUDA, std::string(#expr) + ": " + bnbp_nccl::api().GetErrorString(r__)); \
     } while (0)
+#define NCCL(fn) bnbp_nccl::api().fn
 
 // enqueue: local reduction of (sweeps, converged) of n cases, then the two all-reduces (sum / max); the totals land
 // in h->pin_summary once `st` has drained
@@ -1134,8 +1213,8 @@ int enqueue_summary(bnbp_handle* h, const int32_t* d_sweeps, const uint8_t* d_co
         CU_TRY(cudaGetLastError());
     }
     if (h->comm && h->comm_world > 1) {
-        NCCL_TRY(ncclAllReduce(d, d, 4, ncclUint64, ncclSum, h->comm, st));
-        NCCL_TRY(ncclAllReduce(d + 4, d + 4, 1, ncclUint64, ncclMax, h->comm, st));
+        NCCL_TRY(NCCL(AllReduce)(d, d, 4, ncclUint64, ncclSum, h->comm, st));
+        NCCL_TRY(NCCL(AllReduce)(d + 4, d + 4, 1, ncclUint64, ncclMax, h->comm, st));
     }
     CU_TRY(cudaMemcpyAsync(h->pin_summary, d, 8 * 8, cudaMemcpyDeviceToHost, st));
     return BNBP_OK;
@@ -1253,6 +1332,7 @@ int validate_params(const bnbp_run_params* prm)
     if (!prm) return fail(BNBP_ERR_INVALID, "run params are NULL");
     if (std::isnan(prm->epsilon)) return fail(BNBP_ERR_INVALID, "epsilon is NaN");
     if (!(prm->damping >= 0.0 && prm->damping < 1.0)) return fail(BNBP_ERR_INVALID, "damping must be in [0,1)");
+    if (prm->semiring != BNBP_SUM_PRODUCT && prm->semiring != BNBP_MAX_PRODUCT) return fail(BNBP_ERR_INVALID, "semiring out of range");
     return BNBP_OK;
 }
 
@@ -1704,17 +1784,17 @@ int run_group(bnbp_handle* g, const bnbp_evidence* ev, const bnbp_run_params* pr
     for (int i = 0; i < G; ++i)
         if (rcs[(size_t)i]) return fail(rcs[(size_t)i], "device " + std::to_string(g->members[(size_t)i]->device) + ": " + errs[(size_t)i]);
     // summary: per-case counts are still on each device (whole-shard staging of bnbp_run_batch)
-    NCCL_TRY(ncclGroupStart());
+    NCCL_TRY(NCCL(GroupStart)());
     for (int i = 0; i < G; ++i) {
         bnbp_handle* m = g->members[(size_t)i];
         CU_TRY(cudaSetDevice(m->device));
         const int64_t n = hi[(size_t)i] - lo[(size_t)i];
         if ((rc = enqueue_summary(m, (const int32_t*)m->s_out_sweeps.p, (const uint8_t*)m->s_out_conv.p, n, m->stream))) {
-            ncclGroupEnd();
+            NCCL(GroupEnd)();
             return rc;
         }
     }
-    NCCL_TRY(ncclGroupEnd());
+    NCCL_TRY(NCCL(GroupEnd)());
     for (int i = 0; i < G; ++i) {
         CU_TRY(cudaSetDevice(g->members[(size_t)i]->device));
         CU_TRY(wait_stream(g->members[(size_t)i]->stream));
@@ -1824,7 +1904,7 @@ void bnbp_destroy(bnbp_handle* h)
         return;
     }
     cudaSetDevice(h->device);
-    if (h->comm) { ncclCommDestroy(h->comm); h->comm = nullptr; }
+    if (h->comm) { NCCL(CommDestroy)(h->comm); h->comm = nullptr; }
     if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
     for (cudaEvent_t e : h->ev_comm) cudaEventDestroy(e);
     if (h->pin_summary) cudaFreeHost(h->pin_summary);
@@ -1957,6 +2037,7 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
                           int32_t* out_sweeps, uint8_t* out_converged, void* stream)
 {
     if (!h || !ev || !out_marginals) return fail(BNBP_ERR_INVALID, "bnbp_run_batch_device: NULL argument");
+    NvtxRange nvtx_call("bnbp_run_batch_device");
     int rc = validate_params(prm);
     if (rc) return rc;
     if (ev->n_cases < 0) return fail(BNBP_ERR_INVALID, "n_cases < 0");
@@ -2015,12 +2096,12 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
             }
             CU_TRY(cudaEventRecord(h->ev_comm[(size_t)n_chunk + 1], st));
             CU_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_comm[(size_t)n_chunk + 1], 0));
-            NCCL_TRY(ncclGroupStart());
+            NCCL_TRY(NCCL(GroupStart)());
             for (int r = 0; r < h->comm_world; ++r) {
                 char* const slot = base + ((size_t)r * (size_t)ev->n_cases + (size_t)c0) * row_bytes;
-                NCCL_TRY(ncclBroadcast(slot, slot, (size_t)n * h->Vout, h->tsize == 4 ? ncclFloat : ncclDouble, r, h->comm, h->comm_stream));
+                NCCL_TRY(NCCL(Broadcast)(slot, slot, (size_t)n * h->Vout, h->tsize == 4 ? ncclFloat : ncclDouble, r, h->comm, h->comm_stream));
             }
-            NCCL_TRY(ncclGroupEnd());
+            NCCL_TRY(NCCL(GroupEnd)());
         }
     }
     if (exchange) {
@@ -2050,6 +2131,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
 {
     if (!h || !ev || !out_marginals_v) return fail(BNBP_ERR_INVALID, "bnbp_run_batch: NULL argument");
     const auto t_entry = std::chrono::steady_clock::now();
+    NvtxRange nvtx_call("bnbp_run_batch (host buffers: H2D evidence | kernels | D2H marginals, pipelined by chunk)");
     int rc = validate_params(prm);
     if (rc) return rc;
     if (!h->members.empty()) return run_group(h, ev, prm, out_marginals_v, out_sweeps, out_converged);
@@ -2200,6 +2282,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
             if (!mono) return fail(BNBP_ERR_INVALID, "ev_off not monotone");
         }
         // evidence of this chunk, into its place in the whole-batch arrays
+        std::unique_ptr<NvtxRange> nvtx_h2d(new NvtxRange("bnbp: enqueue H2D evidence of a chunk"));
         CU_TRY(cudaMemcpyAsync((int64_t*)h->s_ev_off.p + c0, ev->ev_off + c0, (size_t)(n + 1) * 8, cudaMemcpyHostToDevice, hs));
         if (b > a) CU_TRY(cudaMemcpyAsync((int32_t*)h->s_ev_node.p + a, ev->ev_node + a, (size_t)(b - a) * 4, cudaMemcpyHostToDevice, hs));
         DevEvidence de{(const int64_t*)h->s_ev_off.p + c0, 0, (const int32_t*)h->s_ev_node.p, nullptr, nullptr, nullptr, 0};
@@ -2221,6 +2304,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
             de.ev_state = (const int32_t*)h->s_ev_state.p;
         }
         CU_TRY(cudaEventRecord(e_up, hs));
+        nvtx_h2d.reset();
         CU_TRY(cudaStreamWaitEvent(st, e_up, 0));
         char* slot = whole ? (char*)h->s_out_all.p + (size_t)c0 * row_bytes : (char*)h->s_out[idx & 1].p;
         if (!whole && idx >= 2) CU_TRY(cudaStreamWaitEvent(st, h->ev_chunk[3 * (idx - 2) + 2], 0));   // ring slot is free again
@@ -2237,6 +2321,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
         CU_TRY(cudaEventRecord(e_done, st));
         CU_TRY(cudaStreamWaitEvent(cs, e_done, 0));
         mark(cs);
+        NvtxRange nvtx_d2h("bnbp: enqueue D2H marginals of a chunk");
         CU_TRY(cudaMemcpyAsync(out_marginals + (size_t)c0 * row_bytes, slot, (size_t)n * row_bytes, cudaMemcpyDeviceToHost, cs));
         mark(cs);
         // per-case counts: into the library's pinned staging (the caller's arrays are usually pageable, and
@@ -2256,6 +2341,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     CU_TRY(cudaEventRecord(h->ev_total[1], st));
     h->total_recorded = true;
     const auto t_wait = std::chrono::steady_clock::now();
+    NvtxRange nvtx_wait("bnbp: wait for the streams");
     if ((rc = check_error_flag(h, st))) return rc;
     CU_TRY(wait_stream(cs));
     h->last_host_wait_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_wait).count();
@@ -2573,7 +2659,7 @@ int bnbp_create_multi(const bnbp_flat_network* net, const bnbp_options* opt, con
         if ((rc = comm_resources(m))) return rc;
     }
     std::vector<ncclComm_t> comms(devs.size(), nullptr);
-    NCCL_TRY(ncclCommInitAll(comms.data(), (int)devs.size(), devs.data()));
+    NCCL_TRY(NCCL(CommInitAll)(comms.data(), (int)devs.size(), devs.data()));
     for (size_t i = 0; i < devs.size(); ++i) {
         g->members[i]->comm = comms[i];
         g->members[i]->comm_rank = (int)i;
@@ -2595,7 +2681,7 @@ int bnbp_comm_unique_id(void* id_out)
     if (!id_out) return fail(BNBP_ERR_INVALID, "bnbp_comm_unique_id: NULL argument");
     static_assert(sizeof(ncclUniqueId) <= BNBP_COMM_ID_BYTES, "ncclUniqueId larger than BNBP_COMM_ID_BYTES");
     ncclUniqueId id;
-    NCCL_TRY(ncclGetUniqueId(&id));
+    NCCL_TRY(NCCL(GetUniqueId)(&id));
     memset(id_out, 0, BNBP_COMM_ID_BYTES);
     memcpy(id_out, &id, sizeof id);
     return BNBP_OK;
@@ -2612,7 +2698,7 @@ int bnbp_comm_init(bnbp_handle* h, int32_t world, int32_t rank, const void* id_i
     CU_TRY(cudaSetDevice(h->device));
     ncclUniqueId id;
     memcpy(&id, id_in, sizeof id);
-    NCCL_TRY(ncclCommInitRank(&h->comm, world, id, rank));
+    NCCL_TRY(NCCL(CommInitRank)(&h->comm, world, id, rank));
     h->comm_world = world;
     h->comm_rank = rank;
     return BNBP_OK;

@@ -70,6 +70,7 @@ template <typename T> struct SweepArgs {
     int32_t  prev_tested;
     T eps;
     T damping;
+    int32_t prefetch;           // 1: every node prefetches the inputs of the NEXT node of the walk into L2 (sweep_kernel)
 };
 
 template <typename T, int VEC> struct alignas(sizeof(T) * VEC) Pk { T v[VEC]; };
@@ -111,7 +112,7 @@ __device__ __forceinline__ void atomic_max_nonneg(float* p, float v)
 // Sweep launchers: defined in bnbp_sweep.cuh, explicitly instantiated one (T, VEC, RMAX) per
 // translation unit (bnbp_sweep_inst.cu) so the build parallelises.
 template <typename T, int VEC, int RMAX, int KNET>
-cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze, bool check, cudaStream_t st);
+cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze, bool check, cudaStream_t st, bool maxp);
 template <typename T, int VEC, int RMAX, int KNET> cudaError_t set_sweep_smem(int bytes);
 
 // ------------------------------------------------------------------------------------------------

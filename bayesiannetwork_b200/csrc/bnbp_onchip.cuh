@@ -61,7 +61,7 @@ struct OcArgs {                         // mirrors OnchipArgs in bnbp_jit.h
 constexpr int ROLES = BNBP_ROLES;
 constexpr int OC_THREADS = 32 * ROLES;
 constexpr int RETIRE_BATCH = 8;         // frozen lanes a group collects before it writes marginals and refills
-// shared memory: [PL][32] pi/lambda | [M][32] messages | partial deltas [2][ROLES][32] | tickets [32]
+// shared memory: [PL][32] pi/lambda | [M][32] messages | partial deltas [ROLES][32] | tickets [32]
 
 __device__ __forceinline__ void oc_barrier() { asm volatile("bar.sync 1, %0;" ::"n"(OC_THREADS) : "memory"); }
 
@@ -112,8 +112,8 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
     extern __shared__ __align__(16) unsigned char oc_smem[];
     T* const s_pl = reinterpret_cast<T*>(oc_smem);
     T* const s_msg = s_pl + (long long)BNBP_PL * 32;
-    T* const s_delta = s_msg + (long long)BNBP_M * 32;                        // [2][ROLES][32]
-    long long* const s_case = reinterpret_cast<long long*>(s_delta + 2 * ROLES * 32);   // [32]
+    T* const s_delta = s_msg + (long long)BNBP_M * 32;                        // [ROLES][32]
+    long long* const s_case = reinterpret_cast<long long*>(s_delta + ROLES * 32);       // [32]
 
     const int lane = threadIdx.x & 31;
     const int role = threadIdx.x >> 5;
@@ -125,7 +125,6 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
     long long cid = -1;                 // the case this lane works on (-1: needs one, -2: none left)
     int sw = 0;                         // sweeps its case has run
     bool fin = false, fconv = false;    // the case has stopped (frozen until the group retires a batch) / it met delta < eps
-    int flip = 0;                       // which half of s_delta this sweep writes
 #pragma unroll
     for (int w = 0; w < BNBP_W; ++w) evl[w] = 0u;
 
@@ -205,10 +204,11 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
 #undef BNBP_SYNC
 #undef BNBP_COMP
         }
-        T* const dpart = s_delta + (long long)(flip * ROLES) * 32;
+        // partial deltas: written after this sweep's phase-A barrier, read by every warp right after the commit barrier and
+        // before ITS next phase-A barrier -- so the next sweep's writes cannot overtake a slow reader
+        T* const dpart = s_delta;
         if constexpr (CHECK) dpart[role * 32 + lane] = c.dmax[0];
         oc_barrier();                                      // commit (:135-143): every time-(t+1) value is written
-        flip ^= 1;
         const bool active = c.act[0];
         if (active) ++sw;
 

@@ -27,7 +27,16 @@ constexpr int BLOCK = 128;
 // of the reference's (k^2+k+1)|CPT|.  The last parent and the states of X are unrolled to RMAX
 // and live in registers; parents further out keep their messages / accumulators in a per-thread
 // shared-memory scratch column (dynamic index, conflict-free [value][thread] layout).
-template <typename T, int VEC, int RMAX> struct ParentCtx {
+// MAXP: the max-product semiring (opt-in extension, bnbp_run_params.semiring): every sum over parent configurations /
+// child states of :174-200 and :240-266 becomes a maximum -- all factors are non-negative, so the prefix-product
+// recursion below carries over with acc = max(acc, a * b) in place of acc += a * b.  fmax ignores NaN.
+template <bool MAXP, typename T> __device__ __forceinline__ T acc_op(T a, T b, T acc)
+{
+    if constexpr (MAXP) return fmax(acc, a * b);
+    else return fma(a, b, acc);
+}
+
+template <typename T, int VEC, int RMAX, bool MAXP = false> struct ParentCtx {
     const T* cpt;
     int r, rk;
     int rj[KMAX];
@@ -44,8 +53,8 @@ template <typename T, int VEC, int RMAX> struct ParentCtx {
 //   SRC_T2     the per-case table T2[uA] of GEMM 2: r = 1 and lambda = 1, only lambda-messages come out
 enum { SRC_CPT = 0, SRC_T1 = 1, SRC_T2 = 2 };
 
-template <int SRC, typename T, int VEC, int RMAX>
-__device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T (&P)[VEC], int q, T (&ret)[VEC])
+template <int SRC, typename T, int VEC, int RMAX, bool MAXP>
+__device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX, MAXP>& c, const T (&P)[VEC], int q, T (&ret)[VEC])
 {
     constexpr size_t STR = SRC == SRC_CPT ? 1 : (size_t)BLOCK * VEC;   // per-case tables are batch-minor
     const int rr = SRC == SRC_T2 ? 1 : c.r;
@@ -73,8 +82,8 @@ __device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T 
                 if constexpr (SRC == SRC_T2) {
                     w[v] = p[v];
                 } else {
-                    w[v] = fma(c.lam[x][v], p[v], w[v]);
-                    c.pacc[x][v] = fma(p[v], pm[v], c.pacc[x][v]);
+                    w[v] = acc_op<MAXP>(c.lam[x][v], p[v], w[v]);
+                    c.pacc[x][v] = acc_op<MAXP>(p[v], pm[v], c.pacc[x][v]);
                 }
             }
         };
@@ -89,8 +98,8 @@ __device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T 
         }
 #pragma unroll
         for (int v = 0; v < VEC; ++v) {
-            c.lacck[b][v] = fma(P[v], w[v], c.lacck[b][v]);
-            ret[v] = fma(c.mk[b][v], w[v], ret[v]);
+            c.lacck[b][v] = acc_op<MAXP>(P[v], w[v], c.lacck[b][v]);
+            ret[v] = acc_op<MAXP>(c.mk[b][v], w[v], ret[v]);
         }
     };
     if constexpr (RMAX <= 8) {
@@ -102,11 +111,11 @@ __device__ __forceinline__ void parent_leaf(ParentCtx<T, VEC, RMAX>& c, const T 
     }
 }
 
-template <int LEVEL, int K, int SRC, typename T, int VEC, int RMAX>
-__device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX>& c, const T (&P)[VEC], int q, T (&ret)[VEC])
+template <int LEVEL, int K, int SRC, typename T, int VEC, int RMAX, bool MAXP>
+__device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX, MAXP>& c, const T (&P)[VEC], int q, T (&ret)[VEC])
 {
     if constexpr (LEVEL == K - 1) {
-        parent_leaf<SRC, T, VEC, RMAX>(c, P, q, ret);
+        parent_leaf<SRC, T, VEC, RMAX, MAXP>(c, P, q, ret);
     } else {
         const int rl = c.rj[LEVEL];
 #pragma unroll
@@ -118,32 +127,32 @@ __device__ __forceinline__ void parent_rec(ParentCtx<T, VEC, RMAX>& c, const T (
                 mv[v] = c.scr[((c.soff[LEVEL] + a) * VEC + v) * BLOCK];
                 P2[v] = P[v] * mv[v];
             }
-            parent_rec<LEVEL + 1, K, SRC, T, VEC, RMAX>(c, P2, q * rl + a, R);
+            parent_rec<LEVEL + 1, K, SRC, T, VEC, RMAX, MAXP>(c, P2, q * rl + a, R);
 #pragma unroll
             for (int v = 0; v < VEC; ++v) {
                 T* acc = &c.scr[((c.sacc_base + c.soff[LEVEL] + a) * VEC + v) * BLOCK];
-                *acc = fma(P[v], R[v], *acc);
-                ret[v] = fma(mv[v], R[v], ret[v]);
+                *acc = acc_op<MAXP>(P[v], R[v], *acc);
+                ret[v] = acc_op<MAXP>(mv[v], R[v], ret[v]);
             }
         }
     }
 }
 
-template <int K, int SRC, typename T, int VEC, int RMAX>
-__device__ __forceinline__ void parent_run(ParentCtx<T, VEC, RMAX>& c)
+template <int K, int SRC, typename T, int VEC, int RMAX, bool MAXP>
+__device__ __forceinline__ void parent_run(ParentCtx<T, VEC, RMAX, MAXP>& c)
 {
     T one[VEC], ret[VEC];
 #pragma unroll
     for (int v = 0; v < VEC; ++v) one[v] = T(1);
-    parent_rec<0, K, SRC, T, VEC, RMAX>(c, one, 0, ret);
+    parent_rec<0, K, SRC, T, VEC, RMAX, MAXP>(c, one, 0, ret);
 }
 
 // One group of consecutive parents [j0, j0+kk) of a node against one table: stages their
 // pi-messages (outer ones in the scratch column, the last one in registers), runs the recursion and
 // emits the lambda-messages to exactly these parents.  An ordinary node is one group over its CPT;
 // a dense node is group A over T2 followed by group B over T1.
-template <int SRC, int KNET, typename T, int VEC, int RMAX, typename EmitMsg>
-__device__ __forceinline__ void parent_group(ParentCtx<T, VEC, RMAX>& pc, const T* table, const int32_t* ecard,
+template <int SRC, int KNET, typename T, int VEC, int RMAX, bool MAXP, typename EmitMsg>
+__device__ __forceinline__ void parent_group(ParentCtx<T, VEC, RMAX, MAXP>& pc, const T* table, const int32_t* ecard,
                                              const int32_t* louts, const T* cur, T* scr, int scr_half, int kk,
                                              int slot, EmitMsg& emit_msg)
 {
@@ -190,16 +199,16 @@ __device__ __forceinline__ void parent_group(ParentCtx<T, VEC, RMAX>& pc, const 
                 for (int v = 0; v < VEC; ++v) pc.mk[u][v] = mm.v[v];
             }
     }
-    if (kk == 1) parent_run<1, SRC, T, VEC, RMAX>(pc);
-    else if (kk == 2) parent_run<2, SRC, T, VEC, RMAX>(pc);
+    if (kk == 1) parent_run<1, SRC, T, VEC, RMAX, MAXP>(pc);
+    else if (kk == 2) parent_run<2, SRC, T, VEC, RMAX, MAXP>(pc);
     else if constexpr (KNET > 2) {
-        if (kk == 3) parent_run<3, SRC, T, VEC, RMAX>(pc);
-        else if (kk == 4) parent_run<4, SRC, T, VEC, RMAX>(pc);
+        if (kk == 3) parent_run<3, SRC, T, VEC, RMAX, MAXP>(pc);
+        else if (kk == 4) parent_run<4, SRC, T, VEC, RMAX, MAXP>(pc);
         else if constexpr (KNET > 4) {
-            if (kk == 5) parent_run<5, SRC, T, VEC, RMAX>(pc);
-            else if (kk == 6) parent_run<6, SRC, T, VEC, RMAX>(pc);
-            else if (kk == 7) parent_run<7, SRC, T, VEC, RMAX>(pc);
-            else parent_run<8, SRC, T, VEC, RMAX>(pc);
+            if (kk == 5) parent_run<5, SRC, T, VEC, RMAX, MAXP>(pc);
+            else if (kk == 6) parent_run<6, SRC, T, VEC, RMAX, MAXP>(pc);
+            else if (kk == 7) parent_run<7, SRC, T, VEC, RMAX, MAXP>(pc);
+            else parent_run<8, SRC, T, VEC, RMAX, MAXP>(pc);
         }
     }
     // lambda-messages to the outer parents (accumulated in scratch) ...
@@ -229,7 +238,7 @@ __device__ __forceinline__ void parent_group(ParentCtx<T, VEC, RMAX>& pc, const 
 template <typename T> __device__ __forceinline__ T recip(T s) { return T(1) / s; }
 
 // ------------------------------------------------------------------------------------------------
-template <typename T, int VEC, int RMAX, int KNET, bool FREEZE, bool CHECK>
+template <typename T, int VEC, int RMAX, int KNET, bool FREEZE, bool CHECK, bool MAXP = false>
 __global__ void __launch_bounds__(BLOCK)
 sweep_kernel(const SweepArgs<T> a)
 {
@@ -343,9 +352,26 @@ sweep_kernel(const SweepArgs<T> a)
     Pk<uint32_t, VEC> evw;
     int evw_idx = -1;
 
+    const int n_total = a.chunk_off[a.n_chunks];
+    const int pin_total = a.nodes[0].lin_off;          // the lambda inboxes follow the pi inboxes in a message buffer
+
     for (int X = n0; X < n1; ++X) {
         const NodeMeta nd = a.nodes[X];
         const int r = nd.card, k = nd.k, m = nd.m;
+        if (a.prefetch && X + 1 < n1) {
+            // The walk is a dependent chain per node -- load the inputs, compute, store -- and at 12-16 resident warps per
+            // SM (128-168 registers) the loads of one node do not cover the HBM latency (r02a: 8.6-10.2 long-scoreboard
+            // stall cycles per issue, DRAM at 25-54 % of peak on dag2000 / grid100).  Asking L2 for the NEXT node's rows
+            // now (its pi/lambda and its two inboxes) doubles the requests in flight without a single extra register.
+            const NodeMeta nn = a.nodes[X + 1];
+            const int pin_len = (X + 2 < n_total ? a.nodes[X + 2].pin_off : pin_total) - nn.pin_off;
+            const T* p0 = pl + (size_t)nn.pl_off * TBC;
+            for (int i = 0; i < 2 * nn.card; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (size_t)i * TBC));
+            p0 = cur + (size_t)nn.pin_off * TBC;
+            for (int i = 0; i < pin_len; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (size_t)i * TBC));
+            p0 = cur + (size_t)nn.lin_off * TBC;
+            for (int i = 0; i < nn.m * nn.card; ++i) asm volatile("prefetch.global.L2 [%0];" ::"l"(p0 + (size_t)i * TBC));
+        }
         if ((X >> 5) != evw_idx) { evw_idx = X >> 5; evw = ldp<uint32_t, VEC>(evb + (size_t)evw_idx * TBC); }
         bool upd[VEC];                                  // may pi_X / lambda_X be rewritten?
 #pragma unroll
@@ -355,7 +381,7 @@ sweep_kernel(const SweepArgs<T> a)
         T* const pX = pl + (size_t)nd.pl_off * TBC;
         T* const lX = pX + (size_t)r * TBC;
         T pi[RMAX][VEC];
-        ParentCtx<T, VEC, RMAX> pc;
+        ParentCtx<T, VEC, RMAX, MAXP> pc;
 #pragma unroll
         for (int x = 0; x < RMAX; ++x) {
             if (x < r) {
@@ -513,9 +539,11 @@ sweep_kernel(const SweepArgs<T> a)
 }
 
 template <typename T, int VEC, int RMAX, int KNET>
-cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze, bool check, cudaStream_t st)
+cudaError_t launch_sweep_vr(const SweepArgs<T>& a, dim3 grid, size_t smem, bool freeze, bool check, cudaStream_t st, bool maxp)
 {
-    if (check) sweep_kernel<T, VEC, RMAX, KNET, true, true><<<grid, BLOCK, smem, st>>>(a);
+    // max-product runs one flavour only: freeze + check (with eps <= 0 no case ever freezes: a fixed sweep count)
+    if (maxp) sweep_kernel<T, VEC, RMAX, KNET, true, true, true><<<grid, BLOCK, smem, st>>>(a);
+    else if (check) sweep_kernel<T, VEC, RMAX, KNET, true, true><<<grid, BLOCK, smem, st>>>(a);
     else if (freeze) sweep_kernel<T, VEC, RMAX, KNET, true, false><<<grid, BLOCK, smem, st>>>(a);
     else sweep_kernel<T, VEC, RMAX, KNET, false, false><<<grid, BLOCK, smem, st>>>(a);
     return cudaGetLastError();
@@ -527,6 +555,8 @@ template <typename T, int VEC, int RMAX, int KNET> cudaError_t set_sweep_smem(in
     e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+    if (e != cudaSuccess) return e;
+    e = cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, true, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
     if (e != cudaSuccess) return e;
     return cudaFuncSetAttribute(sweep_kernel<T, VEC, RMAX, KNET, true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
 }

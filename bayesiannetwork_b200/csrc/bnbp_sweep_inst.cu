@@ -5,6 +5,6 @@
 #error "define BNBP_T, BNBP_VEC, BNBP_RMAX and BNBP_KNET"
 #endif
 namespace bnbp {
-template cudaError_t launch_sweep_vr<BNBP_T, BNBP_VEC, BNBP_RMAX, BNBP_KNET>(const SweepArgs<BNBP_T>&, dim3, size_t, bool, bool, cudaStream_t);
+template cudaError_t launch_sweep_vr<BNBP_T, BNBP_VEC, BNBP_RMAX, BNBP_KNET>(const SweepArgs<BNBP_T>&, dim3, size_t, bool, bool, cudaStream_t, bool);
 template cudaError_t set_sweep_smem<BNBP_T, BNBP_VEC, BNBP_RMAX, BNBP_KNET>(int);
 } // namespace bnbp

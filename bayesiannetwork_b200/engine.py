@@ -124,9 +124,10 @@ class BeliefPropagation:
                  max_sweeps: int = 0, damping: float = 0.0, check_interval: int = 1,
                  out: Optional[np.ndarray] = None, out_sweeps: Optional[np.ndarray] = None,
                  out_converged: Optional[np.ndarray] = None, query_nodes: Optional[Sequence[int]] = None,
-                 out_dtype=np.float64) -> BPResult:
+                 out_dtype=np.float64, semiring: str = "sum") -> BPResult:
         """``query_nodes``: only these nodes' marginals are returned (columns in the given order);
-        ``out_dtype=np.float32`` (fp32 handles): float marginals, half the device-to-host copy."""
+        ``out_dtype=np.float32`` (fp32 handles): float marginals, half the device-to-host copy;
+        ``semiring="max"``: max-product (max-marginals) instead of the reference's sum-product."""
         if evidence is None:
             evidence = EvidenceBatch.empty(1)   # operator()(epsilon) by-pass (:24-28)
         ev = evidence
@@ -148,7 +149,8 @@ class BeliefPropagation:
                               _vp(ev.ev_val_off) if ev.is_soft else None,
                               _vp(ev.ev_values) if ev.is_soft else None)
         prm = _capi.RunParamsC(float(epsilon), int(max_sweeps), float(damping), int(check_interval),
-                               2 if out_dtype == np.float32 else 0, 0, 0 if q is None else int(q.size), _vp(q))
+                               2 if out_dtype == np.float32 else 0, 0, 0 if q is None else int(q.size), _vp(q),
+                               {"sum": 0, "max": 1}[semiring])
         _capi.check(self._lib.bnbp_run_batch(self._h, C.byref(evc), C.byref(prm), _vp(out), _vp(sweeps), _vp(conv)))
         return BPResult(out.reshape(n, V), sweeps, conv)
 

@@ -107,6 +107,7 @@ public:
         int precision = BNBP_FP64;   // the reference computes in double
         int device = -1;             // CUDA device ordinal, -1 = current
         int specialize = BNBP_SPEC_AUTO;
+        int semiring = BNBP_SUM_PRODUCT;   // extension: BNBP_MAX_PRODUCT = max-marginals (the reference is sum-product)
         // several GPUs of this box: a call shards its cases over these ordinals by contiguous ranges,
         // one host thread and stream set per device; {-1} = every visible device; empty = `device` alone.
         // Results do not depend on the sharding (bit for bit).
@@ -219,8 +220,17 @@ public:
     // Zero-copy form: CSR evidence over vertex_list() indices (see bnbp_evidence in <bnbp.h>).
     flat_result run_flat(bnbp_evidence const& ev, options const& opt)
     {
+        flat_result out;
+        run_flat(ev, opt, out);
+        return out;
+    }
+
+    // The same into a result the caller keeps between calls: its page-locked buffers are reused when they are large
+    // enough (pinning 0.9 GB for 1M alarm37 cases costs a few hundred milliseconds -- more than ten calls).
+    void run_flat(bnbp_evidence const& ev, options const& opt, flat_result& out)
+    {
         sync_network(opt);
-        return run_synced(ev, opt);
+        run_synced(ev, opt, out);
     }
 
     // Statistics of the last run (device milliseconds, launches, bytes per case): bnbp_get_stats.
@@ -288,7 +298,14 @@ private:
     flat_result run_synced(bnbp_evidence const& ev, options const& opt)
     {
         flat_result out;
+        run_synced(ev, opt, out);
+        return out;
+    }
+
+    void run_synced(bnbp_evidence const& ev, options const& opt, flat_result& out)
+    {
         out.n_cases = static_cast<std::size_t>(ev.n_cases);
+        out.vertex.clear();
         std::vector<std::int32_t> query;
         for (vertex_type const& v : opt.query) {
             std::size_t index = 0;
@@ -298,13 +315,13 @@ private:
         }
         if (query.empty())
             for (std::size_t i = 0; i < flat_.card.size(); ++i) out.vertex.push_back(i);
-        out.offset.resize(out.vertex.size() + 1, 0);
+        out.offset.assign(out.vertex.size() + 1, 0);
         for (std::size_t i = 0; i < out.vertex.size(); ++i)
             out.offset[i + 1] = out.offset[i] + static_cast<std::size_t>(flat_.card[out.vertex[i]]);
         out.values_per_case = out.offset.back();
         void* dst;
-        if (opt.float_marginals) { out.marginals_f32.resize(out.n_cases * out.values_per_case); dst = out.marginals_f32.data(); }
-        else { out.marginals.resize(out.n_cases * out.values_per_case); dst = out.marginals.data(); }
+        if (opt.float_marginals) { out.marginals.resize(0); out.marginals_f32.resize(out.n_cases * out.values_per_case); dst = out.marginals_f32.data(); }
+        else { out.marginals_f32.resize(0); out.marginals.resize(out.n_cases * out.values_per_case); dst = out.marginals.data(); }
         out.sweeps.resize(out.n_cases);
         out.converged.resize(out.n_cases);
         bnbp_run_params prm = bnbp_run_params();
@@ -313,12 +330,12 @@ private:
         prm.damping = opt.damping;
         prm.check_interval = opt.check_interval;
         prm.out_precision = opt.float_marginals ? BNBP_OUT_FP32 : BNBP_OUT_DEFAULT;
+        prm.semiring = opt.semiring;
         prm.n_query = static_cast<std::int32_t>(query.size());
         prm.query_nodes = query.empty() ? nullptr : query.data();
         if (bnbp_run_batch(handle_, &ev, &prm, dst, out.sweeps.data(), out.converged.data()) != BNBP_OK)
             throw std::runtime_error(last_error("bnbp_run_batch"));
         if (!opt.devices.empty()) bnbp_get_summary(handle_, &out.summary);
-        return out;
     }
 
     // the map-returning overloads keep the reference's result shape: every vertex, double

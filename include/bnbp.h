@@ -102,7 +102,8 @@ typedef struct bnbp_options {
                                    shared memory runs init, every sweep, the stopping rule and the beliefs of a case in ONE
                                    launch, 32 cases per CTA, the node walk split over 4 warps; HBM sees evidence in and
                                    marginals out only.  0 = default (eligible networks, specialize == AUTO, hard evidence,
-                                   batches >= 4096 cases), 1 = always (error if impossible), -1 = never (streaming kernels) */
+                                   fixed sweep count without damping, batches >= 4096 cases), 1 = always (error if
+                                   impossible; also epsilon mode and damping), -1 = never (streaming kernels)            */
     int32_t reserved[4];
 } bnbp_options;
 
@@ -123,6 +124,7 @@ typedef struct bnbp_evidence {
 } bnbp_evidence;
 
 enum { BNBP_OUT_DEFAULT = 0, BNBP_OUT_FP64 = 1, BNBP_OUT_FP32 = 2 };
+enum { BNBP_SUM_PRODUCT = 0, BNBP_MAX_PRODUCT = 1 };
 
 typedef struct bnbp_run_params {
     double  epsilon;        /* stop a case when its delta < epsilon (reference default 0.001).
@@ -143,7 +145,11 @@ typedef struct bnbp_run_params {
     int32_t n_query;        /* > 0: only the marginals of query_nodes[0..n_query) are written, in that order: a row
                                is sum card[query_nodes[i]] values instead of sum r_X (0 = every node)   */
     const int32_t* query_nodes;   /* host array, read during the call                                   */
-    int32_t reserved[4];
+    int32_t semiring;       /* BNBP_SUM_PRODUCT (default: the reference, belief_propagation.hpp:174-266) or
+                               BNBP_MAX_PRODUCT (extension): every sum over parent configurations and
+                               child states becomes a maximum, beliefs are max-marginals (exact on polytrees); same
+                               schedule, normalisation and stopping rule.  Runs on the generic sweep kernel.        */
+    int32_t reserved[3];
 } bnbp_run_params;
 
 /* Convergence summary of a sharded run (the only collective besides the gather). */

@@ -42,6 +42,8 @@ typedef struct {
     int32_t* ched;           /* in-edge index (position in par[]) of that child edge */
     int64_t* voff;           /* per node offset into pi/lambda vectors, [n+1] */
     int64_t* moff;           /* per in-edge offset into message vectors (length card[parent]), [E+1] */
+    int32_t semiring;        /* 0 = the reference's sum-product; 1 = max-product (extension: every += over parent
+                                configurations / child states below becomes a maximum; fmax drops NaN) */
 } net_t;
 
 static int build_net(net_t* g)
@@ -105,7 +107,7 @@ static void calc_pi(const net_t* g, const state_t* s, int32_t x, double* out)
         for (int32_t i = 0; i < r; ++i) {
             double value = cpt[q * r + i];
             for (int32_t j = 0; j < k; ++j) value *= s->pmsg[g->moff[e0 + j] + s->cfg[j]];
-            out[i] += value;
+            if (g->semiring) out[i] = fmax(out[i], value); else out[i] += value;
         }
         for (int32_t j = k - 1; j >= 0; --j) {       /* odometer, last parent fastest (:286-290) */
             if (++s->cfg[j] < g->card[g->par[e0 + j]]) break;
@@ -155,7 +157,7 @@ static void calc_lambda_msg(const net_t* g, const state_t* s, int32_t x, int32_t
             double value = times * cpt[q * r + i];
             for (int32_t j = 0; j < k; ++j)
                 if (j != jt) value *= s->pmsg[g->moff[e0 + j] + s->cfg[j]];
-            out[s->cfg[jt]] += value;
+            if (g->semiring) out[s->cfg[jt]] = fmax(out[s->cfg[jt]], value); else out[s->cfg[jt]] += value;
             for (int32_t j = k - 1; j >= 0; --j) {
                 if (++s->cfg[j] < g->card[g->par[e0 + j]]) break;
                 s->cfg[j] = 0;
@@ -278,18 +280,19 @@ int bp_oracle_max_threads(void)
 #endif
 }
 
-/* Returns 0 on success.  out_marginals is [n_cases][sum card] row-major. */
-int bp_oracle_run(int32_t n_nodes, const int32_t* card, const int32_t* parent_off,
+/* Returns 0 on success.  out_marginals is [n_cases][sum card] row-major.  semiring: see net_t. */
+int bp_oracle_run_semiring(int32_t n_nodes, const int32_t* card, const int32_t* parent_off,
                   const int32_t* parents, const int64_t* cpt_off, const double* cpt,
                   int64_t n_cases, const int64_t* ev_off, const int32_t* ev_node,
                   const int32_t* ev_state, const int64_t* ev_val_off, const double* ev_values,
                   double eps, int32_t max_sweeps, double damping, int32_t check_interval,
-                  int32_t n_threads,
+                  int32_t n_threads, int32_t semiring,
                   double* out_marginals, int32_t* out_sweeps, uint8_t* out_converged)
 {
     net_t g;
     memset(&g, 0, sizeof g);
     g.n = n_nodes; g.card = card; g.poff = parent_off; g.par = parents; g.coff = cpt_off; g.cpt = cpt;
+    g.semiring = semiring;
     if (build_net(&g)) return -1;
     if (max_sweeps <= 0) max_sweeps = 1 << 30;
     if (check_interval <= 0) check_interval = 1;
@@ -323,6 +326,19 @@ int bp_oracle_run(int32_t n_nodes, const int32_t* card, const int32_t* parent_of
     }
     free_net(&g);
     return err;
+}
+
+int bp_oracle_run(int32_t n_nodes, const int32_t* card, const int32_t* parent_off,
+                  const int32_t* parents, const int64_t* cpt_off, const double* cpt,
+                  int64_t n_cases, const int64_t* ev_off, const int32_t* ev_node,
+                  const int32_t* ev_state, const int64_t* ev_val_off, const double* ev_values,
+                  double eps, int32_t max_sweeps, double damping, int32_t check_interval,
+                  int32_t n_threads,
+                  double* out_marginals, int32_t* out_sweeps, uint8_t* out_converged)
+{
+    return bp_oracle_run_semiring(n_nodes, card, parent_off, parents, cpt_off, cpt, n_cases, ev_off, ev_node, ev_state,
+                                  ev_val_off, ev_values, eps, max_sweeps, damping, check_interval, n_threads, 0,
+                                  out_marginals, out_sweeps, out_converged);
 }
 
 /* ------------------------------------------------------------------------------------------------

@@ -60,18 +60,18 @@ def port_max_threads() -> int:
     return int(_port.bp_oracle_max_threads())
 
 
-def run_port(net, ev, eps=1e-3, max_sweeps=0, damping=0.0, check_interval=1, threads=1):
-    """C restatement.  Returns (marginals [B, sum r], sweeps [B], converged [B])."""
+def run_port(net, ev, eps=1e-3, max_sweeps=0, damping=0.0, check_interval=1, threads=1, semiring=0):
+    """C restatement.  Returns (marginals [B, sum r], sweeps [B], converged [B]).  semiring=1: max-product."""
     global _port
     if _port is None:
         _port = C.CDLL(PORT_SO)
     out = np.empty((ev.n_cases, net.belief_values), dtype=np.float64)
     sweeps = np.empty(ev.n_cases, dtype=np.int32)
     conv = np.empty(ev.n_cases, dtype=np.uint8)
-    _port.bp_oracle_run.restype = C.c_int
-    rc = _port.bp_oracle_run(*_net_args(net), *_ev_args(ev), C.c_double(eps), C.c_int32(max_sweeps),
-                             C.c_double(damping), C.c_int32(check_interval), C.c_int32(threads),
-                             _ptr(out, C.c_double), _ptr(sweeps, C.c_int32), _ptr(conv, C.c_uint8))
+    _port.bp_oracle_run_semiring.restype = C.c_int
+    rc = _port.bp_oracle_run_semiring(*_net_args(net), *_ev_args(ev), C.c_double(eps), C.c_int32(max_sweeps),
+                                      C.c_double(damping), C.c_int32(check_interval), C.c_int32(threads), C.c_int32(semiring),
+                                      _ptr(out, C.c_double), _ptr(sweeps, C.c_int32), _ptr(conv, C.c_uint8))
     if rc != 0:
         raise RuntimeError("bp_oracle_run failed")
     return out, sweeps, conv

@@ -209,7 +209,7 @@ def test_onchip_full_size_alarm37_properties(BP, oracle_mod):
         {int(ev.ev_node[e]): int(ev.ev_state[e]) for e in range(ev.ev_off[c], ev.ev_off[c + 1])} for c in idx])
     om, _, _ = oracle_mod.run_port(net, sample, eps=0.0, max_sweeps=20, threads=0)
     assert_close(m[idx], om, what="alarm37 sample", **TOL["fp64"])
-    res = bp(ev, 1e-6, max_sweeps=200)
+    res = BP(net, onchip="always")(ev, 1e-6, max_sweeps=200)      # (the default takes the streaming kernels in epsilon mode)
     om, osw, ocv = oracle_mod.run_port(net, sample, eps=1e-6, max_sweeps=200, threads=0)
     assert np.array_equal(res.sweeps[idx], osw) and np.array_equal(res.converged[idx], ocv)
     assert_close(res.marginals[idx], om, what="alarm37 eps sample", **TOL["fp64"])

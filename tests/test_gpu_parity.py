@@ -218,3 +218,30 @@ def test_full_size_alarm37_properties(BP, oracle_mod):
         {int(ev.ev_node[e]): int(ev.ev_state[e]) for e in range(ev.ev_off[c], ev.ev_off[c + 1])} for c in idx])
     om, _, _ = oracle_mod.run_port(net, sample, eps=0.0, max_sweeps=20, threads=0)
     assert_close(m[idx], om, what="alarm37 sample", **TOL["fp64"])
+
+
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_max_product_matches_oracle(BP, oracle_mod, precision):
+    """bnbp_run_params.semiring = BNBP_MAX_PRODUCT (extension): polytree (exact max-marginals), loopy grid, a DAG with
+    4-parent nodes, fixed sweeps and the stopping rule; the default stays sum-product."""
+    nets = [("polytree60", synth.random_polytree(60, card_hi=4, seed=21), dict(p=0.15), 1e-8, 300),
+            ("grid8", synth.grid(8, seed=4), dict(p=0.1), 0.0, 25),
+            ("dag120", synth.random_dag(120, 4, 2, 5, seed=6), dict(p=0.1), 0.0, 10),
+            ("alarm37", synth.alarm37(), dict(exact_k=4), 1e-6, 200)]
+    for name, net, evkw, eps, cap in nets:
+        if precision == "fp32" and eps > 0:
+            continue
+        ev = synth.make_evidence(net, 300, seed=23, **evkw)
+        om, osw, ocv = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap, threads=0, semiring=1)
+        bp = BP(net, precision, dense_min_cpt=-1)
+        res = bp(ev, eps, max_sweeps=cap, semiring="max")
+        assert np.array_equal(res.sweeps, osw), (name, np.nonzero(res.sweeps != osw)[0][:5])
+        assert np.array_equal(res.converged, ocv), name
+        assert_close(res.marginals, om, what=f"max-product {name}", **TOL[precision])
+        sump = bp(ev, eps, max_sweeps=cap).marginals                 # the same handle still does sum-product
+        assert np.abs(sump - res.marginals).max() > 1e-4
+    # a handle whose large CPTs sit on the dense (matrix product) path refuses the max semiring
+    from bayesiannetwork_b200.engine import BnbpError
+    big = synth.high_card(6, card=16, n_parents=2, seed=9)
+    with pytest.raises(BnbpError):
+        BP(big, "fp64", dense_min_cpt=256)(synth.make_evidence(big, 8, p=0.2), 0.0, max_sweeps=3, semiring="max")

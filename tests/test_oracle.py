@@ -131,3 +131,37 @@ def test_torch_evidence_generator_is_bit_identical_to_numpy():
             o, nd, st = synth.make_evidence_torch(net, 300, p=0.1, case_offset=off, device="cpu", chunk_elems=20000)
             assert np.array_equal(a.ev_off, o.numpy()) and np.array_equal(a.ev_node, nd.numpy())
             assert np.array_equal(a.ev_state, st.numpy())
+
+
+def _max_marginals_brute_force(net, evidence):
+    """max over all completions of P(x, rest) for every (node, state): what max-product BP computes on a polytree."""
+    import itertools
+    best = [np.zeros(int(r)) for r in net.card]
+    for st in itertools.product(*[range(int(r)) for r in net.card]):
+        if any(st[n] != s for n, s in evidence.items()):
+            continue
+        p = 1.0
+        for x in range(net.n_nodes):
+            q = 0
+            for u in net.parents[net.parent_off[x]:net.parent_off[x + 1]]:
+                q = q * int(net.card[u]) + st[u]
+            p *= net.cpt[net.cpt_off[x] + q * int(net.card[x]) + st[x]]
+        for x in range(net.n_nodes):
+            best[x][st[x]] = max(best[x][st[x]], p)
+    return np.concatenate([b / b.sum() for b in best])
+
+
+def test_max_product_port_gives_max_marginals_on_polytrees(oracle_mod):
+    """The oracle's max-product switch (SURVEY 8 f4 extension; the reference is sum-product only): on a polytree the
+    normalised beliefs are the normalised max-marginals -- pinned by brute-force enumeration."""
+    net = synth.random_polytree(9, card_hi=3, max_parents=2, seed=5)
+    cases = [{}, {2: 1}, {0: 0, 7: 1}, {4: 0, 5: 1, 8: 0}]
+    cases = [{n: s % int(net.card[n]) for n, s in c.items()} for c in cases]
+    ev = EvidenceBatch.from_cases(net, cases)
+    got, sw, cv = oracle_mod.run_port(net, ev, eps=1e-13, max_sweeps=100, semiring=1)
+    assert cv.all()
+    for c, case in enumerate(cases):
+        assert_close(got[c], _max_marginals_brute_force(net, case), rtol=1e-10, atol=1e-13, what=f"max-marginals case {c}")
+    # and it is a different thing from the sum-product marginals
+    sump, _, _ = oracle_mod.run_port(net, ev, eps=1e-13, max_sweeps=100)
+    assert np.abs(sump - got).max() > 1e-3
