@@ -1216,7 +1216,15 @@ int enqueue_summary(bnbp_handle* h, const int32_t* d_sweeps, const uint8_t* d_co
         NCCL_TRY(NCCL(AllReduce)(d, d, 4, ncclUint64, ncclSum, h->comm, st));
         NCCL_TRY(NCCL(AllReduce)(d + 4, d + 4, 1, ncclUint64, ncclMax, h->comm, st));
     }
-    CU_TRY(cudaMemcpyAsync(h->pin_summary, d, 8 * 8, cudaMemcpyDeviceToHost, st));
+    return BNBP_OK;
+}
+
+// the totals into pinned host memory (its own step: inside an ncclGroupStart / ncclGroupEnd bracket the all-reduces are
+// only ENQUEUED at ncclGroupEnd, so a copy issued with them would overtake them -- r02c: a group of two devices
+// reported one device's share)
+int fetch_summary(bnbp_handle* h, cudaStream_t st)
+{
+    CU_TRY(cudaMemcpyAsync(h->pin_summary, h->d_summary.p, 8 * 8, cudaMemcpyDeviceToHost, st));
     return BNBP_OK;
 }
 
@@ -1797,6 +1805,7 @@ int run_group(bnbp_handle* g, const bnbp_evidence* ev, const bnbp_run_params* pr
     NCCL_TRY(NCCL(GroupEnd)());
     for (int i = 0; i < G; ++i) {
         CU_TRY(cudaSetDevice(g->members[(size_t)i]->device));
+        if ((rc = fetch_summary(g->members[(size_t)i], g->members[(size_t)i]->stream))) return rc;
         CU_TRY(wait_stream(g->members[(size_t)i]->stream));
     }
     read_summary(g->members[0], &g->last_summary);
@@ -1890,6 +1899,11 @@ int bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_hand
     if (smem > 48 * 1024) {
         cudaError_t e = h->precision == BNBP_FP32 ? set_smem<float>(h.get(), (int)smem) : set_smem<double>(h.get(), (int)smem);
         if (e != cudaSuccess) return fail(BNBP_ERR_CUDA, std::string("shared-memory opt-in: ") + cudaGetErrorString(e));
+    }
+    {   // the default output layout (every node): device tables exist before any communicator does
+        bnbp_run_params all_nodes;
+        memset(&all_nodes, 0, sizeof all_nodes);
+        if ((rc = set_query(h.get(), all_nodes))) return rc;
     }
     *out = h.release();
     return BNBP_OK;
@@ -2714,6 +2728,7 @@ int bnbp_comm_summary(bnbp_handle* h, const int32_t* d_sweeps, const uint8_t* d_
     CU_TRY(cudaSetDevice(h->device));
     cudaStream_t st = stream ? (cudaStream_t)stream : h->stream;
     if ((rc = enqueue_summary(h, d_sweeps, d_converged, n_cases, st))) return rc;
+    if ((rc = fetch_summary(h, st))) return rc;
     CU_TRY(wait_stream(st));
     read_summary(h, out);
     h->last_summary = *out;

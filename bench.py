@@ -286,7 +286,7 @@ def walk_flops(net) -> float:
 
 
 def measure_config(key, workload, total_cases, base_gpus, precision, parity_cases, binding, *, torch, dist, dev,
-                   local_rank, rank, world, with_cpu):
+                   local_rank, rank, world, with_cpu, hostpg=None):
     from bayesiannetwork_b200.engine import BeliefPropagation
     from bayesiannetwork_b200.flat import EvidenceBatch
     factory, _, evkw, sweeps = synth.WORKLOADS[workload]
@@ -308,15 +308,19 @@ def measure_config(key, workload, total_cases, base_gpus, precision, parity_case
     def step():
         bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=0.0, max_sweeps=sweeps, stream=stream)
 
-    def barrier():
-        if world > 1:
-            dist.barrier()
+    def barrier():                                       # host-side (gloo): see main()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=hostpg)
 
     t0 = time.perf_counter()
     step()                                               # warm-up (allocates the state arena)
     barrier()
     warm_s = time.perf_counter() - t0
+    if world > 1:                                        # every rank must take the same number of steps
+        t = torch.tensor([warm_s], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=hostpg)
+        warm_s = float(t[0])
     steps = 2 if warm_s < 5.0 else 1
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
@@ -331,9 +335,9 @@ def measure_config(key, workload, total_cases, base_gpus, precision, parity_case
     sweep_ms = (st["last_sweep_ms"] - dense_ms) / max(1, st["last_sweep_launches"])
     dense_ms_per_sweep = dense_ms / max(1, st["last_sweep_launches"])
     if world > 1:
-        t = torch.tensor([ms, sweep_ms, dense_ms_per_sweep], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, sweep_ms, dense_ms_per_sweep = (float(x) for x in t)
+        t = torch.tensor([ms, sweep_ms, dense_ms_per_sweep, float(steps)], dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX, group=hostpg)
+        ms, sweep_ms, dense_ms_per_sweep = (float(x) for x in t[:3])
     value = world * n * sweeps * steps / (ms * 1e-3)
     per_gpu = value / world
     peak, peak_src = measured_peaks()
@@ -453,6 +457,10 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "bnbp" else args.warmup
 
+    if os.environ.get("BNBP_BENCH_WATCHDOG"):
+        # debugging aid for multi-rank runs: every N seconds each rank prints where its Python threads are
+        import faulthandler
+        faulthandler.dump_traceback_later(int(os.environ["BNBP_BENCH_WATCHDOG"]), repeat=True, exit=False)
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -469,9 +477,17 @@ def main():
         raise SystemExit("bench.py: no CUDA device -- the bnbp path has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    hostpg = None
     if world > 1:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
+        # Barriers and the max-over-ranks of the timings go over a HOST group (gloo).  An NCCL barrier is a kernel that
+        # spins on the GPU until every rank has joined, and once peer access is on, a cudaMalloc on rank A (pinned / staging
+        # buffers of the e2e leg, a new handle per `configs` entry) waits for rank B's device -- which is spinning in the
+        # barrier waiting for A.  r02c: rank 0 does 200 ms of extra work (the N-rank = 1-rank check), rank 1 reached the next
+        # barrier first, and the run sat there until the NCCL watchdog fired.  The NCCL traffic of this bench is the
+        # library's own (gather + summary inside the timed step, no allocation anywhere near it).
+        hostpg = dist.new_group(backend="gloo")
 
     net, ev, sweeps = build_workload(args.workload, args.cases or None, rank, args.network or None)
     if args.network:
@@ -485,11 +501,11 @@ def main():
     gather = world > 1 and not args.no_gather
     if world > 1:
         # the communicator lives in libbnbp: rank 0 draws the id, torch.distributed only ships its 128 bytes
-        uid = torch.zeros(128, dtype=torch.uint8, device=dev)
+        uid = torch.zeros(128, dtype=torch.uint8)
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(BeliefPropagation.comm_unique_id()), dtype=torch.uint8))
-        dist.broadcast(uid, 0)
-        bp.comm_init(world, rank, bytes(uid.cpu().numpy().tobytes()))
+        dist.broadcast(uid, 0, group=hostpg)
+        bp.comm_init(world, rank, bytes(uid.numpy().tobytes()))
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
@@ -515,9 +531,17 @@ def main():
             summaries.append(bp.comm_summary(d_sw, d_cv, n, stream=stream))
 
     def barrier():
-        if world > 1:
-            dist.barrier()
         torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier(group=hostpg)
+
+    def reduce_host(values, op):
+        """max / sum over the ranks of a few host numbers (gloo)."""
+        if world == 1:
+            return list(values)
+        t = torch.tensor(list(values), dtype=torch.float64)
+        dist.all_reduce(t, op=op, group=hostpg)
+        return [float(x) for x in t]
 
     # nvidia-smi is started BEFORE the warm-up: its NVML initialisation takes driver locks and, started
     # right in front of the timed region, stalled the first timed launches by 7-70 ms (r01l); only the
@@ -525,6 +549,12 @@ def main():
     sampler = ClockSampler(local_rank) if rank == 0 else None
     if sampler:
         sampler.wait_first()
+    if world > 1:
+        # first call without the exchange: whatever the handle allocates on first use is allocated on every rank before
+        # any rank can sit in a collective (a cudaMalloc next to a peer's spinning NCCL kernel deadlocks, see hostpg above)
+        bp.run_device(n, d_off, d_node, d_state, d_out, epsilon=args.epsilon, max_sweeps=sweeps,
+                      out_sweeps=d_sw, out_converged=d_cv, stream=stream)
+        barrier()
     for _ in range(args.warmup):
         step()
     barrier()
@@ -546,9 +576,7 @@ def main():
     sweep_ms_per_launch = (st["last_sweep_ms"] - dense_ms) / max(1, st["last_sweep_launches"])
     dense_ms_per_sweep = dense_ms / max(1, st["last_sweep_launches"])
     if world > 1:
-        t = torch.tensor([ms, sweep_ms_per_launch, dense_ms_per_sweep], dtype=torch.float64, device=dev)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, sweep_ms_per_launch, dense_ms_per_sweep = float(t[0]), float(t[1]), float(t[2])
+        ms, sweep_ms_per_launch, dense_ms_per_sweep = reduce_host([ms, sweep_ms_per_launch, dense_ms_per_sweep], dist.ReduceOp.MAX)
     clocks = sampler.stop() if sampler else None
     multi_gpu = None
     if world > 1:
@@ -577,12 +605,12 @@ def main():
         # time-to-solution mode: count the sweeps each case actually executed (same every step)
         tot = torch.stack([d_sw.sum(dtype=torch.int64), (d_cv != 0).sum(dtype=torch.int64),
                            d_sw.max().to(torch.int64)])
+        tot = [float(x) for x in tot.tolist()]
         if world > 1:
-            mx = tot[2:].clone()
-            dist.all_reduce(tot, op=dist.ReduceOp.SUM)
-            dist.all_reduce(mx, op=dist.ReduceOp.MAX)
+            mx = reduce_host(tot[2:], dist.ReduceOp.MAX)
+            tot = reduce_host(tot, dist.ReduceOp.SUM)
             tot[2] = mx[0]
-        case_sweeps, n_conv, max_sw = (int(x) for x in tot.tolist())
+        case_sweeps, n_conv, max_sw = (int(x) for x in tot)
         value = case_sweeps * args.steps / (ms * 1e-3)
         eps_info = {"epsilon": args.epsilon, "max_sweeps": sweeps, "case_sweeps_per_step": case_sweeps,
                     "mean_sweeps_per_case": case_sweeps / (world * n), "max_sweeps_seen": max_sw,
@@ -702,10 +730,7 @@ def main():
         torch.cuda.synchronize()
         dt = time.perf_counter() - t0
         gc.enable()
-        if world > 1:
-            t = torch.tensor([dt], dtype=torch.float64, device=dev)
-            dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            dt = float(t[0])
+        dt = reduce_host([dt], dist.ReduceOp.MAX)[0]
         # context for the number: what the host link moves when it does nothing else (the marginals
         # are 8*V bytes per case; on PCIe this copy, not the kernels, bounds the host-buffer call)
         probe = torch.empty(n * V, dtype=torch.float64, device=dev)
@@ -742,11 +767,7 @@ def main():
                 handle(ev_pinned, args.epsilon, max_sweeps=sweeps, out_sweeps=sw_np, out_converged=cv_np, **kw)
             dtv = time.perf_counter() - t0
             gc.enable()
-            if world > 1:
-                t = torch.tensor([dtv], dtype=torch.float64, device=dev)
-                dist.all_reduce(t, op=dist.ReduceOp.MAX)
-                dtv = float(t[0])
-            return dtv
+            return reduce_host([dtv], dist.ReduceOp.MAX)[0]
         variants = []
         calls = 5
         q = np.unique(np.linspace(0, net.n_nodes - 1, min(8, net.n_nodes)).astype(np.int32))
@@ -820,7 +841,7 @@ def main():
             for precision in precisions:
                 configs.append(measure_config(key, workload, total, base_gpus, precision, samples[1 if world > 1 else 0], binding,
                                               torch=torch, dist=dist, dev=dev, local_rank=local_rank, rank=rank, world=world,
-                                              with_cpu=not args.no_cpu))
+                                              with_cpu=not args.no_cpu, hostpg=hostpg))
 
     if rank == 0:
         line = {

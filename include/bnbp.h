@@ -232,7 +232,12 @@ void  bnbp_host_free(void* p);
  * One process per device (torchrun, MPI): every rank creates an ordinary handle, rank 0 draws an id with
  * bnbp_comm_unique_id and ships it to the others by whatever means the launcher has, all call bnbp_comm_init;
  * bnbp_run_batch_device with bnbp_run_params.gather then leaves ALL marginals on every rank, and
- * bnbp_comm_summary all-reduces the per-case counts of the last run. */
+ * bnbp_comm_summary all-reduces the per-case counts of the last run.
+ * Allocation and collectives: an NCCL collective is a kernel that spins until every rank has joined, and with peer
+ * access on, a cudaMalloc on one rank waits for its peers' devices.  A handle allocates on the FIRST call of a given
+ * shape (state arena, staging); make that call without `gather` (or give every rank the same first call and no other
+ * allocating work around it), and synchronise the ranks on the host, not with an NCCL barrier, around phases that
+ * allocate (new handles, pinned buffers).  bench.py does both. */
 int  bnbp_create_multi(const bnbp_flat_network* net, const bnbp_options* opt, const int32_t* devices, int32_t n_devices,
                        bnbp_handle** out);
 int  bnbp_get_summary(const bnbp_handle* h, bnbp_summary* out);      /* of the last bnbp_run_batch of a group handle */

@@ -227,7 +227,10 @@ def test_max_product_matches_oracle(BP, oracle_mod, precision):
     nets = [("polytree60", synth.random_polytree(60, card_hi=4, seed=21), dict(p=0.15), 1e-8, 300),
             ("grid8", synth.grid(8, seed=4), dict(p=0.1), 0.0, 25),
             ("dag120", synth.random_dag(120, 4, 2, 5, seed=6), dict(p=0.1), 0.0, 10),
-            ("alarm37", synth.alarm37(), dict(exact_k=4), 1e-6, 200)]
+            ("alarm37", synth.alarm37(), dict(exact_k=4), 0.0, 12)]
+    # (loopy networks at fixed sweep counts: a maximum is not smooth -- where two configurations tie to rounding, which
+    #  one wins differs between evaluation orders and the difference is carried, not damped, through further sweeps;
+    #  after 37 sweeps of alarm37 in epsilon mode 2 of 31 500 entries were 4.7e-10 apart, r02c)
     for name, net, evkw, eps, cap in nets:
         if precision == "fp32" and eps > 0:
             continue
