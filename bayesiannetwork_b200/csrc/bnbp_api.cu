@@ -685,8 +685,10 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
     sa.eps = (T)prm.epsilon;
     sa.damping = (T)prm.damping;
     {
-        static const int prefetch = getenv("BNBP_PREFETCH") ? atoi(getenv("BNBP_PREFETCH")) : 1;   // tuning knob (A/B runs)
-        sa.prefetch = prefetch;
+        // next-node L2 prefetch: pays where a node is a handful of rows and the walk is pure latency (grid100, cardinality 2:
+        // +9 %, r02d), costs where a node has dozens of rows and the kernel already issues at 22 % (dag2000, cardinality <= 8: -10 %)
+        static const int knob = getenv("BNBP_PREFETCH") ? atoi(getenv("BNBP_PREFETCH")) : -1;      // tuning knob (A/B runs)
+        sa.prefetch = knob >= 0 ? knob : (h->rmax <= 4 ? 1 : 0);
     }
     T* delta = (T*)h->d_delta.p;
     const size_t smem = (size_t)BLOCK_THREADS * (size_t)h->scratch_vals * h->vec * sizeof(T);
@@ -1251,10 +1253,10 @@ int64_t wave_cases(const bnbp_handle* h, const bnbp_run_params& prm)
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
     int blocks = 4;
     if (h->run_onchip) {
-        // persistent grid: one "wave" = 8 rounds of 32 cases on every resident CTA
+        // persistent grid: one "wave" = 4 rounds of 32 cases on every resident CTA
         int nb = 1;
         for (int i = 0; i < 4; ++i) if (h->oc_state[i] == 1) nb = std::max(nb, h->oc[i].blocks_per_sm);
-        return (int64_t)sms * nb * 32 * 8;
+        return (int64_t)sms * nb * 32 * 4;
     }
     if (h->run_spec) {
         const bool plain = !(prm.epsilon > 0.0) && prm.damping == 0.0;
@@ -1314,6 +1316,36 @@ std::vector<int64_t> plan_chunks(int64_t n, int64_t wave, double rho)
     int64_t placed = 0;
     for (int64_t x : w) if (x > 0) { plan.push_back(x * wave); placed += x * wave; }
     plan.back() += n - placed;                         // the fraction of a wave that is left
+    return plan;
+}
+
+// Chunk sizes for the on-chip kernel, where the kernels of a batch and the copy of its marginals take about the same
+// time (alarm37 fp64: 15.5 ms vs 15.4 ms per 1M cases).  Two ends are exposed: the kernels of the FIRST chunk (nothing to
+// copy yet) and the copy of the LAST one (nothing left to compute), so the chunks grow and shrink again:
+// weights 1 2 3 4 5 4 3 2 1 in whole waves.  With the copy-bound plan of the streaming kernels (7 % + 14 % + 4 x 20 %) the
+// last copy alone was 3 ms of a 20.0 ms call (r02b).
+std::vector<int64_t> plan_chunks_balanced(int64_t n, int64_t wave)
+{
+    std::vector<int64_t> plan;
+    const int64_t W = wave > 0 ? n / wave : 0;
+    if (W < 3 || getenv("BNBP_ONE_CHUNK")) { plan.push_back(n); return plan; }
+    int k = 9;
+    if (const char* e = getenv("BNBP_CHUNKS")) k = std::max(1, atoi(e));
+    k = (int)std::min<int64_t>(k, W);
+    std::vector<double> w((size_t)k);
+    double sum = 0.0;
+    for (int i = 0; i < k; ++i) { w[(size_t)i] = 1.0 + std::min(i, k - 1 - i); sum += w[(size_t)i]; }
+    int64_t placed = 0;
+    for (int i = 0; i < k; ++i) {
+        int64_t waves = std::max<int64_t>(1, (int64_t)std::llround(w[(size_t)i] / sum * (double)W));
+        if (placed + waves * wave > n) waves = std::max<int64_t>(0, (n - placed) / wave);
+        if (waves == 0) break;
+        plan.push_back(waves * wave);
+        placed += waves * wave;
+    }
+    if (plan.empty()) { plan.push_back(n); return plan; }
+    // the remainder joins the largest chunk (the middle one): neither end grows
+    *std::max_element(plan.begin(), plan.end()) += n - placed;
     return plan;
 }
 
@@ -2082,9 +2114,10 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     char* const mine = base + (gather ? (size_t)h->comm_rank * (size_t)ev->n_cases * row_bytes : 0);
     int64_t step_cases = h->run_onchip ? ev->n_cases : h->cap;            // on chip: no resident state arena, one launch
     if (exchange) {
-        // 4 chunks of >= 8 MB each when the batch allows it (launch latency of the collective vs overlap)
+        // 8 chunks of >= 8 MB each when the batch allows it: the exchange of chunk i hides behind the kernels of chunk
+        // i+1, so what stays exposed is the last chunk's -- 1/8 of (world-1)/world x the marginals over NVLink
         const int64_t min_cases = std::max<int64_t>(32, (int64_t)((8u << 20) / std::max<size_t>(1, row_bytes)));
-        int64_t per = std::max(min_cases, (ev->n_cases + 3) / 4);
+        int64_t per = std::max(min_cases, (ev->n_cases + 7) / 8);
         per = (per + 31) / 32 * 32;
         step_cases = std::min(step_cases, per);
     }
@@ -2188,8 +2221,8 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     const size_t out_elem = out_f32 ? 4 : 8;
     double rho = ((double)h->Vout * (double)out_elem / (h->link_gbs * 1e9)) /
                  std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / (h->hbm_gbs * 1e9));
-    if (h->run_onchip) rho = 2.0;                          // the kernel moves ~1 KB per case: the call is bound by the copy
-    std::vector<int64_t> plan = plan_chunks(ev->n_cases, wave, rho);
+    if (h->run_onchip) rho = 1.0;                          // the kernel moves ~1 KB per case: kernels and copy take about the same time
+    std::vector<int64_t> plan = h->run_onchip ? plan_chunks_balanced(ev->n_cases, wave) : plan_chunks(ev->n_cases, wave, rho);
     if (prm->epsilon > 0.0 && plan.size() > 2 && !getenv("BNBP_CHUNKS") && !h->run_onchip) {
         // eps mode: the host waits inside every chunk (termination census), so chunks do not overlap each
         // other's kernels, only the copy of the chunk before; two chunks (~60/40 in whole waves) keep the

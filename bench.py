@@ -858,6 +858,7 @@ def main():
                        "kernel_family": ("on-chip multi-sweep (NVRTC sm_100a, state in shared memory)" if onchip else
                                          "network-specialised (NVRTC sm_100a)" if st["last_specialised"] else "generic"),
                        "cases_per_tile": int(st["cases_per_tile"]),
+                       "spec_compile_ms": st["spec_compile_ms"],     # NVRTC time this handle paid (0: every kernel came from the cubin cache)
                        "l2": (f"on-chip kernel: no state in HBM; evidence in + marginals out = {(ev.nbytes() + n * V * tsize) / 1e9:.2f} GB per step vs 126 MB of L2"
                               if onchip else
                               f"inputs larger than L2: {st['resident_cases'] * (S + net.msg_values) * tsize / 1e9:.2f} GB "
