@@ -40,6 +40,7 @@ struct Api {
     decltype(&::ncclAllReduce) AllReduce = nullptr;
     decltype(&::ncclBroadcast) Broadcast = nullptr;
     decltype(&::ncclCommDestroy) CommDestroy = nullptr;
+    decltype(&::ncclCommAbort) CommAbort = nullptr;
     decltype(&::ncclCommInitAll) CommInitAll = nullptr;
     decltype(&::ncclCommInitRank) CommInitRank = nullptr;
     decltype(&::ncclGetErrorString) GetErrorString = nullptr;
@@ -63,6 +64,7 @@ static Api& api()
         BNBP_NCCL_SYM(AllReduce, "ncclAllReduce")
         BNBP_NCCL_SYM(Broadcast, "ncclBroadcast")
         BNBP_NCCL_SYM(CommDestroy, "ncclCommDestroy")
+        BNBP_NCCL_SYM(CommAbort, "ncclCommAbort")
         BNBP_NCCL_SYM(CommInitAll, "ncclCommInitAll")
         BNBP_NCCL_SYM(CommInitRank, "ncclCommInitRank")
         BNBP_NCCL_SYM(GetErrorString, "ncclGetErrorString")
@@ -1950,7 +1952,9 @@ void bnbp_destroy(bnbp_handle* h)
         return;
     }
     cudaSetDevice(h->device);
-    if (h->comm) { NCCL(CommDestroy)(h->comm); h->comm = nullptr; }
+    // ncclCommAbort, not ncclCommDestroy: destroying flushes the communicator WITH the peers and blocks until they join,
+    // so a rank that leaves early (an error, an exception unwinding through the handle) would hang instead of exiting
+    if (h->comm) { if (h->stream) cudaStreamSynchronize(h->stream); NCCL(CommAbort)(h->comm); h->comm = nullptr; }
     if (h->comm_stream) { cudaStreamSynchronize(h->comm_stream); cudaStreamDestroy(h->comm_stream); }
     for (cudaEvent_t e : h->ev_comm) cudaEventDestroy(e);
     if (h->pin_summary) cudaFreeHost(h->pin_summary);

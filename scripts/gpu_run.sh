@@ -20,7 +20,7 @@ for step in "$@"; do
   echo "=== $step"
   case $kind in
     tests)
-      timeout 1500 python -m pytest ${rest:-tests} -m gpu -x -q > ${out}_pytest_gpu.log 2>&1; tail -n 6 ${out}_pytest_gpu.log ;;
+      timeout 1500 python -m pytest ${rest:-tests} -m gpu -x -q --durations=15 > ${out}_pytest_gpu.log 2>&1; tail -n 24 ${out}_pytest_gpu.log ;;
     bench)
       name=${rest%%:*}; args=${rest#*:}; [ "$args" == "$rest" ] && args=""; name=${name:-default}
       timeout 900 python bench.py $args > ${out}_bench_${name}.json 2> ${out}_bench_${name}.err; cut -c1-400 ${out}_bench_${name}.json; tail -n 3 ${out}_bench_${name}.err ;;
