@@ -12,8 +12,10 @@ from concurrent.futures import ThreadPoolExecutor
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIBDIR = os.path.join(HERE, "lib")
-OBJDIR = os.path.join(LIBDIR, "obj")
-LIB = os.path.join(LIBDIR, "libbnbp.so")
+# BNBP_BUILD_TAG: an alternative build next to the product library (kernel-tuning A/B runs pick it with BNBP_LIB)
+_TAG = os.environ.get("BNBP_BUILD_TAG", "")
+OBJDIR = os.path.join(LIBDIR, "obj" + ("_" + _TAG if _TAG else ""))
+LIB = os.path.join(LIBDIR, "libbnbp" + ("_" + _TAG if _TAG else "") + ".so")
 SPEC_SRC = os.path.join(CSRC, "bnbp_spec.cuh")           # compiled at run time by NVRTC ...
 SPEC_EMBED = os.path.join(CSRC, "bnbp_spec_embed.inc")   # ... from this generated raw-string copy
 ONCHIP_SRC = os.path.join(CSRC, "bnbp_onchip.cuh")       # the on-chip multi-sweep kernel, appended behind it
@@ -98,7 +100,7 @@ def build(force: bool = False, verbose: bool = False, extra=()) -> str:
 
     def compile_one(u):
         src, obj, defs = u
-        tune = [f"-DBNBP_MINB={os.environ['BNBP_MINB']}"] if os.environ.get("BNBP_MINB") else []
+        tune = [f"-DBNBP_GEN_MINB={os.environ['BNBP_GEN_MINB']}"] if os.environ.get("BNBP_GEN_MINB") else []
         cmd = [nvcc, *NVCC_FLAGS, *extra, *defs, *tune, "-c", "-o", obj, src]
         r = subprocess.run(cmd, env=_env(), capture_output=True, text=True)
         if r.returncode != 0:

@@ -208,6 +208,7 @@ struct bnbp_handle {
     SpecKernel oc[4];
     int oc_state[4] = {0, 0, 0, 0};    // 0 untried, 1 loaded, -1 failed
     bool run_onchip = false;           // this run: the whole case (init, every sweep, beliefs) in one on-chip kernel
+    int reserve_sms = 0;               // this run: SMs the on-chip grid leaves to the concurrent NCCL exchange (gather)
     int last_onchip = 0;
     double oc_imbalance = 1.0;         // busiest role / mean role cost of the node partition
     double spec_compile_ms = 0.0;
@@ -1025,6 +1026,7 @@ int run_onchip(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_
     a.interval = prm.check_interval > 0 ? prm.check_interval : 1;
     int sms = 148;
     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+    a.first_reserved_sm = sms - std::min(std::max(0, h->reserve_sms), sms / 2);
     const int64_t groups = (n + 31) / 32;
     const unsigned blocks = (unsigned)std::min<int64_t>(groups, (int64_t)sms * std::max(1, k.blocks_per_sm));
     if ((int)h->ev_sweep.size() < 2 * (h->ev_sweep_used + 1)) {
@@ -2114,6 +2116,13 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
     const bool gather = prm->gather != 0;
     if (gather && (!h->comm || h->comm_world < 1)) return fail(BNBP_ERR_INVALID, "gather needs a communicator (bnbp_comm_init)");
     const bool exchange = gather && h->comm_world > 1;
+    // SMs left to the exchange while the on-chip grid runs: 4 per peer, at most 16 (5 % of the SMs at N >= 5); the
+    // collective of chunk i then really runs beside the kernels of chunk i+1
+    h->reserve_sms = 0;
+    if (exchange) {
+        h->reserve_sms = std::min(16, 4 * (h->comm_world - 1));
+        if (const char* e = getenv("BNBP_GATHER_SMS")) h->reserve_sms = std::max(0, atoi(e));
+    }
     char* const base = (char*)out_marginals;
     char* const mine = base + (gather ? (size_t)h->comm_rank * (size_t)ev->n_cases * row_bytes : 0);
     int64_t step_cases = h->run_onchip ? ev->n_cases : h->cap;            // on chip: no resident state arena, one launch
@@ -2209,6 +2218,7 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     h->ev_dense_used = 0;
     h->last_compactions = 0;
     if (ev->n_cases == 0) return BNBP_OK;
+    h->reserve_sms = 0;
     if ((rc = set_query(h, *prm))) return rc;
     if ((rc = choose_kernels(h, ev->n_cases, *prm, soft, !out_f32))) return rc;
     if ((rc = measure_rates(h))) return rc;

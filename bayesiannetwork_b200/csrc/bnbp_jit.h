@@ -112,6 +112,7 @@ template <typename T> struct OnchipArgs {
     T damping;
     int max_sweeps;
     int interval;
+    int first_reserved_sm;
 };
 
 // <<<blocks, threads, smem, st>>> bnbp_onchip_run(args)

@@ -56,6 +56,7 @@ struct OcArgs {                         // mirrors OnchipArgs in bnbp_jit.h
     T damping;
     int max_sweeps;
     int interval;                       // convergence tested every interval-th sweep (1 = reference)
+    int first_reserved_sm;              // CTAs that land on an SM with %smid >= this leave at once (>= #SMs: none)
 };
 
 constexpr int ROLES = BNBP_ROLES;
@@ -115,6 +116,16 @@ bnbp_onchip_run(const bnbp_spec::OcArgs a)
     T* const s_delta = s_msg + (long long)BNBP_M * 32;                        // [ROLES][32]
     long long* const s_case = reinterpret_cast<long long*>(s_delta + ROLES * 32);       // [32]
 
+    // Compute / communication split of the SMs (gather runs).  This grid is persistent and fills every SM (two
+    // groups = 226 KB of shared memory, 64 K registers), so a concurrent NCCL kernel -- the exchange of the previous chunk's
+    // marginals -- finds no SM to run on and the "overlap" degenerates into a queue (r02f: +1.27 ms per step at N = 2, the
+    // full serial cost).  The CTAs that land on the last few SMs therefore leave at once; the ticket counter hands their
+    // share of the cases to the others, and the collective has those SMs to itself.
+    {
+        unsigned smid;
+        asm("mov.u32 %0, %%smid;" : "=r"(smid));
+        if ((int)smid >= a.first_reserved_sm) return;
+    }
     const int lane = threadIdx.x & 31;
     const int role = threadIdx.x >> 5;
     const bool eps_mode = a.eps > T(0);

@@ -238,8 +238,11 @@ __device__ __forceinline__ void parent_group(ParentCtx<T, VEC, RMAX, MAXP>& pc, 
 template <typename T> __device__ __forceinline__ T recip(T s) { return T(1) / s; }
 
 // ------------------------------------------------------------------------------------------------
+#ifndef BNBP_GEN_MINB
+#define BNBP_GEN_MINB 1        // tuning knob (an alternative build, selected with BNBP_LIB): resident blocks per SM asked of ptxas
+#endif
 template <typename T, int VEC, int RMAX, int KNET, bool FREEZE, bool CHECK, bool MAXP = false>
-__global__ void __launch_bounds__(BLOCK)
+__global__ void __launch_bounds__(BLOCK, BNBP_GEN_MINB)
 sweep_kernel(const SweepArgs<T> a)
 {
     extern __shared__ __align__(16) unsigned char smem_raw[];

@@ -516,7 +516,15 @@ def main():
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(BeliefPropagation.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0, group=hostpg)
-        bp.comm_init(world, rank, bytes(uid.numpy().tobytes()))
+        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the ONE JSON line
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
+        try:
+            bp.comm_init(world, rank, bytes(uid.numpy().tobytes()))
+        finally:
+            os.dup2(saved_stdout, 1)
+            os.close(saved_stdout)
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
