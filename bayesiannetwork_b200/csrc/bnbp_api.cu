@@ -2155,7 +2155,16 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
                 h->ev_comm.push_back(e);
             }
             CU_TRY(cudaEventRecord(h->ev_comm[(size_t)n_chunk + 1], st));
-            CU_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_comm[(size_t)n_chunk + 1], 0));
+        }
+    }
+    if (exchange) {
+        // the collectives are enqueued AFTER all the kernels: an ncclGroupEnd costs the host ~0.1 ms, and issued between
+        // two chunks it left the compute stream empty for that long, eight times per batch (r02g: the exchange cost its
+        // full serial time whatever the SM split).  Each group waits for the event of its chunk on the library's own stream.
+        int i = 0;
+        for (int64_t c0 = 0; c0 < ev->n_cases; c0 += step_cases, ++i) {
+            const int64_t n = std::min<int64_t>(step_cases, ev->n_cases - c0);
+            CU_TRY(cudaStreamWaitEvent(h->comm_stream, h->ev_comm[(size_t)i + 1], 0));
             NCCL_TRY(NCCL(GroupStart)());
             for (int r = 0; r < h->comm_world; ++r) {
                 char* const slot = base + ((size_t)r * (size_t)ev->n_cases + (size_t)c0) * row_bytes;
@@ -2163,8 +2172,6 @@ int bnbp_run_batch_device(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_ru
             }
             NCCL_TRY(NCCL(GroupEnd)());
         }
-    }
-    if (exchange) {
         // whatever follows on `st` sees every rank's rows
         CU_TRY(cudaEventRecord(h->ev_comm[0], h->comm_stream));
         CU_TRY(cudaStreamWaitEvent(st, h->ev_comm[0], 0));
