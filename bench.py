@@ -12,7 +12,7 @@ One "step" = one pass of the hot path over one batch of synthetic evidence cases
           evidence in and host marginals out, copies inside the timed region.
 Multi-GPU: one process per GPU, cases sharded by contiguous ranges (weak scaling: every rank runs
 the full per-GPU batch), no data-path collective; NCCL only all-reduces the sweep / convergence
-summary each step (and all-gathers marginals with --gather).
+summary each step; a second timed pass gathers the marginals inside the library (config.multi_gpu.with_gather).
 """
 from __future__ import annotations
 
@@ -456,8 +456,8 @@ def main():
     ap.add_argument("--dense-tensor", type=int, default=0,
                     help="fp32: dense products on the tensor cores (0 = library default, 1 = every product, -1 = never)")
     ap.add_argument("--no-gather", action="store_true",
-                    help="N > 1: skip the gather of the marginals (default: every rank ends a step with ALL marginals, "
-                         "exchanged over NCCL inside bnbp_run_batch_device)")
+                    help="N > 1: skip the second timed pass in which every rank ends a step with ALL marginals "
+                         "(exchanged over NCCL inside bnbp_run_batch_device) and the N-rank = 1-rank check that uses it")
     ap.add_argument("--onchip", default="auto", choices=["auto", "always", "never"],
                     help="the on-chip multi-sweep kernel (state in shared memory for all sweeps)")
     ap.add_argument("--no-e2e", action="store_true")
@@ -532,7 +532,7 @@ def main():
     d_state = torch.from_numpy(ev.ev_state).to(dev)
     # with the gather every rank holds [world * n, V]; its own kernels write rows [rank * n, (rank + 1) * n) in place
     gathered = torch.empty((world * n, V), dtype=tdtype, device=dev) if gather else None
-    d_out = gathered[rank * n:(rank + 1) * n] if gather else torch.empty((n, V), dtype=tdtype, device=dev)
+    d_out = torch.empty((n, V), dtype=tdtype, device=dev)
     d_sw = torch.empty(n, dtype=torch.int32, device=dev)
     d_cv = torch.empty(n, dtype=torch.uint8, device=dev)
     summaries = []
@@ -541,11 +541,14 @@ def main():
     torch.cuda.set_stream(tstream)
     stream = tstream.cuda_stream
 
-    def step():
-        # the only collectives of the path, both inside libbnbp (NCCL): the gather of the marginals, chunk by chunk
-        # behind the kernels of the next chunk, and the all-reduce of the convergence summary
-        bp.run_device(n, d_off, d_node, d_state, gathered if gather else d_out, epsilon=args.epsilon, max_sweeps=sweeps,
-                      out_sweeps=d_sw, out_converged=d_cv, stream=stream, gather=gather)
+    def step(with_gather=False):
+        # The collectives of the path live in libbnbp (NCCL).  Every step ends with the all-reduce of the convergence summary;
+        # the marginals stay sharded on the GPU that computed them ("leave marginals sharded and gather on
+        # demand") in the headline steps, and a second timed pass below runs the same step WITH the gather inside
+        # bnbp_run_batch_device, so the line carries both numbers.
+        g = with_gather and gather
+        bp.run_device(n, d_off, d_node, d_state, gathered if g else d_out, epsilon=args.epsilon, max_sweeps=sweeps,
+                      out_sweeps=d_sw, out_converged=d_cv, stream=stream, gather=g)
         if world > 1:
             summaries.append(bp.comm_summary(d_sw, d_cv, n, stream=stream))
 
@@ -588,6 +591,24 @@ def main():
     barrier()
     ms = e0.elapsed_time(e1)
     st = bp.stats()
+    gather_pass = None
+    if gather:
+        # the same step with the gather of the marginals inside the call (every rank ends it with ALL marginals)
+        g_steps = max(3, args.steps // 2)
+        for _ in range(2):
+            step(with_gather=True)
+        barrier()
+        g0, g1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        g0.record()
+        for _ in range(g_steps):
+            step(with_gather=True)
+        g1.record()
+        barrier()
+        g_ms = reduce_host([g0.elapsed_time(g1)], dist.ReduceOp.MAX)[0]
+        gather_pass = {"steps": g_steps, "ms_per_step": g_ms / g_steps,
+                       "value": (None if args.epsilon > 0 else world * n * sweeps * g_steps / (g_ms * 1e-3)), "unit": UNIT,
+                       "gathered_bytes_per_step_per_rank": int(world * n * V * tsize),
+                       "received_bytes_per_step_per_rank": int((world - 1) * n * V * tsize)}
     launches_per_step = int(st["last_kernel_launches"])
     # the library's own CUDA events: around all sweeps of the last step, and around the dense
     # contraction launches inside them (nodes with large CPTs; 0 for the other workloads)
@@ -601,8 +622,12 @@ def main():
     if world > 1:
         # the N-rank sharded run equals a 1-rank run: rank 0 recomputes, on its own GPU, the first cases of EVERY rank's
         # shard (evidence is a function of the case index) and compares them with the rows the gather delivered
-        multi_gpu = {"summary_all_reduce": summaries[-1] if summaries else None, "collectives": "ncclAllReduce (summary) + grouped ncclBroadcast "
-                     "per rank and chunk (gather), issued by libbnbp on its own stream", "gathered_bytes_per_step": int(world * n * V * tsize) if gather else 0}
+        multi_gpu = {"summary_all_reduce": summaries[-1] if summaries else None,
+                     "collectives": "every step: ncclAllReduce of the convergence summary; gather pass: grouped ncclBroadcast per rank and "
+                                    "chunk, all issued by libbnbp (the timed headline steps keep the marginals sharded)",
+                     "with_gather": gather_pass}
+        if gather_pass:
+            gather_pass["cost_ms_per_step"] = gather_pass["ms_per_step"] - ms / args.steps
         if gather and rank == 0 and not args.network:
             # 4096 cases per rank: the recomputation takes the same kernel family as the batch (the on-chip kernel from
             # 4096 cases up; 256 cases would run the generic kernel, whose rounding differs in the last bits)
