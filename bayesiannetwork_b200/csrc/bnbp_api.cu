@@ -1324,32 +1324,21 @@ std::vector<int64_t> plan_chunks(int64_t n, int64_t wave, double rho)
 }
 
 // Chunk sizes for the on-chip kernel, where the kernels of a batch and the copy of its marginals take about the same
-// time (alarm37 fp64: 15.5 ms vs 15.4 ms per 1M cases).  Two ends are exposed: the kernels of the FIRST chunk (nothing to
-// copy yet) and the copy of the LAST one (nothing left to compute), so the chunks grow and shrink again:
-// weights 1 2 3 4 5 4 3 2 1 in whole waves.  With the copy-bound plan of the streaming kernels (7 % + 14 % + 4 x 20 %) the
-// last copy alone was 3 ms of a 20.0 ms call (r02b).
+// time (alarm37 fp64: 15.2 ms vs 15.4 ms per 1M cases).  With equal rates the copy of chunk i runs beside the kernels of
+// chunk i+1 and the call costs T/k + T: EQUAL chunks, as many as the launch overhead allows (14 of two waves each for 1M
+// cases).  Measured: the copy-bound plan of the streaming kernels (7 % + 14 % + 4 x 20 %) 19.8 ms per call, a grow-and-shrink
+// plan (1 2 3 4 5 4 3 2 1) 20.9 ms -- the copy engine waits while the chunks grow and falls behind when they shrink (r02d, r02i).
 std::vector<int64_t> plan_chunks_balanced(int64_t n, int64_t wave)
 {
     std::vector<int64_t> plan;
     const int64_t W = wave > 0 ? n / wave : 0;
     if (W < 3 || getenv("BNBP_ONE_CHUNK")) { plan.push_back(n); return plan; }
-    int k = 9;
+    int64_t k = std::min<int64_t>(16, (W + 1) / 2);            // two waves per chunk, at most 16 chunks
     if (const char* e = getenv("BNBP_CHUNKS")) k = std::max(1, atoi(e));
-    k = (int)std::min<int64_t>(k, W);
-    std::vector<double> w((size_t)k);
-    double sum = 0.0;
-    for (int i = 0; i < k; ++i) { w[(size_t)i] = 1.0 + std::min(i, k - 1 - i); sum += w[(size_t)i]; }
-    int64_t placed = 0;
-    for (int i = 0; i < k; ++i) {
-        int64_t waves = std::max<int64_t>(1, (int64_t)std::llround(w[(size_t)i] / sum * (double)W));
-        if (placed + waves * wave > n) waves = std::max<int64_t>(0, (n - placed) / wave);
-        if (waves == 0) break;
-        plan.push_back(waves * wave);
-        placed += waves * wave;
-    }
-    if (plan.empty()) { plan.push_back(n); return plan; }
-    // the remainder joins the largest chunk (the middle one): neither end grows
-    *std::max_element(plan.begin(), plan.end()) += n - placed;
+    k = std::max<int64_t>(1, std::min(k, W));
+    const int64_t per = (W / k) * wave;                       // whole waves; the last chunk takes the remainder
+    for (int64_t i = 0; i < k; ++i) plan.push_back(per);
+    plan.back() += n - per * k;
     return plan;
 }
 
@@ -1780,7 +1769,10 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         // ---- on-chip kernel: the state of a 32-case group (pi/lambda + both message buffers) must fit the
         //      shared memory of one CTA
         constexpr size_t SMEM_OPTIN = 227 * 1024;
-        h->oc_roles = 4;
+        // warps per group: 6 in fp64 (1 439 M case-sweeps/s on alarm37 against 1 377 M with 4 and 1 398 M with 8, r02i: more
+        // warps hide more of the instruction-fetch latency until the busiest role -- node 28 alone is a quarter of the
+        // arithmetic -- sets the pace); 4 in fp32, where four groups per SM leave 128 registers per thread
+        h->oc_roles = h->precision == BNBP_FP32 ? 4 : 6;
         if (const char* ev = getenv("BNBP_OC_ROLES")) h->oc_roles = std::min(16, std::max(1, atoi(ev)));
         h->oc_ahead = 1;
         if (const char* ev = getenv("BNBP_OC_AHEAD")) h->oc_ahead = std::min(4, std::max(0, atoi(ev)));

@@ -11,7 +11,7 @@
 //   * the group is walked by BNBP_ROLES warps: lane = case, warp = a fixed subset of the nodes (longest-
 //     processing-time partition of the per-node cost, made by the network compiler).  Every warp runs the
 //     fully unrolled straight-line code of ITS nodes (the node arithmetic of bnbp_spec.cuh, CPT entries as
-//     constant-bank operands), so the 4 schedulers of the SM work on different nodes of the same 32 cases;
+//     constant-bank operands), so the schedulers of the SM work on different nodes of the same 32 cases;
 //   * a sweep has two phases.  A: every warp reads the inbox of its nodes (the time-t messages addressed to them)
 //     into registers; barrier; B: it computes its nodes and overwrites the inboxes of their neighbours with the
 //     time-(t+1) messages; barrier.  All four updates read time-t state only (:75-101), so this IS the Jacobi
@@ -23,7 +23,7 @@
 //     rcp_norm): 40 % fewer instructions per sweep;
 //   * the convergence test (:105-131,:147) is free: each warp reduces |new - old| over the messages it emits in
 //     registers (the old value is the word it is about to overwrite), the per-case maximum over the warps goes
-//     through 4 x 32 shared-memory words at the sweep barrier;
+//     through ROLES x 32 shared-memory words at the sweep barrier;
 //   * a lane whose case has stopped (delta < epsilon, or the sweep cap) is frozen; once 8 lanes of the group wait
 //     (or nothing else runs) they write their marginals, take the next cases from a global ticket counter, load
 //     their evidence and start over at sweep 0 while the other lanes carry on: in epsilon mode no lane waits for

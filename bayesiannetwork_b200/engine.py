@@ -133,6 +133,8 @@ class BeliefPropagation:
         ev = evidence
         q = None if query_nodes is None else np.ascontiguousarray(query_nodes, dtype=np.int32)
         n = ev.n_cases
+        if q is not None and q.size and (int(q.min()) < 0 or int(q.max()) >= self.net.n_nodes):
+            raise BnbpError(1, "query node id out of range")
         V = self.net.belief_values if q is None or q.size == 0 else int(self.net.card[q].sum())
         out_dtype = np.dtype(out_dtype)
         if out is None:
