@@ -1336,9 +1336,12 @@ std::vector<int64_t> plan_chunks_balanced(int64_t n, int64_t wave)
     int64_t k = std::min<int64_t>(16, (W + 1) / 2);            // two waves per chunk, at most 16 chunks
     if (const char* e = getenv("BNBP_CHUNKS")) k = std::max(1, atoi(e));
     k = std::max<int64_t>(1, std::min(k, W));
-    const int64_t per = (W / k) * wave;                       // whole waves; the last chunk takes the remainder
-    for (int64_t i = 0; i < k; ++i) plan.push_back(per);
-    plan.back() += n - per * k;
+    // W whole waves over k chunks, as evenly as they divide (the first W % k chunks get one more); the last chunk also
+    // takes the cases beyond the last whole wave (< 1 wave).  (r02j: the remainder of W / k went to the last chunk, which
+    // then held half the batch -- 25 ms per call instead of 17.)
+    const int64_t base = W / k, extra = W % k;
+    for (int64_t i = 0; i < k; ++i) plan.push_back((base + (i < extra ? 1 : 0)) * wave);
+    plan.back() += n - W * wave;
     return plan;
 }
 
@@ -2235,7 +2238,14 @@ int bnbp_run_batch(bnbp_handle* h, const bnbp_evidence* ev, const bnbp_run_param
     double rho = ((double)h->Vout * (double)out_elem / (h->link_gbs * 1e9)) /
                  std::max(1e-12, sweeps_est * 2.0 * (double)(h->PL + h->M) * (double)h->tsize / (h->hbm_gbs * 1e9));
     if (h->run_onchip) rho = 1.0;                          // the kernel moves ~1 KB per case: kernels and copy take about the same time
-    std::vector<int64_t> plan = h->run_onchip ? plan_chunks_balanced(ev->n_cases, wave) : plan_chunks(ev->n_cases, wave, rho);
+    std::vector<int64_t> plan;
+    if (h->run_onchip) {
+        // equal chunks (plan_chunks_balanced); BNBP_OC_PLAN=ramp (tuning knob): the copy-bound plan of the streaming kernels
+        const char* mode = getenv("BNBP_OC_PLAN");
+        plan = (mode && !strcmp(mode, "ramp")) ? plan_chunks(ev->n_cases, 2 * wave, 2.0) : plan_chunks_balanced(ev->n_cases, wave);
+    } else {
+        plan = plan_chunks(ev->n_cases, wave, rho);
+    }
     if (prm->epsilon > 0.0 && plan.size() > 2 && !getenv("BNBP_CHUNKS") && !h->run_onchip) {
         // eps mode: the host waits inside every chunk (termination census), so chunks do not overlap each
         // other's kernels, only the copy of the chunk before; two chunks (~60/40 in whole waves) keep the
