@@ -489,7 +489,13 @@ def main():
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
     hostpg = None
+    saved_stdout = None
     if world > 1:
+        # stdout carries ONE JSON line: NCCL prints its version banner there when its first communicator starts working,
+        # so until that line is printed, file descriptor 1 points at stderr
+        sys.stdout.flush()
+        saved_stdout = os.dup(1)
+        os.dup2(2, 1)
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", rank=rank, world_size=world, device_id=dev)
         # Barriers and the max-over-ranks of the timings go over a HOST group (gloo).  An NCCL barrier is a kernel that
@@ -516,15 +522,7 @@ def main():
         if rank == 0:
             uid.copy_(torch.frombuffer(bytearray(BeliefPropagation.comm_unique_id()), dtype=torch.uint8))
         dist.broadcast(uid, 0, group=hostpg)
-        # NCCL prints its version banner on stdout when the first communicator comes up: keep stdout for the ONE JSON line
-        sys.stdout.flush()
-        saved_stdout = os.dup(1)
-        os.dup2(2, 1)
-        try:
-            bp.comm_init(world, rank, bytes(uid.numpy().tobytes()))
-        finally:
-            os.dup2(saved_stdout, 1)
-            os.close(saved_stdout)
+        bp.comm_init(world, rank, bytes(uid.numpy().tobytes()))
 
     # ---- device-resident inputs --------------------------------------------------------------------
     d_off = torch.from_numpy(ev.ev_off).to(dev)
@@ -912,6 +910,9 @@ def main():
             "roofline": roofline, "dense": dense, "cpu_baseline": cpu, "e2e": e2e,
             "gpu_launches": launches_per_step * args.steps, "clocks": clocks, "configs": configs,
         }
+        if saved_stdout is not None:
+            sys.stdout.flush()
+            os.dup2(saved_stdout, 1)
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
