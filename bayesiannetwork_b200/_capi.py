@@ -61,7 +61,8 @@ class StatsC(C.Structure):
                 ("last_fused", C.c_int64), ("last_compactions", C.c_int64),
                 ("last_host_ms", C.c_double), ("last_host_wait_ms", C.c_double),
                 ("last_onchip", C.c_int64), ("onchip_roles", C.c_int64), ("onchip_smem_bytes", C.c_int64),
-                ("onchip_blocks_per_sm", C.c_int64), ("onchip_role_imbalance", C.c_double)]
+                ("onchip_blocks_per_sm", C.c_int64), ("onchip_role_imbalance", C.c_double),
+                ("spec_class_count", C.c_int64)]
 
 
 EXPORTS = ["bnbp_device_count", "bnbp_last_error", "bnbp_create", "bnbp_destroy", "bnbp_run_batch",

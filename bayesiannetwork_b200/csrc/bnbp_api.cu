@@ -183,6 +183,8 @@ struct bnbp_handle {
     bool spec_eligible_ = false;
     std::string spec_why;              // why the network is not specialised
     int spec_vec = 1, spec_minb = 1, spec_ahead = 1;
+    bool spec_classloop = false;       // the specialised walk loops over node SHAPE classes (networks too large to unroll)
+    int spec_classes_n = 0;
     static constexpr int NSPEC = 8;    // variants of bnbp_spec.cuh
     SpecKernel spec[NSPEC];            // + 3 plain-first (no message loads), 4 plain-last (no message stores),
                                        //   5 first + K0, 6/7 last + K4 (marginals in T / in double)
@@ -408,6 +410,8 @@ int ensure_spec(bnbp_handle* h, int v)
     SpecConfig cfg;
     cfg.fp32 = h->precision == BNBP_FP32;
     cfg.vec = h->spec_vec; cfg.minb = spec_minb_for(h, v); cfg.variant = v; cfg.ahead = h->spec_ahead;
+    cfg.classloop = h->spec_classloop;
+    if (cfg.classloop && v > 4) return fail(BNBP_ERR_INVALID, "class-looped walks exist for variants 0-4");
     const std::string src = spec_source(spec_layout(h), cfg);
     std::vector<char> cubin;
     std::string err;
@@ -1757,6 +1761,28 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
             h->spec_eligible_ = false;
             h->spec_why = "the dense contraction path is active for this network";
         }
+        // Class-looped walk (bnbp_spec.cuh, BNBP_CLASSLOOP): networks the unrolled walk refuses for their SIZE whose
+        // nodes fall into few shape classes -- one unrolled body per class, looped over the class's nodes (cfg 3: the
+        // 10 000-node grid has 9 classes).  BNBP_CLASSLOOP=0 never, 1 (default) where the unrolled walk is refused,
+        // 2 wherever possible (the tests run the small networks through both code generators).
+        {
+            int mode = 1;
+            if (const char* ev = getenv("BNBP_CLASSLOOP")) mode = atoi(ev);
+            h->spec_classloop = false;
+            h->spec_classes_n = 0;
+            if (mode != 0 && (!h->spec_eligible_ || mode >= 2)) {
+                std::string why2 = "the dense contraction path is active for this network";
+                if (h->TS == 0 && class_eligible(L, h->precision == BNBP_FP32, &why2)) {
+                    h->spec_eligible_ = true;
+                    h->spec_classloop = true;
+                    h->spec_classes_n = (int)spec_classes(L).size();
+                    h->spec_why.clear();
+                    h->fuse_ok = false;            // K0 / K4 fused into the first / last sweep need the nodes in column order
+                } else if (!h->spec_eligible_) {
+                    h->spec_why += "; class-looped walk: " + why2;
+                }
+            }
+        }
         // measured on B200 (profiles/r01c): one case per thread beats 2/4 in both precisions -- the
         // kernel is HBM-latency bound, so resident warps (registers per thread) matter more than
         // wider accesses; fp64 1.147 ms/sweep at (1,3,1), fp32 0.620 ms at (1,4,1) for 1M alarm37 cases
@@ -1780,8 +1806,9 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         h->oc_ahead = 1;
         if (const char* ev = getenv("BNBP_OC_AHEAD")) h->oc_ahead = std::min(4, std::max(0, atoi(ev)));
         h->oc_smem = onchip_smem_bytes(L, h->precision == BNBP_FP32, h->oc_roles);
-        h->oc_eligible = h->spec_eligible_ && h->oc_smem <= SMEM_OPTIN;
+        h->oc_eligible = h->spec_eligible_ && !h->spec_classloop && h->oc_smem <= SMEM_OPTIN;
         if (!h->spec_eligible_) h->oc_why = h->spec_why;
+        else if (h->spec_classloop) h->oc_why = "the network is walked class by class (the on-chip kernel unrolls the walk node by node)";
         else if (!h->oc_eligible) h->oc_why = "the state of 32 cases (" + std::to_string(h->oc_smem) + " B) exceeds the shared memory of an SM";
         h->oc_minb = (int)std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (h->oc_smem + 1024)));
         if (const char* ev = getenv("BNBP_OC_MINB")) h->oc_minb = std::min(16, std::max(1, atoi(ev)));
@@ -2045,9 +2072,11 @@ int bnbp_precompile(const bnbp_flat_network* net, const bnbp_options* opt, int32
     for (int v = 0; v < bnbp_handle::NSPEC; ++v) {
         if (!(variant_mask & (1 << v))) continue;
         if (v == 7 && h.precision != BNBP_FP32) continue;     // marginals in double from a float kernel only
+        if (v > 4 && h.spec_classloop) continue;              // no K0 / K4 fusion in a class-looped walk
         SpecConfig cfg;
         cfg.fp32 = h.precision == BNBP_FP32;
         cfg.vec = h.spec_vec; cfg.minb = spec_minb_for(&h, v); cfg.variant = v; cfg.ahead = h.spec_ahead;
+        cfg.classloop = h.spec_classloop;
         std::vector<char> cubin;
         std::string err;
         if (!spec_compile(spec_source(spec_layout(&h), cfg), &cubin, nullptr, nullptr, &err)) return fail(BNBP_ERR_CUDA, err);
@@ -2066,6 +2095,8 @@ int bnbp_spec_source(const bnbp_flat_network* net, const bnbp_options* opt, int3
     SpecConfig cfg;
     cfg.fp32 = h.precision == BNBP_FP32;
     cfg.vec = h.spec_vec; cfg.minb = spec_minb_for(&h, variant); cfg.variant = variant; cfg.ahead = h.spec_ahead;
+    cfg.classloop = h.spec_classloop;
+    if (cfg.classloop && variant > 4) return fail(BNBP_ERR_INVALID, "a class-looped walk has variants 0-4 only");
     if (variant >= 8) {
         if (!h.oc_eligible) return fail(BNBP_ERR_INVALID, "network is not eligible for the on-chip kernel: " + h.oc_why);
         cfg.vec = 1; cfg.minb = h.oc_minb; cfg.ahead = h.oc_ahead; cfg.roles = h.oc_roles;
@@ -2629,6 +2660,7 @@ int bnbp_get_stats(const bnbp_handle* hc, bnbp_stats* out)
     out->last_kernel_launches = h->last_kernel_launches;
     out->resident_cases = h->cap;
     out->last_specialised = h->last_specialised;
+    out->spec_class_count = h->spec_classloop ? h->spec_classes_n : 0;
     out->cases_per_tile = h->tb;
     out->spec_compile_ms = h->spec_compile_ms;
     out->dense_nodes = h->dense_nodes;

@@ -55,6 +55,101 @@ bool spec_eligible(const SpecLayout& L, bool fp32, std::string* why)
     return true;
 }
 
+// ---- class-looped walks (bnbp_spec.cuh, BNBP_CLASSLOOP) ------------------------------------------------
+// The shape of a node is all its arithmetic depends on: (R, K, M, parent cardinalities).
+static std::vector<int> node_shape(const SpecLayout& L, int x)
+{
+    const NodeMeta& nd = L.nodes[x];
+    std::vector<int> key = {nd.card, nd.k, nd.m};
+    for (int j = 0; j < nd.k; ++j) key.push_back(L.e_card[nd.e0 + j]);
+    return key;
+}
+
+std::vector<std::vector<int>> spec_classes(const SpecLayout& L)
+{
+    std::vector<std::vector<int>> keys, members;
+    for (int x = 0; x < L.N; ++x) {
+        const std::vector<int> key = node_shape(L, x);
+        size_t c = 0;
+        while (c < keys.size() && keys[c] != key) ++c;
+        if (c == keys.size()) { keys.push_back(key); members.emplace_back(); }
+        members[c].push_back(x);
+    }
+    return members;
+}
+
+bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
+{
+    (void)fp32;
+    auto no = [&](const char* w) { if (why) *why = w; return false; };
+    if (L.N < 1) return no("empty network");
+    const std::vector<std::vector<int>> cls = spec_classes(L);
+    if (cls.size() > 96) return no("more than 96 node shape classes: one unrolled body per class would not fit the instruction caches");
+    double fma = 0;
+    for (const std::vector<int>& mem : cls) {
+        const NodeMeta& nd = L.nodes[mem[0]];
+        if (nd.k > 6) return no("in-degree > 6: accumulators would not fit the register file");
+        if (nd.card > 16) return no("cardinality > 16: accumulators would not fit the register file");
+        int sum_ru = 0;
+        int64_t Q = 1;
+        for (int j = 0; j < nd.k; ++j) {
+            if (L.e_card[nd.e0 + j] > 16) return no("parent cardinality > 16");
+            sum_ru += L.e_card[nd.e0 + j];
+            Q *= L.e_card[nd.e0 + j];
+        }
+        if (nd.m > 16) return no("a hub with more than 16 children: the class record would not stay in registers");
+        // the loop holds the inputs of TWO nodes (the one computed and the one loaded ahead), CPT entries included
+        const int64_t nq = Q * nd.card;
+        // (bnbp_spec.cuh: CPT_REG_MAX = 32 entries ride along in registers, larger tables are read where they are used)
+        const int64_t inputs = 2 * nd.card + sum_ru + (nd.m <= 4 ? nd.m * nd.card : 0) + (nq <= 32 ? nq : 0);
+        if (inputs > 64) return no("a node class needs more than 64 input values per case: two sets of them would not fit the register file");
+        if (nq > 1024) return no("a CPT of more than 1024 entries in a looped class (the dense path is the one for it)");
+        fma += 3.0 * (double)nq;
+    }
+    if (fma > 8000) return no("the class bodies together would exceed ~8k multiply-adds (NVRTC compile time)");
+    return true;
+}
+
+static std::string class_source(const SpecLayout& L, const SpecConfig& cfg, std::ostringstream& s)
+{
+    const std::vector<std::vector<int>> cls = spec_classes(L);
+    s << "#define BNBP_CLASSLOOP 1\n";
+    std::ostringstream rec, walk;
+    size_t n_rec = 0;
+    for (size_t c = 0; c < cls.size(); ++c) {
+        const NodeMeta& nd = L.nodes[cls[c][0]];
+        int rumax = 0;
+        for (int j = 0; j < nd.k; ++j) rumax = std::max(rumax, (int)L.e_card[nd.e0 + j]);
+        // shape only; the per-node members of the unrolled mode exist (zeroed) so that both modes name them
+        s << "struct C" << c << " { static constexpr int R=" << nd.card << ",K=" << nd.k << ",M=" << nd.m << ",RUMAX=" << rumax
+          << ",X=0,PL=0,PIN=0,LIN=0,CPT=0,BEL=0,GJ0=0;";
+        auto arr = [&](const char* name, int n, auto get) {
+            s << " static constexpr int " << name << "[" << std::max(n, 1) << "]={";
+            for (int j = 0; j < std::max(n, 1); ++j) s << (j ? "," : "") << (j < n ? get(j) : 0);
+            s << "};";
+        };
+        arr("RU", nd.k, [&](int j) { return (int)L.e_card[nd.e0 + j]; });
+        arr("LO", nd.k, [&](int) { return 0; });
+        arr("PO", nd.m, [&](int) { return 0; });
+        s << " };   // " << cls[c].size() << " nodes\n";
+        walk << " BNBP_CLASS(C" << c << "," << n_rec << "," << cls[c].size() << ")";
+        for (int x : cls[c]) {
+            const NodeMeta& nx = L.nodes[x];
+            rec << x << "," << nx.pl_off << "," << nx.pin_off << "," << nx.lin_off << "," << nx.cpt_off;
+            for (int j = 0; j < nx.k; ++j) rec << "," << L.e_lam_out[nx.e0 + j];
+            for (int j = 0; j < nx.m; ++j) rec << "," << L.c_pi_out[nx.c0 + j];
+            rec << ",\n";
+            n_rec += (size_t)(5 + nx.k + nx.m);
+        }
+    }
+    s << "// per node, class by class: X, PL, PIN, LIN, CPT, LO[K], PO[M]\n";
+    s << "__device__ const int bnbp_rec[" << n_rec + 1 << "] = {\n" << rec.str() << "0};\n";
+    s << "#define BNBP_WALK" << walk.str() << "\n";
+    (void)cfg;
+    s << kSpecHeader;
+    return s.str();
+}
+
 // ---- role partition of the on-chip kernel ------------------------------------------------------------
 double spec_node_cost(const SpecLayout& L, int x)
 {
@@ -117,7 +212,9 @@ std::string spec_source(const SpecLayout& L, const SpecConfig& cfg)
     s << "#define BNBP_NCPT " << L.cpt_values << "\n";
     s << "#define BNBP_N " << L.N << "\n#define BNBP_V " << L.V << "\n";
     const bool onchip = cfg.variant >= 8;
+    if (cfg.classloop && cfg.variant > 4) return "#error \"class-looped walks exist for variants 0-4\"\n";
     s << "#define BNBP_OUT " << ((cfg.fp32 && cfg.variant != 7 && !(onchip && cfg.out_double)) ? "float" : "double") << "\n";
+    if (cfg.classloop) return class_source(L, cfg, s);
     // groups of consecutive nodes whose marginals fit the 32-column tile of variants 6/7
     std::vector<int> gj0((size_t)L.N, 0), gend((size_t)L.N, 0);   // group start column per node, 1 = last node of its group
     for (int x = 0; x < L.N;) {

@@ -31,6 +31,7 @@ struct SpecConfig {
     int minb = 1;       // __launch_bounds__ min blocks per SM
     int variant = 0;    // 0 plain, 1 freeze, 2 freeze + check, 3 first, 4 last, 5 first + K0, 6/7 last + K4 (bnbp_spec.cuh)
     int ahead = 1;      // software-pipeline depth of the input loads
+    bool classloop = false;     // one loop per node SHAPE class instead of one unrolled body per node (large networks)
     // on-chip variants (8 plain, 9 check: bnbp_onchip.cuh)
     int roles = 4;              // warps that share the node walk of a 32-case group
     bool out_double = false;    // marginals in double from a float kernel (the host-buffer call)
@@ -46,6 +47,11 @@ size_t onchip_smem_bytes(const SpecLayout& L, bool fp32, int roles);
 
 // Can (and should) this network be specialised?  why != nullptr receives the reason when not.
 bool spec_eligible(const SpecLayout& L, bool fp32, std::string* why);
+
+// Class-looped mode: a network too large to unroll node by node whose nodes fall into few shape classes
+// (R, K, M, parent cardinalities) -- the grids of cfg 3.  spec_classes: members of every class in node order.
+bool class_eligible(const SpecLayout& L, bool fp32, std::string* why);
+std::vector<std::vector<int>> spec_classes(const SpecLayout& L);
 
 std::string spec_source(const SpecLayout& L, const SpecConfig& cfg);
 

@@ -194,6 +194,8 @@ typedef struct bnbp_stats {
     int64_t onchip_smem_bytes;       /* shared memory of one group: (PL + 2M) * 32 values + reduction scratch          */
     int64_t onchip_blocks_per_sm;    /* resident groups per SM of the loaded on-chip kernel (0: none loaded yet)        */
     double  onchip_role_imbalance;   /* busiest role / mean role cost of the node partition (1 = perfectly balanced)    */
+    int64_t spec_class_count;        /* node shape classes of a CLASS-LOOPED specialised walk (networks too large to unroll
+                                        node by node: one unrolled body per class, looped over its nodes); 0 otherwise   */
 } bnbp_stats;
 
 typedef struct bnbp_handle bnbp_handle;

@@ -1,0 +1,37 @@
+// spec_emul.cpp -- host emulation of ONE generated sweep kernel (see cuda_host_shim.h).  Built by
+// tests/test_netcompiler_emul.py as   g++ -O1 -std=c++17 -ffp-contract=off -DBNBP_GENERATED='"<file>"' -shared ...
+#include "cuda_host_shim.h"
+#include BNBP_GENERATED
+
+extern "C" {
+
+int emul_pl() { return BNBP_PL; }
+int emul_m() { return BNBP_M; }
+int emul_w() { return BNBP_W; }
+int emul_tbc() { return (int)bnbp_spec::TBC; }
+int emul_variant() { return BNBP_VARIANT; }
+int emul_value_bytes() { return (int)sizeof(T); }
+
+void emul_set_cpt(const T* cpt, long long n) { memcpy(bnbp_cpt, cpt, (size_t)n * sizeof(T)); }
+
+// One launch of <<<tiles, 128>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux).  delta / status / sweeps / last_active: the
+// per-case arrays of the freeze / check variants (ignored by the plain ones).
+void emul_launch(T* pl, const T* cur, T* nxt, const unsigned* evbits, int tiles, int n_inner, T eps, T damping,
+                 int sweep_index, int prev_tested, const T* delta_prev, T* delta_cur, T* delta_next,
+                 unsigned char* status, int* sweeps, int* last_active)
+{
+    bnbp_spec::Aux a;
+    memset(&a, 0, sizeof a);
+    a.delta_prev = delta_prev; a.delta_cur = delta_cur; a.delta_next = delta_next;
+    a.status = status; a.sweeps = sweeps; a.last_active = last_active;
+    a.sweep_index = sweep_index; a.prev_tested = prev_tested;
+    a.eps = eps; a.damping = damping; a.n_inner = n_inner;
+    for (int t = 0; t < tiles; ++t)
+        for (int tid = 0; tid < 128; ++tid) {
+            blockIdx.x = (unsigned)t;
+            threadIdx.x = (unsigned)tid;
+            bnbp_spec_sweep(pl, cur, nxt, evbits, a);
+        }
+}
+
+}

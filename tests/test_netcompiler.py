@@ -55,8 +55,17 @@ def test_ineligible_networks_are_reported(engine):
     from bayesiannetwork_b200.engine import BnbpError
     with pytest.raises(BnbpError, match="not eligible"):
         engine.precompile(synth.high_card(6, card=32, n_parents=2, seed=10), "fp64", 1)
-    with pytest.raises(BnbpError, match="not eligible"):
-        engine.spec_source(synth.grid(40), "fp64", 0)             # 1600 nodes
+    # 1600 nodes: too many to unroll node by node -- walked class by class instead (round 2, BNBP_CLASSLOOP) ...
+    assert "#define BNBP_CLASSLOOP 1" in engine.spec_source(synth.grid(40), "fp64", 0)
+    # ... unless that is switched off, or the node shapes are too many / too large for it as well
+    os.environ["BNBP_CLASSLOOP"] = "0"
+    try:
+        with pytest.raises(BnbpError, match="not eligible.*1024 nodes"):
+            engine.spec_source(synth.grid(40), "fp64", 0)
+    finally:
+        del os.environ["BNBP_CLASSLOOP"]
+    with pytest.raises(BnbpError, match="not eligible.*class-looped walk"):
+        engine.spec_source(synth.random_dag(1500, max_parents=4, card_lo=2, card_hi=8, seed=3), "fp64", 0)
 
 
 def test_cmake_project_configures(tmp_path):
