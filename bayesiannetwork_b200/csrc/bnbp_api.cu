@@ -1789,6 +1789,10 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         h->spec_vec = 1;
         h->spec_minb = h->precision == BNBP_FP32 ? 4 : 3;
         h->spec_ahead = 1;
+        // class-looped walks over SMALL nodes (the grid of cfg 3: 20 input values per node, 128 registers) keep one more
+        // block per SM resident: 16 warps with a node's loads in flight each instead of 12, and the 512 tiles of the 65 536
+        // cases of cfg 3 are ONE wave of 148 x 4 blocks instead of 1.15 waves of 148 x 3
+        if (h->spec_classloop && class_max_inputs(L) <= 24) h->spec_minb = h->precision == BNBP_FP32 ? 5 : 4;
         if (const char* ev = getenv("BNBP_SPEC_VEC")) {
             const int v = atoi(ev);
             if (v == 1 || v == 2 || (v == 4 && h->tsize == 4)) h->spec_vec = v;

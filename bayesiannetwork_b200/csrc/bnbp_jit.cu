@@ -78,6 +78,23 @@ std::vector<std::vector<int>> spec_classes(const SpecLayout& L)
     return members;
 }
 
+// input values per case of a node as the class loop holds them (pi, lambda, both inboxes, CPT entries in registers)
+static int64_t class_inputs(const SpecLayout& L, int x)
+{
+    const NodeMeta& nd = L.nodes[x];
+    int64_t sum_ru = 0, Q = 1;
+    for (int j = 0; j < nd.k; ++j) { sum_ru += L.e_card[nd.e0 + j]; Q *= L.e_card[nd.e0 + j]; }
+    const int64_t nq = Q * nd.card;
+    return 2 * nd.card + sum_ru + (nd.m <= 4 ? nd.m * nd.card : 0) + (nq <= 32 ? nq : 0);
+}
+
+int class_max_inputs(const SpecLayout& L)
+{
+    int64_t mx = 0;
+    for (int x = 0; x < L.N; ++x) mx = std::max(mx, class_inputs(L, x));
+    return (int)mx;
+}
+
 bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
 {
     (void)fp32;
@@ -101,7 +118,7 @@ bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
         // the loop holds the inputs of TWO nodes (the one computed and the one loaded ahead), CPT entries included
         const int64_t nq = Q * nd.card;
         // (bnbp_spec.cuh: CPT_REG_MAX = 32 entries ride along in registers, larger tables are read where they are used)
-        const int64_t inputs = 2 * nd.card + sum_ru + (nd.m <= 4 ? nd.m * nd.card : 0) + (nq <= 32 ? nq : 0);
+        const int64_t inputs = class_inputs(L, mem[0]);
         if (inputs > 64) return no("a node class needs more than 64 input values per case: two sets of them would not fit the register file");
         if (nq > 1024) return no("a CPT of more than 1024 entries in a looped class (the dense path is the one for it)");
         fma += 3.0 * (double)nq;

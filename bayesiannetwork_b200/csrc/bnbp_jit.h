@@ -52,6 +52,7 @@ bool spec_eligible(const SpecLayout& L, bool fp32, std::string* why);
 // (R, K, M, parent cardinalities) -- the grids of cfg 3.  spec_classes: members of every class in node order.
 bool class_eligible(const SpecLayout& L, bool fp32, std::string* why);
 std::vector<std::vector<int>> spec_classes(const SpecLayout& L);
+int class_max_inputs(const SpecLayout& L);     // most input values per case any node's class loop holds (register pressure)
 
 std::string spec_source(const SpecLayout& L, const SpecConfig& cfg);
 

@@ -359,7 +359,11 @@ def measure_config(key, workload, total_cases, base_gpus, precision, parity_case
     kern = {"sweep_kernel_ms_per_sweep": sweep_ms, "dense_ms_per_sweep": dense_ms_per_sweep,
             "sweep_kernel_hbm_frac": (2.0 * S * tsize * min(n, st["resident_cases"]) / (sweep_ms * 1e-3) / 1e9 / peak) if sweep_ms > 0 else None,
             "resident_cases": int(st["resident_cases"]), "dense_nodes": int(st["dense_nodes"]),
-            "kernel_launches_per_step": int(st["last_kernel_launches"])}
+            "kernel_launches_per_step": int(st["last_kernel_launches"]),
+            "sweep_kernel": (f"bnbp_spec_sweep, class-looped: one unrolled body per node shape class ({int(st['spec_class_count'])} classes "
+                             f"for {net.n_nodes} nodes), NVRTC sm_100a" if st.get("spec_class_count", 0)
+                             else "bnbp_spec_sweep (network-specialised, NVRTC sm_100a)" if st["last_specialised"] else "sweep_kernel (generic)"),
+            "spec_compile_ms": st["spec_compile_ms"]}
     if binding == "hbm":
         roof = hbm
     elif binding == "fma":
@@ -900,6 +904,8 @@ def main():
                                     else "synchronous, fixed sweeps, no damping"), "eps_mode": eps_info,
                        "sharding": f"cases x{world}", "gather": gather, "multi_gpu": multi_gpu,
                        "kernel_family": ("on-chip multi-sweep (NVRTC sm_100a, state in shared memory)" if onchip else
+                                         f"network-specialised, class-looped walk over {int(st['spec_class_count'])} node shape classes (NVRTC sm_100a)"
+                                         if st["last_specialised"] and st.get("spec_class_count", 0) else
                                          "network-specialised (NVRTC sm_100a)" if st["last_specialised"] else "generic"),
                        "cases_per_tile": int(st["cases_per_tile"]),
                        "spec_compile_ms": st["spec_compile_ms"],     # NVRTC time this handle paid (0: every kernel came from the cubin cache)

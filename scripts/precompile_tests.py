@@ -39,16 +39,33 @@ def jobs():
         f = load_fixture(fx, name)
         out.append((f["net"], "fp64", (1 << 8) | (1 << 10)))
     out.append((synth.random_dag(20, 3, 2, 4, seed=31), "fp64", 1 << 8))
+    # class-looped walks (tests/test_gpu_classloop.py): the small networks forced through the class generator, alarm37 for
+    # the bit-for-bit comparison with the unrolled walk, and the network the mode exists for (cfg 3, the 100 x 100 grid)
+    import test_gpu_classloop as cl
+    force = {"BNBP_CLASSLOOP": "2"}
+    for name, net, evkw, eps, cap in cl._cases():
+        for prec in ("fp64", "fp32"):
+            if prec == "fp32" and eps > 0:
+                continue
+            out.append((net, prec, 0b00100 if eps > 0 else 0b11001, force))
+    out.append((synth.alarm37(), "fp64", 0b11101, force))
+    out.append((synth.grid(100), "fp64", 0b11101))
+    out.append((synth.grid(100), "fp32", 0b11001))
     return out
 
 
 def one(job):
     from bayesiannetwork_b200 import engine
-    net, prec, mask = job
+    net, prec, mask = job[:3]
+    env = job[3] if len(job) > 3 else {}
+    os.environ.update(env)                 # knobs the library reads when it lays the network out (one job per worker call)
     try:
         engine.precompile(net, prec, mask)
     except engine.BnbpError as e:          # e.g. a test network whose state does not fit the on-chip kernel: the test skips it
         return net.name, prec, mask, f"not compiled: {e}"
+    finally:
+        for k in env:
+            os.environ.pop(k, None)
     return net.name, prec, mask
 
 

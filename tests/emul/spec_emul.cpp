@@ -1,8 +1,12 @@
 // spec_emul.cpp -- host emulation of ONE generated sweep kernel (see cuda_host_shim.h).  Built by
-// tests/test_netcompiler_emul.py as   g++ -O1 -std=c++17 -ffp-contract=off -DBNBP_GENERATED='"<file>"' -shared ...
+// tests/test_netcompiler_emul.py as   g++ -O0 -std=c++17 -ffp-contract=off -fvisibility=hidden -fno-gnu-unique
+//                                         -DBNBP_GENERATED='"<file>"' -shared ...
+// Hidden visibility / no unique symbols: a test process loads several of these objects, and every one of them defines
+// trait structs of the same names (N0, C0, ...) with static data members -- they must not be unified across objects.
 #include "cuda_host_shim.h"
 #include BNBP_GENERATED
 
+#pragma GCC visibility push(default)
 extern "C" {
 
 int emul_pl() { return BNBP_PL; }
@@ -35,3 +39,4 @@ void emul_launch(T* pl, const T* cur, T* nxt, const unsigned* evbits, int tiles,
 }
 
 }
+#pragma GCC visibility pop

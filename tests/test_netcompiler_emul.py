@@ -46,7 +46,7 @@ class Emulated:
         so = os.path.join(workdir, tag + ".so")
         with open(cu, "w") as f:
             f.write(src)
-        cmd = ["g++", "-O1", "-std=c++17", "-ffp-contract=off", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "emul"),
+        cmd = ["g++", "-O0", "-std=c++17", "-ffp-contract=off", "-fvisibility=hidden", "-fno-gnu-unique", "-Wno-unknown-pragmas", "-I", os.path.join(HERE, "emul"),
                f'-DBNBP_GENERATED="{cu}"', "-shared", "-fPIC", "-o", so, os.path.join(HERE, "emul", "spec_emul.cpp")]
         r = subprocess.run(cmd, capture_output=True, text=True)
         assert r.returncode == 0, r.stderr[-3000:]
