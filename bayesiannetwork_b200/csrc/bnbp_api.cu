@@ -812,7 +812,19 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 // ones: looping wins for grids of whole waves and for short grids (the chunks of the host-buffer
                 // pipeline, +3 % e2e), separate launches for one long ragged grid (18.45 waves: -3 %, r01o).
                 ax.n_inner = 1;
-                if (variant == 0 && !eps_mode && prm.damping == 0.0 && !getenv("BNBP_NO_LOOP")) {
+                // class-looped walk on a batch that does not fill the SMs (cfg 3 sharded 8 ways: 64 tiles for 148 SMs): the
+                // plain variants take node SLICES in grid.y -- block (tile, y) walks the y-th slice of every node class -- until
+                // one wave of blocks is resident.  Such a launch is one sweep (slices of sweep t+1 read what every slice of
+                // sweep t wrote), so it does not loop.
+                unsigned node_slices = 1;
+                if (h->spec_classloop && (variant == 0 || variant == 3 || variant == 4) && !getenv("BNBP_NO_NODE_SLICES")) {
+                    int sms = 148;
+                    cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
+                    const int64_t wave_blocks = (int64_t)sms * std::max(1, h->spec[variant].blocks_per_sm);
+                    if (tiles_cur < wave_blocks) node_slices = (unsigned)std::min<int64_t>(16, (wave_blocks + tiles_cur - 1) / tiles_cur);
+                    if (const char* e = getenv("BNBP_NODE_SLICES")) node_slices = (unsigned)std::min(64, std::max(1, atoi(e)));
+                }
+                if (node_slices == 1 && variant == 0 && !eps_mode && prm.damping == 0.0 && !getenv("BNBP_NO_LOOP")) {
                     int sms = 148;
                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
                     const int64_t wave_blocks = (int64_t)sms * std::max(1, h->spec[0].blocks_per_sm);
@@ -821,7 +833,7 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                 }
                 n_inner = ax.n_inner;
                 std::string err;
-                if (!spec_launch(h->spec[variant], (unsigned)tiles_cur, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err))
+                if (!spec_launch(h->spec[variant], (unsigned)tiles_cur, st, sa.pl, sa.msg_cur, sa.msg_nxt, sa.evbits, &ax, &err, node_slices))
                     return fail(BNBP_ERR_CUDA, err);
             } else {
                 cudaError_t e = launch_sweep<T>(h, sa, grid, smem, eps_mode && !split, check && !split, st, prm.semiring == BNBP_MAX_PRODUCT);

@@ -572,11 +572,11 @@ bool spec_upload_cpt(const SpecKernel& k, const void* host, size_t bytes, std::s
 }
 
 bool spec_launch(const SpecKernel& k, unsigned tiles, cudaStream_t st, void* pl, const void* cur, void* nxt,
-                 const void* evbits, const void* aux, std::string* err)
+                 const void* evbits, const void* aux, std::string* err, unsigned node_slices)
 {
     Driver& d = driver();
     void* params[5] = {&pl, (void*)&cur, &nxt, (void*)&evbits, const_cast<void*>(aux)};
-    CUresult r = d.launchKernel((CUfunction)k.function, tiles, 1, 1, 128, 1, 1, 0, (CUstream)st, params, nullptr);
+    CUresult r = d.launchKernel((CUfunction)k.function, tiles, node_slices ? node_slices : 1, 1, 128, 1, 1, 0, (CUstream)st, params, nullptr);
     if (r != CUDA_SUCCESS) { if (err) *err = cu_err(d, "cuLaunchKernel(bnbp_spec_sweep)", r); return false; }
     return true;
 }

@@ -97,9 +97,10 @@ bool spec_load(const std::vector<char>& cubin, SpecKernel* out, std::string* err
 void spec_unload(SpecKernel* k);
 bool spec_upload_cpt(const SpecKernel& k, const void* host, size_t bytes, std::string* err);
 
-// <<<tiles, 128, 0, st>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux)
+// <<<(tiles, node_slices), 128, 0, st>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux)
+// node_slices > 1: class-looped PLAIN variants only -- block (tile, y) walks the y-th slice of every node class (one sweep per launch)
 bool spec_launch(const SpecKernel& k, unsigned tiles, cudaStream_t st, void* pl, const void* cur, void* nxt,
-                 const void* evbits, const void* aux, std::string* err);
+                 const void* evbits, const void* aux, std::string* err, unsigned node_slices = 1);
 
 // mirrors bnbp_spec::OcArgs (device side) for T = double / float
 template <typename T> struct OnchipArgs {

@@ -19,7 +19,7 @@
 #define __shared__ static
 
 struct emul_dim3 { unsigned x = 0, y = 0, z = 0; };
-static emul_dim3 threadIdx, blockIdx;
+static emul_dim3 threadIdx, blockIdx, gridDim;
 
 template <typename U> static inline U __ldg(const U* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { return a * b; }      // built with -ffp-contract=off

@@ -18,11 +18,11 @@ int emul_value_bytes() { return (int)sizeof(T); }
 
 void emul_set_cpt(const T* cpt, long long n) { memcpy(bnbp_cpt, cpt, (size_t)n * sizeof(T)); }
 
-// One launch of <<<tiles, 128>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux).  delta / status / sweeps / last_active: the
+// One launch of <<<(tiles, node_slices), 128>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux).  delta / status / sweeps / last_active: the
 // per-case arrays of the freeze / check variants (ignored by the plain ones).
 void emul_launch(T* pl, const T* cur, T* nxt, const unsigned* evbits, int tiles, int n_inner, T eps, T damping,
                  int sweep_index, int prev_tested, const T* delta_prev, T* delta_cur, T* delta_next,
-                 unsigned char* status, int* sweeps, int* last_active)
+                 unsigned char* status, int* sweeps, int* last_active, int node_slices)
 {
     bnbp_spec::Aux a;
     memset(&a, 0, sizeof a);
@@ -30,12 +30,17 @@ void emul_launch(T* pl, const T* cur, T* nxt, const unsigned* evbits, int tiles,
     a.status = status; a.sweeps = sweeps; a.last_active = last_active;
     a.sweep_index = sweep_index; a.prev_tested = prev_tested;
     a.eps = eps; a.damping = damping; a.n_inner = n_inner;
-    for (int t = 0; t < tiles; ++t)
-        for (int tid = 0; tid < 128; ++tid) {
-            blockIdx.x = (unsigned)t;
-            threadIdx.x = (unsigned)tid;
-            bnbp_spec_sweep(pl, cur, nxt, evbits, a);
-        }
+    // grid (tiles, node_slices), slices outermost and in DESCENDING order: nothing may depend on the order of blocks
+    gridDim.x = (unsigned)tiles;
+    gridDim.y = (unsigned)(node_slices > 0 ? node_slices : 1);
+    for (int y = (int)gridDim.y - 1; y >= 0; --y)
+        for (int t = 0; t < tiles; ++t)
+            for (int tid = 0; tid < 128; ++tid) {
+                blockIdx.x = (unsigned)t;
+                blockIdx.y = (unsigned)y;
+                threadIdx.x = (unsigned)tid;
+                bnbp_spec_sweep(pl, cur, nxt, evbits, a);
+            }
 }
 
 }

@@ -121,3 +121,25 @@ def test_grid100_wide_batch_default_path_is_class_looped(BP, oracle_mod, grid100
     for i in (0, 127, 128, 4095, 4096, 4172):
         om, _, _ = oracle_mod.run_port(net, ev.slice(i, i + 1), eps=0.0, max_sweeps=6, threads=0)
         assert_close(a.marginals[i:i + 1], om, what=f"grid100 wide batch case {i}", **TOL["fp64"])
+
+
+def test_grid100_small_batch_takes_node_slices(BP, oracle_mod, monkeypatch, grid100):
+    """cfg 3 sharded over several GPUs leaves a few thousand cases per device: fewer tiles than SMs.  The plain variants
+    then run with node slices in grid.y (block (tile, y) walks the y-th slice of every class, one sweep per launch);
+    sliced == unsliced bit for bit, and both agree with the oracle."""
+    net = grid100
+    ev = synth.make_evidence(net, 1100, p=0.10, seed=6)           # 9 tiles -> 16 slices
+    bp = BP(net, "fp64", specialize="always")
+    a = bp(ev, 0.0, max_sweeps=7)
+    st = bp.stats()
+    assert st["spec_class_count"] > 0 and st["last_sweep_launches"] == 7
+    monkeypatch.setenv("BNBP_NO_NODE_SLICES", "1")
+    b = bp(ev, 0.0, max_sweeps=7)
+    assert np.array_equal(a.marginals, b.marginals)
+    monkeypatch.delenv("BNBP_NO_NODE_SLICES")
+    monkeypatch.setenv("BNBP_NODE_SLICES", "5")
+    c = bp(ev, 0.0, max_sweeps=7)
+    assert np.array_equal(a.marginals, c.marginals)
+    for i in (0, 511, 1099):
+        om, _, _ = oracle_mod.run_port(net, ev.slice(i, i + 1), eps=0.0, max_sweeps=7, threads=0)
+        assert_close(a.marginals[i:i + 1], om, what=f"grid100 sliced case {i}", **TOL["fp64"])

@@ -59,13 +59,13 @@ class Emulated:
         cpt = np.ascontiguousarray(net.cpt, dtype=self.T)
         self.lib.emul_set_cpt(cpt.ctypes.data_as(C.c_void_p), C.c_longlong(cpt.size))
 
-    def launch(self, st, cur, nxt, n_inner=1, eps=0.0, damping=0.0, sweep_index=0, prev_tested=0, per_case=None):
+    def launch(self, st, cur, nxt, n_inner=1, eps=0.0, damping=0.0, sweep_index=0, prev_tested=0, per_case=None, node_slices=1):
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         pc = per_case or {}
         self.lib.emul_launch(p(st["pl"]), p(cur), p(nxt), p(st["evbits"]), C.c_int(st["tiles"]), C.c_int(n_inner),
                              self.cT(eps), self.cT(damping), C.c_int(sweep_index), C.c_int(prev_tested),
                              p(pc.get("delta_prev")), p(pc.get("delta_cur")), p(pc.get("delta_next")),
-                             p(pc.get("status")), p(pc.get("sweeps")), p(pc.get("last_active")))
+                             p(pc.get("status")), p(pc.get("sweeps")), p(pc.get("last_active")), C.c_int(node_slices))
 
 
 def initial_state(net, ev, k):
@@ -142,13 +142,15 @@ def test_generated_sweeps_match_the_oracle_on_the_host(engine, oracle_mod, tmp_p
 
 def test_classloop_equals_unrolled_bit_for_bit_and_loops_in_kernel(engine, tmp_path):
     """Same arithmetic per node in both code generators: the arenas agree bit for bit; the in-kernel loop over
-    sweeps (variant 0, n_inner) equals separate launches; two cases per thread (16-byte accesses) equal one."""
+    sweeps (variant 0, n_inner) equals separate launches; two cases per thread (16-byte accesses) equal one; node slices
+    in grid.y (small batches) equal the unsliced walk."""
     net = synth.random_dag(30, max_parents=3, card_lo=2, card_hi=4, seed=5)
     net.name = "dag30"
     ev = synth.make_evidence(net, 300, seed=4, p=0.2)
     res = {}
-    for mode, cl, vec, inner in (("unrolled", False, 1, 1), ("classloop", True, 1, 1), ("classloop_inner", True, 1, 6),
-                                 ("classloop_vec2", True, 2, 1)):
+    for mode, cl, vec, inner, slices in (("unrolled", False, 1, 1, 1), ("classloop", True, 1, 1, 1), ("classloop_inner", True, 1, 6, 1),
+                                         ("classloop_vec2", True, 2, 1, 1), ("classloop_slices3", True, 1, 1, 3),
+                                         ("classloop_slices16", True, 1, 1, 16)):     # 16 slices: more than most classes have nodes
         k = Emulated(engine, net, "fp64", 0, cl, str(tmp_path), vec=vec)
         st = initial_state(net, ev, k)
         cur, nxt = st["msg"]
@@ -156,12 +158,12 @@ def test_classloop_equals_unrolled_bit_for_bit_and_loops_in_kernel(engine, tmp_p
             k.launch(st, cur, nxt, n_inner=inner)             # buffers swapped per inner sweep: 6 sweeps end in `cur`
         else:
             for _ in range(6):
-                k.launch(st, cur, nxt)
+                k.launch(st, cur, nxt, node_slices=slices)    # grid.y: block (tile, y) walks the y-th slice of every class
                 cur, nxt = nxt, cur
         # case-major copies, so that the tile width (128 x cases per thread) does not matter
         res[mode] = (st["pl"].transpose(0, 2, 1).reshape(-1, k.PL)[:ev.n_cases].copy(),
                      cur.transpose(0, 2, 1).reshape(-1, k.M)[:ev.n_cases].copy())
-    for mode in ("classloop", "classloop_inner", "classloop_vec2"):
+    for mode in ("classloop", "classloop_inner", "classloop_vec2", "classloop_slices3", "classloop_slices16"):
         assert np.array_equal(res[mode][0], res["unrolled"][0]), mode
         assert np.array_equal(res[mode][1], res["unrolled"][1]), mode
 
