@@ -530,8 +530,16 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
             if (mode > 0) return rc;
         }
     }
-    const bool want = h->specialize == BNBP_SPEC_ALWAYS ||
-                      (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
+    bool want = h->specialize == BNBP_SPEC_ALWAYS ||
+                (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
+    if (want && h->spec_classloop && h->specialize == BNBP_SPEC_AUTO) {
+        // A class-looped walk covers a batch that does not fill the SMs with node slices in grid.y -- in its PLAIN variants.
+        // The freeze / check variants (epsilon mode below the split threshold, damping) keep per-case state one block must
+        // own, so a small batch would leave most SMs idle; the generic kernel splits its node walk in every flavour.
+        const bool plain_variants = (!(prm.epsilon > 0.0) && prm.damping == 0.0) ||
+                                    (prm.epsilon > 0.0 && prm.damping == 0.0 && n_cases >= 16384 && !getenv("BNBP_NO_SPLIT"));
+        if (!plain_variants && n_cases < 32768) want = false;
+    }
     if (want) {
         if (!h->spec_eligible_)
             return fail(BNBP_ERR_INVALID, "specialize=ALWAYS but the network is not eligible: " + h->spec_why);
@@ -821,8 +829,10 @@ int run_chunk(bnbp_handle* h, int64_t n, const DevEvidence& de, const bnbp_run_p
                     int sms = 148;
                     cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device);
                     const int64_t wave_blocks = (int64_t)sms * std::max(1, h->spec[variant].blocks_per_sm);
-                    if (tiles_cur < wave_blocks) node_slices = (unsigned)std::min<int64_t>(16, (wave_blocks + tiles_cur - 1) / tiles_cur);
-                    if (const char* e = getenv("BNBP_NODE_SLICES")) node_slices = (unsigned)std::min(64, std::max(1, atoi(e)));
+                    // as many slices as keep the grid within ONE wave (a second, sparse wave costs a whole block lifetime:
+                    // 512 tiles on 444 slots ran at 0.72 of HBM against 0.95 on 592 slots, r02r)
+                    if (tiles_cur < wave_blocks) node_slices = (unsigned)std::min<int64_t>(32, std::max<int64_t>(1, wave_blocks / tiles_cur));
+                    if (const char* e = getenv("BNBP_NODE_SLICES")) node_slices = (unsigned)std::min(64, std::max(1, atoi(e)));      // tuning / test knob
                 }
                 if (node_slices == 1 && variant == 0 && !eps_mode && prm.damping == 0.0 && !getenv("BNBP_NO_LOOP")) {
                     int sms = 148;

@@ -114,7 +114,7 @@ bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
             sum_ru += L.e_card[nd.e0 + j];
             Q *= L.e_card[nd.e0 + j];
         }
-        if (nd.m > 16) return no("a hub with more than 16 children: the class record would not stay in registers");
+        if (nd.m > 64) return no("a hub with more than 64 children: its class record would not stay in registers");
         // the loop holds the inputs of TWO nodes (the one computed and the one loaded ahead), CPT entries included
         const int64_t nq = Q * nd.card;
         // (bnbp_spec.cuh: CPT_REG_MAX = 32 entries ride along in registers, larger tables are read where they are used)

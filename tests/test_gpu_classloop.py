@@ -128,11 +128,11 @@ def test_grid100_small_batch_takes_node_slices(BP, oracle_mod, monkeypatch, grid
     then run with node slices in grid.y (block (tile, y) walks the y-th slice of every class, one sweep per launch);
     sliced == unsliced bit for bit, and both agree with the oracle."""
     net = grid100
-    ev = synth.make_evidence(net, 1100, p=0.10, seed=6)           # 9 tiles -> 16 slices
+    ev = synth.make_evidence(net, 1100, p=0.10, seed=6)           # 9 tiles -> 32 slices
     bp = BP(net, "fp64", specialize="always")
     a = bp(ev, 0.0, max_sweeps=7)
     st = bp.stats()
-    assert st["spec_class_count"] > 0 and st["last_sweep_launches"] == 7
+    assert st["spec_class_count"] > 0 and st["last_sweep_launches"] >= 7        # one sweep per launch (per chunk of the call)
     monkeypatch.setenv("BNBP_NO_NODE_SLICES", "1")
     b = bp(ev, 0.0, max_sweeps=7)
     assert np.array_equal(a.marginals, b.marginals)
