@@ -294,7 +294,7 @@ namespace {
 
 int pick_rmax(int maxcard)
 {
-    for (int r : {2, 4, 8, 16, 32, 64})
+    for (int r : {2, 4, 8, 16, 32, 64, 128})
         if (maxcard <= r) return r;
     return -1;
 }
@@ -1643,7 +1643,7 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         maxcard = std::max(maxcard, (int)net->card[x]);
     }
     h->rmax = pick_rmax(maxcard);
-    if (h->rmax < 0) return fail(BNBP_ERR_INVALID, "cardinality > 64 is not supported");
+    if (h->rmax < 0) return fail(BNBP_ERR_INVALID, "cardinality > 128 is not supported");
     std::vector<int> nchild(N, 0);
     for (int x = 0; x < N; ++x) {
         const int k = net->parent_off[x + 1] - net->parent_off[x];

@@ -10,4 +10,4 @@
     X(T, 1, 4, 2) X(T, 1, 4, 4) X(T, 1, 4, 8) \
     X(T, 2, 4, 2) X(T, 2, 4, 4) X(T, 2, 4, 8) \
     X(T, 1, 8, 4) X(T, 1, 8, 8) X(T, 2, 8, 4) X(T, 2, 8, 8) \
-    X(T, 1, 16, 8) X(T, 1, 32, 8) X(T, 1, 64, 8)
+    X(T, 1, 16, 8) X(T, 1, 32, 8) X(T, 1, 64, 8) X(T, 1, 128, 8)

@@ -251,3 +251,28 @@ def test_max_product_matches_oracle(BP, oracle_mod, precision):
     big = synth.high_card(6, card=16, n_parents=2, seed=9)
     with pytest.raises(BnbpError):
         BP(big, "fp64", dense_min_cpt=256)(synth.make_evidence(big, 8, p=0.2), 0.0, max_sweeps=3, semiring="max")
+
+
+@pytest.mark.parametrize("dense_min", [0, -1], ids=["dense_default", "walked"])
+@pytest.mark.parametrize("precision", ["fp64", "fp32"])
+def test_cardinality_above_64(BP, oracle_mod, precision, dense_min):
+    """Networks with 65-128 states per node (the 67-state nodes of `barley`, the 100-state nodes of `mildew`): the
+    generic kernel's RMAX = 128 instantiation, with the large CPTs on the dense contraction path (default) and walked."""
+    net = synth._assemble([67, 100, 3, 128, 2, 5], [[], [0], [0, 1], [2], [3], [0]], 91, "wide_cards")
+    ev = synth.make_evidence(net, 150, p=0.3, seed=12)
+    om, osw, ocv = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=9, threads=0)
+    res = BP(net, precision, dense_min_cpt=dense_min)(ev, 0.0, max_sweeps=9)
+    assert np.array_equal(res.sweeps, osw)
+    assert_close(res.marginals, om, what=f"wide_cards {precision}", **TOL[precision])
+    if precision == "fp64":
+        om, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-7, max_sweeps=100, threads=0)
+        res = BP(net, precision, dense_min_cpt=dense_min)(ev, 1e-7, max_sweeps=100)
+        assert np.array_equal(res.sweeps, osw) and np.array_equal(res.converged, ocv)
+        assert_close(res.marginals, om, what="wide_cards eps", **TOL[precision])
+
+
+def test_cardinality_above_128_is_refused(BP):
+    from bayesiannetwork_b200.engine import BnbpError
+    net = synth._assemble([129, 2], [[], [0]], 92, "too_wide")
+    with pytest.raises(BnbpError, match="cardinality > 128"):
+        BP(net)
