@@ -63,13 +63,18 @@ def _precompile_one(v):
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--precompile", action="store_true")
-    ap.add_argument("--cases", type=int, default=1 << 16)
+    ap.add_argument("--cases", default=str(1 << 16), help="batch size, or a comma-separated list of them")
     ap.add_argument("--sweeps", type=int, default=50)
     ap.add_argument("--only", default="", help="comma-separated variant names")
     args = ap.parse_args()
     if args.precompile:
         precompile()
         return
+    for n in [int(c) for c in str(args.cases).split(",")]:
+        run(args, n)
+
+
+def run(args, n):
     import numpy as np
     import torch
     from bayesiannetwork_b200 import synth
@@ -79,7 +84,7 @@ def main():
 
     dev = torch.device("cuda:0")
     net = synth.grid(100)
-    n, sweeps = args.cases, args.sweeps
+    sweeps = args.sweeps
     S, V = net.state_values, net.belief_values
     peak = 6544.0
     try:
