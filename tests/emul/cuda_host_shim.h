@@ -24,7 +24,7 @@ static emul_dim3 threadIdx, blockIdx, gridDim;
 template <typename U> static inline U __ldg(const U* p) { return *p; }
 static inline double __dmul_rn(double a, double b) { return a * b; }      // built with -ffp-contract=off
 static inline float __fmul_rn(float a, float b) { return a * b; }
-static inline unsigned __activemask() { return 1u; }                      // one "lane" at a time
+static inline unsigned __activemask() { return 1u << (threadIdx.x & 31); } // one lane at a time: the calling one is the only live lane
 static inline int __ffs(unsigned v) { return __builtin_ffs((int)v); }
 static inline void __syncwarp() {}
 // inline PTX exists only in code paths of the on-chip kernel (discarded `if constexpr` branches here)

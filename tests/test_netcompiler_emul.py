@@ -227,3 +227,42 @@ def test_grid100_is_walked_class_by_class(engine):
     assert sorted(seen) == list(range(net.n_nodes))
     with pytest.raises(engine.BnbpError, match="variants 0-4"):
         engine.spec_source(net, "fp64", 6)
+
+
+def run_eps(k, net, ev, eps, cap):
+    """The host loop of an epsilon-mode run on the freeze + check variant (bnbp_api.cu run_chunk, check_interval 1): launch t
+    tests its own sweep (delta_cur) and freezes the cases whose delta of launch t-1 was below epsilon (status / sweeps),
+    three delta buffers rotate; what is still running after the last launch is settled from its last delta."""
+    st = initial_state(net, ev, k)
+    n = st["tiles"] * k.TBC
+    floor = np.finfo(k.T).tiny
+    delta = [np.full(n, floor, k.T) for _ in range(3)]
+    status, sweeps, last_active = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.full(1, -1, np.int32)
+    msg = st["msg"]
+    t = 0
+    while t < cap:
+        pc = dict(delta_prev=delta[(t + 2) % 3], delta_cur=delta[t % 3], delta_next=delta[(t + 1) % 3],
+                  status=status, sweeps=sweeps, last_active=last_active)
+        k.launch(st, msg[t & 1], msg[(t + 1) & 1], eps=eps, sweep_index=t, prev_tested=1 if t > 0 else 0, per_case=pc)
+        t += 1
+        if last_active[0] < t - 1:                            # the launch found every case frozen: nothing ran
+            t -= 1
+            break
+    last = delta[(t - 1) % 3]
+    conv = status.astype(bool) | (last < eps)
+    sw = np.where(status.astype(bool), sweeps, t)
+    return st, sw[:ev.n_cases], conv[:ev.n_cases]
+
+
+@pytest.mark.parametrize("name,classloop", [("alarm37", False), ("alarm37", True), ("grid6", True), ("polytree40", True)])
+def test_epsilon_mode_on_the_host_stops_where_the_oracle_stops(engine, oracle_mod, tmp_path, name, classloop):
+    net = {"alarm37": synth.alarm37, "grid6": lambda: synth.grid(6), "polytree40": lambda: synth.random_polytree(40, card_hi=4, max_parents=3, seed=11)}[name]()
+    net.name = name
+    ev = synth.make_evidence(net, 140, seed=5, **(dict(exact_k=4) if name == "alarm37" else dict(p=0.15)))
+    eps = 1e-6
+    want, osw, ocv = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=300)
+    k = Emulated(engine, net, "fp64", 2, classloop, str(tmp_path))
+    st, sw, conv = run_eps(k, net, ev, eps, 300)
+    assert np.array_equal(sw, osw), np.nonzero(sw != osw)[0][:8]
+    assert np.array_equal(conv, ocv.astype(bool))
+    assert_close(beliefs(net, st, ev.n_cases), want, 1e-9, 1e-12, f"{name} eps mode")
