@@ -100,6 +100,7 @@ bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
     (void)fp32;
     auto no = [&](const char* w) { if (why) *why = w; return false; };
     if (L.N < 1) return no("empty network");
+    if (L.N > (1 << 18)) return no("more than 262 144 nodes: the record table is compiled into the kernel image");
     const std::vector<std::vector<int>> cls = spec_classes(L);
     if (cls.size() > 96) return no("more than 96 node shape classes: one unrolled body per class would not fit the instruction caches");
     double fma = 0;
