@@ -1814,7 +1814,14 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         // class-looped walks over SMALL nodes (the grid of cfg 3: 20 input values per node, 128 registers) keep one more
         // block per SM resident: 16 warps with a node's loads in flight each instead of 12, and the 512 tiles of the 65 536
         // cases of cfg 3 are ONE wave of 148 x 4 blocks instead of 1.15 waves of 148 x 3
-        if (h->spec_classloop && class_max_inputs(L) <= 24) h->spec_minb = h->precision == BNBP_FP32 ? 5 : 4;
+        // Large node classes the other way round: the loop holds the inputs of two nodes, so above ~36 values per node the
+        // 168-register cap of 3 blocks per SM spills (168-352 B of stack per thread on 3-4-state nodes with 3-4 parents); at
+        // 2 blocks per SM the same classes fit the register file, and a node of that size keeps 40+ rows in flight per warp.
+        if (h->spec_classloop) {
+            const int inputs = class_max_inputs(L);
+            if (inputs <= 24) h->spec_minb = h->precision == BNBP_FP32 ? 5 : 4;
+            else if (inputs > 36) h->spec_minb = h->precision == BNBP_FP32 ? 3 : 2;
+        }
         if (const char* ev = getenv("BNBP_SPEC_VEC")) {
             const int v = atoi(ev);
             if (v == 1 || v == 2 || (v == 4 && h->tsize == 4)) h->spec_vec = v;
