@@ -11,6 +11,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <dlfcn.h>
+#include <map>
 #include <mutex>
 #include <sstream>
 #include <sys/stat.h>
@@ -67,13 +68,12 @@ static std::vector<int> node_shape(const SpecLayout& L, int x)
 
 std::vector<std::vector<int>> spec_classes(const SpecLayout& L)
 {
-    std::vector<std::vector<int>> keys, members;
+    std::map<std::vector<int>, size_t> index;            // shape -> class, classes numbered in order of first appearance
+    std::vector<std::vector<int>> members;
     for (int x = 0; x < L.N; ++x) {
-        const std::vector<int> key = node_shape(L, x);
-        size_t c = 0;
-        while (c < keys.size() && keys[c] != key) ++c;
-        if (c == keys.size()) { keys.push_back(key); members.emplace_back(); }
-        members[c].push_back(x);
+        const auto it = index.emplace(node_shape(L, x), members.size());
+        if (it.second) members.emplace_back();
+        members[it.first->second].push_back(x);
     }
     return members;
 }
@@ -101,6 +101,7 @@ bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
     auto no = [&](const char* w) { if (why) *why = w; return false; };
     if (L.N < 1) return no("empty network");
     if (L.N > (1 << 18)) return no("more than 262 144 nodes: the record table is compiled into the kernel image");
+    if (L.cpt_values > 0x7fffffffLL || (int64_t)L.PL + L.M > 0x7fffffffLL) return no("offsets beyond 32 bits (the record table holds ints)");
     const std::vector<std::vector<int>> cls = spec_classes(L);
     if (cls.size() > 96) return no("more than 96 node shape classes: one unrolled body per class would not fit the instruction caches");
     double fma = 0;
@@ -108,11 +109,9 @@ bool class_eligible(const SpecLayout& L, bool fp32, std::string* why)
         const NodeMeta& nd = L.nodes[mem[0]];
         if (nd.k > 6) return no("in-degree > 6: accumulators would not fit the register file");
         if (nd.card > 16) return no("cardinality > 16: accumulators would not fit the register file");
-        int sum_ru = 0;
         int64_t Q = 1;
         for (int j = 0; j < nd.k; ++j) {
             if (L.e_card[nd.e0 + j] > 16) return no("parent cardinality > 16");
-            sum_ru += L.e_card[nd.e0 + j];
             Q *= L.e_card[nd.e0 + j];
         }
         if (nd.m > 64) return no("a hub with more than 64 children: its class record would not stay in registers");
