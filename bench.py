@@ -887,9 +887,19 @@ def main():
             if only and key not in only:
                 continue
             for precision in precisions:
-                configs.append(measure_config(key, workload, total, base_gpus, precision, samples[1 if world > 1 else 0], binding,
-                                              torch=torch, dist=dist, dev=dev, local_rank=local_rank, rank=rank, world=world,
-                                              with_cpu=not args.no_cpu, hostpg=hostpg))
+                try:
+                    configs.append(measure_config(key, workload, total, base_gpus, precision, samples[1 if world > 1 else 0], binding,
+                                                  torch=torch, dist=dist, dev=dev, local_rank=local_rank, rank=rank, world=world,
+                                                  with_cpu=not args.no_cpu, hostpg=hostpg))
+                except Exception as e:            # (a parity sample that is off ends the run inside measure_config: fatal())
+                    if world > 1:                 # the ranks meet at barriers inside the entry: one of them cannot skip it alone
+                        raise
+                    # one GPU: an entry that cannot run here (e.g. no room for its state arena beside another tenant of the
+                    # box) is reported as such; the headline measurement above stands on its own
+                    configs.append({"config": key, "workload": workload, "dtype": "f64" if precision == "fp64" else "f32",
+                                    "value": None, "unit": UNIT, "error": repr(e)[:600]})
+                    gc.collect()
+                    torch.cuda.empty_cache()
 
     if rank == 0:
         line = {
