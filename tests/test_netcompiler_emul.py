@@ -266,3 +266,16 @@ def test_epsilon_mode_on_the_host_stops_where_the_oracle_stops(engine, oracle_mo
     assert np.array_equal(sw, osw), np.nonzero(sw != osw)[0][:8]
     assert np.array_equal(conv, ocv.astype(bool))
     assert_close(beliefs(net, st, ev.n_cases), want, 1e-9, 1e-12, f"{name} eps mode")
+
+
+@pytest.mark.parametrize("classloop", [False, True], ids=["unrolled", "classloop"])
+def test_float_kernels_on_the_host_hold_the_fp32_bar(engine, oracle_mod, tmp_path, classloop):
+    """fp32 handles: the same generated code with T = float against the double-precision oracle at the fp32 bar of
+    BASELINE.json (1e-5 relative + 1e-7 absolute) after 12 sweeps of a loopy network."""
+    net = synth.grid(6)
+    net.name = "grid6"
+    ev = synth.make_evidence(net, 200, seed=8, p=0.15)
+    ks = {v: Emulated(engine, net, "fp32", v, classloop, str(tmp_path)) for v in (0, 3, 4)}
+    st, _ = run_fixed(ks, net, ev, 12)
+    want, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=12)
+    assert_close(beliefs(net, st, ev.n_cases), want, 1e-5, 1e-7, "grid6 fp32")

@@ -165,3 +165,27 @@ def test_max_product_port_gives_max_marginals_on_polytrees(oracle_mod):
     # and it is a different thing from the sum-product marginals
     sump, _, _ = oracle_mod.run_port(net, ev, eps=1e-13, max_sweeps=100)
     assert np.abs(sump - got).max() > 1e-3
+
+
+def test_textbook_burglary_network_known_answer(oracle_mod):
+    """A number from the literature, independent of this repo and of the reference: Pearl's burglary / earthquake alarm
+    network with the probabilities of Russell & Norvig (AIMA, fig. 14.2) gives P(Burglary | JohnCalls, MaryCalls) = 0.284
+    (AIMA section 14.4).  The network is a polytree, so belief propagation is exact on it."""
+    # nodes: 0 Burglary, 1 Earthquake, 2 Alarm (parents 0, 1), 3 JohnCalls (2), 4 MaryCalls (2); state 0 = true, 1 = false
+    card = [2, 2, 2, 2, 2]
+    parents = [[], [], [0, 1], [2], [2]]
+    net = synth._assemble(card, parents, 1, "burglary")
+    cpt = [0.001, 0.999,                      # P(B)
+           0.002, 0.998,                      # P(E)
+           0.95, 0.05, 0.94, 0.06, 0.29, 0.71, 0.001, 0.999,    # P(A | B, E): rows (t,t) (t,f) (f,t) (f,f), first parent slowest
+           0.90, 0.10, 0.05, 0.95,            # P(J | A)
+           0.70, 0.30, 0.01, 0.99]            # P(M | A)
+    net.cpt[:] = cpt
+    ev = EvidenceBatch.from_cases(net, [{3: 0, 4: 0}, {}])
+    m, sw, cv = oracle_mod.run_port(net, ev, eps=1e-12, max_sweeps=100)
+    assert cv.all()
+    assert abs(m[0, 0] - 0.284) < 5e-4                        # P(b | j, m) = 0.284
+    exact = 0.001 * (0.002 * 0.95 * 0.9 * 0.7 + 0.998 * 0.94 * 0.9 * 0.7 + 0.002 * 0.05 * 0.05 * 0.01 + 0.998 * 0.06 * 0.05 * 0.01)
+    other = 0.999 * (0.002 * 0.29 * 0.9 * 0.7 + 0.998 * 0.001 * 0.9 * 0.7 + 0.002 * 0.71 * 0.05 * 0.01 + 0.998 * 0.999 * 0.05 * 0.01)
+    assert abs(m[0, 0] - exact / (exact + other)) < 1e-12
+    assert abs(m[1, 0] - 0.001) < 1e-15 and abs(m[1, 4 * 2 - 2] - 0.05210) < 5e-5          # priors: P(b), P(j) = 0.0521
