@@ -183,3 +183,14 @@ def test_barrier_placement_under_thread_sanitizer(engine, oracle_mod, tmp_path, 
     want, osw, _ = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap)
     assert np.array_equal(sw, osw)
     assert_close(got, want, 1e-9, 1e-12, "on chip under ThreadSanitizer")
+
+
+def test_float_handles_on_chip_hold_the_fp32_bar(engine, oracle_mod, tmp_path):
+    net = _net("alarm37")
+    ev = synth.make_evidence(net, 130, seed=17, exact_k=4)
+    k = OnchipEmulated(engine, net, "fp32", 8, str(tmp_path))
+    assert k.OUT == np.float32                                    # marginals in the handle's precision (bnbp_run_params.out_precision)
+    want, osw, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=20)
+    got, sw, _ = k.run(ev, 0.0, 20)
+    assert np.array_equal(sw, osw)
+    assert_close(got, want, 1e-5, 1e-7, "alarm37 on chip, fp32")
