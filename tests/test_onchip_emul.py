@@ -194,3 +194,41 @@ def test_float_handles_on_chip_hold_the_fp32_bar(engine, oracle_mod, tmp_path):
     got, sw, _ = k.run(ev, 0.0, 20)
     assert np.array_equal(sw, osw)
     assert_close(got, want, 1e-5, 1e-7, "alarm37 on chip, fp32")
+
+
+def test_edge_batches_and_the_reference_fixtures_on_chip(engine, oracle_mod, ref_fixtures, tmp_path):
+    """Batches around the group width (1 ... 65 cases: lanes without a case, one refill with a single case), no evidence
+    at all, every node observed, a sweep cap below the test interval, an epsilon nothing undercuts -- and the reference's own
+    test graphs (Pearl, the resume graph, the impossible-evidence case) from the outputs of the compiled reference."""
+    from bayesiannetwork_b200.flat import EvidenceBatch
+    from helpers import load_fixture
+    net = _net("alarm37")
+    k8 = OnchipEmulated(engine, net, "fp64", 8, str(tmp_path))
+    k9 = OnchipEmulated(engine, net, "fp64", 9, str(tmp_path))
+
+    def check(k, ev, eps, cap, **kw):
+        want, osw, ocv = oracle_mod.run_port(net, ev, eps=eps, max_sweeps=cap, damping=kw.get("damping", 0.0),
+                                             check_interval=kw.get("interval", 1))
+        got, sw, conv = k.run(ev, eps, cap, **kw)
+        assert np.array_equal(sw, osw) and np.array_equal(conv, ocv)
+        assert_close(got, want, 1e-9, 1e-12, f"{ev.n_cases} cases, eps {eps}, cap {cap}, {kw}")
+
+    for n in (1, 31, 33, 65):
+        ev = synth.make_evidence(net, n, seed=n, exact_k=4)
+        check(k8, ev, 0.0, 5)
+        check(k9, ev, 1e-6, 200)
+    check(k9, EvidenceBatch.empty(40), 1e-6, 100)
+    everything = EvidenceBatch.from_cases(net, [{x: int((x + c) % net.card[x]) for x in range(net.n_nodes)} for c in range(5)])
+    check(k8, everything, 0.0, 3)
+    ev = synth.make_evidence(net, 50, seed=3, exact_k=4)
+    check(k9, ev, 0.0, 7, damping=0.3)                  # a fixed count with damping takes the check flavour
+    check(k9, ev, 1e-6, 3, interval=5)                  # the cap comes before the first tested sweep
+    check(k9, ev, 1e-13, 60)
+    check(k9, ev, 10.0, 30)                             # every case stops after its first sweep
+    for name in ("pearl_tests", "pearl_nan", "resume_tests", "pearl_one_sweep"):
+        f = load_fixture(ref_fixtures, name)
+        f["net"].name = name
+        kk = OnchipEmulated(engine, f["net"], "fp64", 9 if f["eps"] > 0 else 8, str(tmp_path))
+        got, sw, conv = kk.run(f["ev"], f["eps"], f["max_sweeps"] if f["max_sweeps"] > 0 else 1 << 20)
+        assert np.array_equal(sw, f["sweeps"]) and np.array_equal(conv, f["converged"]), name
+        assert_close(got, f["marginals"], 1e-9, 1e-12, name)
