@@ -3,7 +3,13 @@
 Cases are independent (belief_propagation.hpp keeps all state per call, :162-172), so there is NO
 data-path collective.  The only exchanges are the two the north star names: the global convergence
 summary (sum of sweeps, all-converged flag) and, on demand, the gather of posterior marginals.
-Works with any ``torch.distributed`` backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests)."""
+Works with any ``torch.distributed`` backend (``nccl`` on the GPU box, ``gloo`` in the CPU tests).
+
+Since round 2 the PRODUCT's exchanges live inside libbnbp (``bnbp_comm_*``, ``bnbp_create_multi``, the chunked gather
+overlapped with the kernels: ``engine.BeliefPropagation.comm_init`` / ``run_device(gather=True)`` / ``comm_summary``),
+where a C++ host can reach them.  What stays here is the sharding arithmetic (the same ranges the library cuts,
+``shard_range``) and torch-level equivalents of the two exchanges, which the world-size-2 gloo tests use to check the
+host logic on a machine without GPUs (``tests/test_dist_gloo.py``)."""
 from __future__ import annotations
 
 from typing import Tuple
