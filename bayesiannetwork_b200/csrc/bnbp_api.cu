@@ -185,6 +185,8 @@ struct bnbp_handle {
     int spec_vec = 1, spec_minb = 1, spec_ahead = 1;
     bool spec_classloop = false;       // the specialised walk loops over node SHAPE classes (networks too large to unroll)
     int spec_classes_n = 0;
+    bool spec_auto_ok = true;          // may AUTO compile the specialised kernels at first use? (false: NVRTC would need minutes
+    bool oc_auto_ok = true;            //  for an unrolled walk of this size and no cubin is cached -- ALWAYS still compiles them)
     static constexpr int NSPEC = 8;    // variants of bnbp_spec.cuh
     SpecKernel spec[NSPEC];            // + 3 plain-first (no message loads), 4 plain-last (no message stores),
                                        //   5 first + K0, 6/7 last + K4 (marginals in T / in double)
@@ -513,8 +515,8 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
         // code per sweep, a retire / refill path every few sweeps) runs at 302 M executed case-sweeps/s on alarm37 against
         // 357-381 M for the streaming kernels with the split convergence test (r02b vs r01fin)
         const bool plain_run = !(prm.epsilon > 0.0) && prm.damping == 0.0;
-        const bool want_oc = mode > 0 || (mode == 0 && h->specialize == BNBP_SPEC_AUTO && h->oc_eligible && !soft_evidence &&
-                                          n_cases >= 4096 && plain_run);
+        const bool want_oc = mode > 0 || (mode == 0 && h->specialize == BNBP_SPEC_AUTO && h->oc_eligible && h->oc_auto_ok &&
+                                          !soft_evidence && n_cases >= 4096 && plain_run);
         if (want_oc) {
             if (!h->oc_eligible) return fail(BNBP_ERR_INVALID, "onchip=ALWAYS but the network is not eligible: " + h->oc_why);
             if (soft_evidence) return fail(BNBP_ERR_INVALID, "onchip=ALWAYS: soft evidence rows take the streaming kernels");
@@ -531,7 +533,7 @@ int choose_kernels(bnbp_handle* h, int64_t n_cases, const bnbp_run_params& prm, 
         }
     }
     bool want = h->specialize == BNBP_SPEC_ALWAYS ||
-                (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && n_cases >= 4096);
+                (h->specialize == BNBP_SPEC_AUTO && h->spec_eligible_ && h->spec_auto_ok && n_cases >= 4096);
     if (want && h->spec_classloop && h->specialize == BNBP_SPEC_AUTO) {
         // A class-looped walk covers a batch that does not fill the SMs with node slices in grid.y -- in its PLAIN variants.
         // The freeze / check variants (epsilon mode below the split threshold, damping) keep per-case state one block must
@@ -1783,16 +1785,46 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
             h->spec_eligible_ = false;
             h->spec_why = "the dense contraction path is active for this network";
         }
-        // Class-looped walk (bnbp_spec.cuh, BNBP_CLASSLOOP): networks the unrolled walk refuses for their SIZE whose
-        // nodes fall into few shape classes -- one unrolled body per class, looped over the class's nodes (cfg 3: the
-        // 10 000-node grid has 9 classes).  BNBP_CLASSLOOP=0 never, 1 (default) where the unrolled walk is refused,
-        // 2 wherever possible (the tests run the small networks through both code generators).
+        // measured on B200 (profiles/r01c): one case per thread beats 2/4 in both precisions -- the
+        // kernel is HBM-latency bound, so resident warps (registers per thread) matter more than
+        // wider accesses; fp64 1.147 ms/sweep at (1,3,1), fp32 0.620 ms at (1,4,1) for 1M alarm37 cases
+        h->spec_vec = 1;
+        h->spec_minb = h->precision == BNBP_FP32 ? 4 : 3;
+        h->spec_ahead = 1;
+        auto env_knobs = [&]() {                       // tuning knobs win over every rule below
+            if (const char* ev = getenv("BNBP_SPEC_VEC")) {
+                const int v = atoi(ev);
+                if (v == 1 || v == 2 || (v == 4 && h->tsize == 4)) h->spec_vec = v;
+            }
+            if (const char* ev = getenv("BNBP_SPEC_MINB")) h->spec_minb = std::min(16, std::max(1, atoi(ev)));
+            if (const char* ev = getenv("BNBP_SPEC_AHEAD")) h->spec_ahead = std::min(4, std::max(0, atoi(ev)));
+        };
+        env_knobs();
+        // What the FIRST use of an unrolled walk costs: NVRTC time grows like N^2.4 with the node count (one variant, measured on
+        // the build box: 37 nodes 13 s, 49: 21 s, 64: 44 s, 100: 144 s, 144: 451 s) and a run needs two to four variants.  Above
+        // 64 nodes the unrolled kernels are therefore taken only when their cubin is already in the cache (bnbp_precompile, or an
+        // earlier ALWAYS run); otherwise the class-looped walk is preferred where the network allows it -- its compile time grows
+        // with the CLASS count (10 000-node grid, 6 classes: 3 s; 100-node DAG, 63 classes: 31 s) -- and else the generic kernel.
+        constexpr int UNROLL_FAST_NODES = 64;
+        const bool static_ok = h->spec_eligible_;
+        bool static_slow = false;
+        if (static_ok && h->N > UNROLL_FAST_NODES) {
+            SpecConfig cfg;
+            cfg.fp32 = h->precision == BNBP_FP32;
+            cfg.vec = h->spec_vec; cfg.minb = spec_minb_for(h, 0); cfg.variant = 0; cfg.ahead = h->spec_ahead;
+            static_slow = !spec_in_cache(spec_source(L, cfg));
+        }
+        h->spec_auto_ok = true;
+        // Class-looped walk (bnbp_spec.cuh, BNBP_CLASSLOOP): networks the unrolled walk refuses for their SIZE -- or would
+        // take minutes to compile -- whose nodes fall into few shape classes: one unrolled body per class, looped over the
+        // class's nodes (cfg 3: the 10 000-node grid has 6 classes).  BNBP_CLASSLOOP=0 never, 1 (default) where the unrolled
+        // walk is refused or slow to compile, 2 wherever possible (the tests run the small networks through both generators).
         {
             int mode = 1;
             if (const char* ev = getenv("BNBP_CLASSLOOP")) mode = atoi(ev);
             h->spec_classloop = false;
             h->spec_classes_n = 0;
-            if (mode != 0 && (!h->spec_eligible_ || mode >= 2)) {
+            if (mode != 0 && (!static_ok || static_slow || mode >= 2)) {
                 std::string why2 = "the dense contraction path is active for this network";
                 if (h->TS == 0 && class_eligible(L, h->precision == BNBP_FP32, &why2)) {
                     h->spec_eligible_ = true;
@@ -1804,13 +1836,12 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
                     h->spec_why += "; class-looped walk: " + why2;
                 }
             }
+            if (static_slow && !h->spec_classloop) {
+                h->spec_auto_ok = false;
+                h->spec_why = "an unrolled walk of " + std::to_string(h->N) + " nodes takes NVRTC minutes and is not in the cubin cache "
+                              "(bnbp_precompile or specialize = ALWAYS compiles it once); AUTO keeps the generic kernel";
+            }
         }
-        // measured on B200 (profiles/r01c): one case per thread beats 2/4 in both precisions -- the
-        // kernel is HBM-latency bound, so resident warps (registers per thread) matter more than
-        // wider accesses; fp64 1.147 ms/sweep at (1,3,1), fp32 0.620 ms at (1,4,1) for 1M alarm37 cases
-        h->spec_vec = 1;
-        h->spec_minb = h->precision == BNBP_FP32 ? 4 : 3;
-        h->spec_ahead = 1;
         // class-looped walks over SMALL nodes (the grid of cfg 3: 20 input values per node, 128 registers) keep one more
         // block per SM resident: 16 warps with a node's loads in flight each instead of 12, and the 512 tiles of the 65 536
         // cases of cfg 3 are ONE wave of 148 x 4 blocks instead of 1.15 waves of 148 x 3
@@ -1821,13 +1852,8 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
             const int inputs = class_max_inputs(L);
             if (inputs <= 24) h->spec_minb = h->precision == BNBP_FP32 ? 5 : 4;
             else if (inputs > 36) h->spec_minb = h->precision == BNBP_FP32 ? 3 : 2;
+            env_knobs();
         }
-        if (const char* ev = getenv("BNBP_SPEC_VEC")) {
-            const int v = atoi(ev);
-            if (v == 1 || v == 2 || (v == 4 && h->tsize == 4)) h->spec_vec = v;
-        }
-        if (const char* ev = getenv("BNBP_SPEC_MINB")) h->spec_minb = std::min(16, std::max(1, atoi(ev)));
-        if (const char* ev = getenv("BNBP_SPEC_AHEAD")) h->spec_ahead = std::min(4, std::max(0, atoi(ev)));
         // ---- on-chip kernel: the state of a 32-case group (pi/lambda + both message buffers) must fit the
         //      shared memory of one CTA
         constexpr size_t SMEM_OPTIN = 227 * 1024;
@@ -1846,6 +1872,15 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
         h->oc_minb = (int)std::max<size_t>(1, std::min<size_t>(8, (228 * 1024) / (h->oc_smem + 1024)));
         if (const char* ev = getenv("BNBP_OC_MINB")) h->oc_minb = std::min(16, std::max(1, atoi(ev)));
         spec_partition(L, h->oc_roles, &h->oc_imbalance);
+        // the on-chip kernel is an unrolled walk too (64 nodes: 76 s of NVRTC): same first-use rule
+        h->oc_auto_ok = true;
+        if (h->oc_eligible && h->N > UNROLL_FAST_NODES) {
+            SpecConfig cfg;
+            cfg.fp32 = h->precision == BNBP_FP32;
+            cfg.vec = 1; cfg.minb = h->oc_minb; cfg.variant = 8; cfg.ahead = h->oc_ahead;
+            cfg.roles = h->oc_roles; cfg.out_double = false;
+            h->oc_auto_ok = spec_in_cache(spec_source(L, cfg));
+        }
     }
     return BNBP_OK;
 }

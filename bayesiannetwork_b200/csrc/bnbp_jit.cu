@@ -398,23 +398,42 @@ std::string spec_cache_dir()
     return "/tmp/bnbp_jitcache_" + std::to_string((long)geteuid());
 }
 
+static const char* const kNvrtcOpts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
+constexpr int kNvrtcOptCount = (int)(sizeof kNvrtcOpts / sizeof kNvrtcOpts[0]);
+
+// file of the cubin of `source` in the cache (key: source text + compiler options)
+static std::string cache_path(const std::string& source)
+{
+    uint64_t h1 = fnv1a(source.data(), source.size(), 0xcbf29ce484222325ull);
+    uint64_t h2 = fnv1a(source.data(), source.size(), 0x84222325cbf29ce4ull);
+    for (int i = 0; i < kNvrtcOptCount; ++i) {
+        h1 = fnv1a(kNvrtcOpts[i], strlen(kNvrtcOpts[i]), h1);
+        h2 = fnv1a(kNvrtcOpts[i], strlen(kNvrtcOpts[i]), h2);
+    }
+    char name[64];
+    snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
+    return spec_cache_dir() + "/" + name;
+}
+
+bool spec_in_cache(const std::string& source)
+{
+    if (getenv("BNBP_NO_CACHE")) return false;
+    struct stat sb;
+    return stat(cache_path(source).c_str(), &sb) == 0 && sb.st_uid == geteuid() && sb.st_size > 0;
+}
+
 bool spec_compile(const std::string& source, std::vector<char>* cubin, bool* from_cache, double* ms, std::string* err,
                   bool bypass_cache)
 {
-    const char* opts[] = {"--gpu-architecture=sm_100a", "--std=c++17", "-lineinfo", "-default-device"};
-    const int n_opts = (int)(sizeof opts / sizeof opts[0]);
-    uint64_t h1 = fnv1a(source.data(), source.size(), 0xcbf29ce484222325ull);
-    uint64_t h2 = fnv1a(source.data(), source.size(), 0x84222325cbf29ce4ull);
-    for (int i = 0; i < n_opts; ++i) { h1 = fnv1a(opts[i], strlen(opts[i]), h1); h2 = fnv1a(opts[i], strlen(opts[i]), h2); }
+    const char* const* opts = kNvrtcOpts;
+    const int n_opts = kNvrtcOptCount;
     // (The compiler version is deliberately NOT part of the key.  It was for a while -- a cubin of another toolkit should
     //  not be picked up -- but a process that has PyTorch loaded resolves libnvrtc.so.12 to PyTorch's bundled copy (12.8
     //  against the toolkit's 12.9), so every kernel precompiled at build time missed the cache and the GPU test run paid
     //  15-80 s of NVRTC per kernel, r02o.  A cubin this driver cannot load is instead replaced on the spot: ensure_spec /
     //  ensure_onchip recompile with bypass_cache when cuModuleLoadData refuses a cached one.)
-    char name[64];
-    snprintf(name, sizeof name, "%016llx%016llx.cubin", (unsigned long long)h1, (unsigned long long)h2);
     const std::string dir = spec_cache_dir();
-    const std::string path = dir + "/" + name;
+    const std::string path = cache_path(source);
     if (from_cache) *from_cache = false;
     if (ms) *ms = 0.0;
     if (!getenv("BNBP_NO_CACHE") && !bypass_cache) {

@@ -90,6 +90,9 @@ struct SpecKernel {                 // one loaded cubin
 bool spec_compile(const std::string& source, std::vector<char>* cubin, bool* from_cache, double* ms, std::string* err,
                   bool bypass_cache = false);
 
+// Is the cubin of this source in the on-disk cache (so that using it costs no NVRTC time)?
+bool spec_in_cache(const std::string& source);
+
 // Load a cubin into the current context and resolve the kernel + the CPT constant.  threads / smem: the launch
 // shape the occupancy is asked for (the on-chip kernel opts in to its dynamic shared memory here).
 bool spec_load(const std::vector<char>& cubin, SpecKernel* out, std::string* err, const char* entry = "bnbp_spec_sweep",

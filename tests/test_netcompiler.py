@@ -81,3 +81,17 @@ def test_cmake_project_configures(tmp_path):
                        capture_output=True, text=True, env=env)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
     assert (tmp_path / "b" / "gen" / "bnbp_spec_embed.inc").exists()
+
+
+def test_first_use_compile_cost_decides_between_the_generators(engine, tmp_path, monkeypatch):
+    """NVRTC time of an unrolled walk grows like N^2.4 (100 nodes: 144 s per variant), so above 64 nodes the unrolled
+    kernels are taken only from the cubin cache; a network that can be walked class by class gets that generator instead
+    (100-node grid: 6 classes, one second)."""
+    monkeypatch.setenv("BNBP_CACHE_DIR", str(tmp_path))           # an empty cache
+    small, mid = synth.grid(8), synth.grid(10)                    # 64 and 100 nodes, both within the unrolled walk's own bounds
+    assert "#define BNBP_CLASSLOOP 1" not in engine.spec_source(small, "fp64", 0)
+    src = engine.spec_source(mid, "fp64", 0)
+    walk = [l for l in src.splitlines() if l.startswith("#define BNBP_WALK")][0]
+    assert "#define BNBP_CLASSLOOP 1" in src and 4 <= walk.count("BNBP_CLASS(") <= 9
+    monkeypatch.setenv("BNBP_CLASSLOOP", "0")                     # never class-looped: the unrolled source is still on offer
+    assert "struct N99 " in engine.spec_source(mid, "fp64", 0)    # (AUTO runs keep the generic kernel until it is compiled once)
