@@ -19,13 +19,14 @@ int emul_value_bytes() { return (int)sizeof(T); }
 void emul_set_cpt(const T* cpt, long long n) { memcpy(bnbp_cpt, cpt, (size_t)n * sizeof(T)); }
 
 // One launch of <<<(tiles, node_slices), 128>>> bnbp_spec_sweep(pl, cur, nxt, evbits, aux).  delta / status / sweeps / last_active: the
-// per-case arrays of the freeze / check variants (ignored by the plain ones).
+// per-case arrays of the freeze / check variants (ignored by the plain ones).  evst: variant 5 only.
 void emul_launch(T* pl, const T* cur, T* nxt, const unsigned* evbits, int tiles, int n_inner, T eps, T damping,
                  int sweep_index, int prev_tested, const T* delta_prev, T* delta_cur, T* delta_next,
-                 unsigned char* status, int* sweeps, int* last_active, int node_slices)
+                 unsigned char* status, int* sweeps, int* last_active, int node_slices, const unsigned char* evst)
 {
     bnbp_spec::Aux a;
     memset(&a, 0, sizeof a);
+    a.evst = evst;                  // variant 5 (first sweep fused with K0): evidence-state bytes [tiles][N][TBC], 0 = not observed
     a.delta_prev = delta_prev; a.delta_cur = delta_cur; a.delta_next = delta_next;
     a.status = status; a.sweeps = sweeps; a.last_active = last_active;
     a.sweep_index = sweep_index; a.prev_tested = prev_tested;

@@ -59,13 +59,14 @@ class Emulated:
         cpt = np.ascontiguousarray(net.cpt, dtype=self.T)
         self.lib.emul_set_cpt(cpt.ctypes.data_as(C.c_void_p), C.c_longlong(cpt.size))
 
-    def launch(self, st, cur, nxt, n_inner=1, eps=0.0, damping=0.0, sweep_index=0, prev_tested=0, per_case=None, node_slices=1):
+    def launch(self, st, cur, nxt, n_inner=1, eps=0.0, damping=0.0, sweep_index=0, prev_tested=0, per_case=None, node_slices=1,
+               evst=None):
         p = lambda a: a.ctypes.data_as(C.c_void_p) if a is not None else None
         pc = per_case or {}
         self.lib.emul_launch(p(st["pl"]), p(cur), p(nxt), p(st["evbits"]), C.c_int(st["tiles"]), C.c_int(n_inner),
                              self.cT(eps), self.cT(damping), C.c_int(sweep_index), C.c_int(prev_tested),
                              p(pc.get("delta_prev")), p(pc.get("delta_cur")), p(pc.get("delta_next")),
-                             p(pc.get("status")), p(pc.get("sweeps")), p(pc.get("last_active")), C.c_int(node_slices))
+                             p(pc.get("status")), p(pc.get("sweeps")), p(pc.get("last_active")), C.c_int(node_slices), p(evst))
 
 
 def initial_state(net, ev, k):
@@ -279,3 +280,27 @@ def test_float_kernels_on_the_host_hold_the_fp32_bar(engine, oracle_mod, tmp_pat
     st, _ = run_fixed(ks, net, ev, 12)
     want, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=12)
     assert_close(beliefs(net, st, ev.n_cases), want, 1e-5, 1e-7, "grid6 fp32")
+
+
+@pytest.mark.parametrize("name", ["alarm37", "grid6"])
+def test_first_sweep_fused_with_the_initialisation(engine, oracle_mod, tmp_path, name):
+    """Variant 5 (unrolled walks): the time-0 pi / lambda (belief_propagation.hpp:33-73) are formed in registers from one
+    evidence-state byte per (node, case) -- nothing of time 0 is read, so the arena may hold garbage when the run starts."""
+    net = synth.alarm37() if name == "alarm37" else synth.grid(6)
+    net.name = name
+    ev = synth.make_evidence(net, 150, seed=21, **(dict(exact_k=4) if name == "alarm37" else dict(p=0.2)))
+    ks = {v: Emulated(engine, net, "fp64", v, False, str(tmp_path)) for v in (5, 0)}
+    st = initial_state(net, ev, ks[0])
+    evst = np.zeros((st["tiles"], net.n_nodes, ks[0].TBC), np.uint8)
+    for c in range(ev.n_cases):
+        for e in range(int(ev.ev_off[c]), int(ev.ev_off[c + 1])):
+            evst[c // ks[0].TBC, int(ev.ev_node[e]), c % ks[0].TBC] = int(ev.ev_state[e]) + 1
+    st["pl"][:] = np.nan                                      # what K0 would have written is never read ...
+    cur, nxt = st["msg"]
+    cur[:] = np.nan                                           # ... nor are the time-0 messages
+    ks[5].launch(st, cur, nxt, evst=evst)
+    for _ in range(5):
+        cur, nxt = nxt, cur
+        ks[0].launch(st, cur, nxt)
+    want, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=6)
+    assert_close(beliefs(net, st, ev.n_cases), want, 1e-9, 1e-12, f"{name} fused first sweep")
