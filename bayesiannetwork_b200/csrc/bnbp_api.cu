@@ -1853,6 +1853,21 @@ int build_layout(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_han
             if (inputs <= 24) h->spec_minb = h->precision == BNBP_FP32 ? 5 : 4;
             else if (inputs > 36) h->spec_minb = h->precision == BNBP_FP32 ? 3 : 2;
             env_knobs();
+            // the same first-use rule for class-looped walks of MANY classes (~0.5 s of NVRTC per class and variant: 63 classes
+            // 31 s): beyond 24 classes AUTO takes them from the cubin cache only
+            constexpr int CLASS_FAST_COUNT = 24;
+            if (h->spec_classes_n > CLASS_FAST_COUNT) {
+                SpecConfig cfg;
+                cfg.fp32 = h->precision == BNBP_FP32;
+                cfg.vec = h->spec_vec; cfg.minb = spec_minb_for(h, 0); cfg.variant = 0; cfg.ahead = h->spec_ahead;
+                cfg.classloop = true;
+                if (!spec_in_cache(spec_source(L, cfg))) {
+                    h->spec_auto_ok = false;
+                    h->spec_why = "a class-looped walk of " + std::to_string(h->spec_classes_n) + " node classes takes NVRTC half a minute per "
+                                  "variant and is not in the cubin cache (bnbp_precompile or specialize = ALWAYS compiles it once); "
+                                  "AUTO keeps the generic kernel";
+                }
+            }
         }
         // ---- on-chip kernel: the state of a 32-case group (pi/lambda + both message buffers) must fit the
         //      shared memory of one CTA
