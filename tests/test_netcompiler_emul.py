@@ -230,10 +230,11 @@ def test_grid100_is_walked_class_by_class(engine):
         engine.spec_source(net, "fp64", 6)
 
 
-def run_eps(k, net, ev, eps, cap):
-    """The host loop of an epsilon-mode run on the freeze + check variant (bnbp_api.cu run_chunk, check_interval 1): launch t
-    tests its own sweep (delta_cur) and freezes the cases whose delta of launch t-1 was below epsilon (status / sweeps),
-    three delta buffers rotate; what is still running after the last launch is settled from its last delta."""
+def run_eps(k, net, ev, eps, cap, interval=1, k_unchecked=None):
+    """The host loop of an epsilon-mode run (bnbp_api.cu run_chunk): launch t runs the freeze + check variant when its sweep
+    is tested (every `interval`-th sweep and the last one) and the freeze variant otherwise; a launch freezes the cases whose
+    delta of a TESTED launch t-1 was below epsilon (status / sweeps), three delta buffers rotate; what is still running
+    after the last launch is settled from its last delta."""
     st = initial_state(net, ev, k)
     n = st["tiles"] * k.TBC
     floor = np.finfo(k.T).tiny
@@ -241,16 +242,20 @@ def run_eps(k, net, ev, eps, cap):
     status, sweeps, last_active = np.zeros(n, np.uint8), np.zeros(n, np.int32), np.full(1, -1, np.int32)
     msg = st["msg"]
     t = 0
+    prev_tested = False
     while t < cap:
+        tested = (t + 1) % interval == 0 or t + 1 >= cap
         pc = dict(delta_prev=delta[(t + 2) % 3], delta_cur=delta[t % 3], delta_next=delta[(t + 1) % 3],
                   status=status, sweeps=sweeps, last_active=last_active)
-        k.launch(st, msg[t & 1], msg[(t + 1) & 1], eps=eps, sweep_index=t, prev_tested=1 if t > 0 else 0, per_case=pc)
+        (k if tested else k_unchecked).launch(st, msg[t & 1], msg[(t + 1) & 1], eps=eps, sweep_index=t,
+                                              prev_tested=1 if prev_tested else 0, per_case=pc)
         t += 1
         if last_active[0] < t - 1:                            # the launch found every case frozen: nothing ran
             t -= 1
             break
+        prev_tested = tested
     last = delta[(t - 1) % 3]
-    conv = status.astype(bool) | (last < eps)
+    conv = status.astype(bool) | ((last < eps) & prev_tested)
     sw = np.where(status.astype(bool), sweeps, t)
     return st, sw[:ev.n_cases], conv[:ev.n_cases]
 
@@ -304,3 +309,56 @@ def test_first_sweep_fused_with_the_initialisation(engine, oracle_mod, tmp_path,
         ks[0].launch(st, cur, nxt)
     want, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=6)
     assert_close(beliefs(net, st, ev.n_cases), want, 1e-9, 1e-12, f"{name} fused first sweep")
+
+
+def test_epsilon_mode_tested_every_third_sweep(engine, oracle_mod, tmp_path):
+    """check_interval = 3 (extension): untested sweeps run the freeze variant (1), tested ones the freeze + check variant (2)."""
+    net = synth.alarm37()
+    net.name = "alarm37"
+    ev = synth.make_evidence(net, 140, seed=6, exact_k=4)
+    want, osw, ocv = oracle_mod.run_port(net, ev, eps=1e-6, max_sweeps=300, check_interval=3)
+    k1, k2 = (Emulated(engine, net, "fp64", v, False, str(tmp_path)) for v in (1, 2))
+    st, sw, conv = run_eps(k2, net, ev, 1e-6, 300, interval=3, k_unchecked=k1)
+    assert np.array_equal(sw, osw) and (osw % 3 == 0).all()
+    assert np.array_equal(conv, ocv.astype(bool))
+    assert_close(beliefs(net, st, ev.n_cases), want, 1e-9, 1e-12, "alarm37 eps mode, interval 3")
+
+
+@pytest.mark.parametrize("precision,variant", [("fp64", 6), ("fp32", 6), ("fp32", 7)], ids=["fp64", "fp32", "fp32_double_marginals"])
+def test_last_sweep_fused_with_the_beliefs(engine, oracle_mod, tmp_path, precision, variant):
+    """Variants 6 / 7: the new pi / lambda of the last sweep stay in registers and BEL = normalize(pi .* lambda)
+    (belief_propagation.hpp:151-158) leaves through a per-warp shared-memory tile as contiguous row segments of the
+    case-major marginals -- a warp-cooperative kernel, emulated with one OS thread per CUDA thread of a block
+    (tests/emul/spec_block_emul.cpp).  A ragged last tile: rows beyond the batch are never written."""
+    net = synth.alarm37()
+    net.name = "alarm37"
+    ev = synth.make_evidence(net, 150, seed=22, exact_k=4)
+    ks = {v: Emulated(engine, net, precision, v, False, str(tmp_path)) for v in (3, 0)}
+    src = engine.spec_source(net, precision, variant)
+    cu, so = str(tmp_path / f"last{variant}.cu"), str(tmp_path / f"last{variant}.so")
+    open(cu, "w").write(src)
+    cmd = ["g++", "-O0", "-std=c++17", "-ffp-contract=off", "-fvisibility=hidden", "-fno-gnu-unique", "-Wno-unknown-pragmas",
+           "-I", os.path.join(HERE, "emul"), f'-DBNBP_GENERATED="{cu}"', "-shared", "-fPIC", "-pthread", "-o", so,
+           os.path.join(HERE, "emul", "spec_block_emul.cpp")]
+    r = subprocess.run(cmd, capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr[-3000:]
+    lib = C.CDLL(so)
+    T = ks[0].T
+    OUT = np.float32 if lib.emul_out_bytes() == 4 else np.float64
+    assert OUT == (np.float64 if variant == 7 or precision == "fp64" else np.float32) and lib.emul_v() == net.belief_values
+    cpt = np.ascontiguousarray(net.cpt, dtype=T)
+    lib.emul_set_cpt(cpt.ctypes.data_as(C.c_void_p), C.c_longlong(cpt.size))
+    st = initial_state(net, ev, ks[0])
+    cur, nxt = st["msg"]
+    ks[3].launch(st, cur, nxt)
+    for _ in range(4):
+        cur, nxt = nxt, cur
+        ks[0].launch(st, cur, nxt)
+    cur, nxt = nxt, cur
+    out = np.full((ev.n_cases + 5, net.belief_values), -7.0, OUT)          # five guard rows behind the batch
+    p = lambda a: a.ctypes.data_as(C.c_void_p)
+    lib.emul_launch_last(p(st["pl"]), p(cur), p(nxt), p(st["evbits"]), C.c_int(st["tiles"]), p(out), C.c_longlong(ev.n_cases))
+    want, _, _ = oracle_mod.run_port(net, ev, eps=0.0, max_sweeps=6)
+    tol = (1e-9, 1e-12) if precision == "fp64" else (1e-5, 1e-7)
+    assert_close(out[:ev.n_cases], want, *tol, f"fused last sweep {precision} v{variant}")
+    assert (out[ev.n_cases:] == -7.0).all()
