@@ -80,3 +80,21 @@ def test_cpp_dropin_over_every_gpu_of_the_box_query_and_float_marginals():
     run_flat with query vertices / float marginals (tests/cpp/test_multi_gpu.cpp)."""
     out = _run(os.path.join(OWN_BIN, "test_multi_gpu"))
     assert out.count("[  ok  ]") == 2, out
+
+
+def test_the_adapter_sketch_of_integration_md_compiles(tmp_path):
+    """INTEGRATION.md shows the reference-side binding a maintainer would add (a 40-line adapter over the C ABI).
+    The text is compiled as it stands -- against the reference's own headers where the reference tree exists, and against
+    this repo's drop-in headers (same public surface) everywhere."""
+    import re
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    text = open(os.path.join(root, "INTEGRATION.md")).read()
+    blocks = [b for b in re.findall(r"```cpp\n(.*?)```", text, flags=re.S) if "class belief_propagation_gpu" in b]
+    assert len(blocks) == 1
+    src = tmp_path / "adapter.cpp"
+    src.write_text(blocks[0] + "\nint main() { bn::graph_t g; bn::inference::belief_propagation_gpu* p = nullptr; (void)p; return 0; }\n")
+    trees = [os.path.join(root, "include")] + (["/root/reference"] if os.path.isdir("/root/reference/bayesian") else [])
+    for inc in trees:
+        r = subprocess.run(["g++", "-std=c++11", "-Wall", "-fsyntax-only", "-I", os.path.join(root, "include"), "-I", inc, str(src)],
+                           capture_output=True, text=True)
+        assert r.returncode == 0, (inc, r.stderr[-2000:])
