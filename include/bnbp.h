@@ -203,6 +203,11 @@ typedef struct bnbp_handle bnbp_handle;
 int  bnbp_device_count(void);
 const char* bnbp_last_error(void);           /* thread-local, never NULL */
 
+/* Lays the network out on the device (replaces belief_propagation::belief_propagation(graph_t const&),
+ * belief_propagation.hpp:16-19).  Validates what the reference leaves undefined (parent ids, ascending parent lists, cycles,
+ * CPT sizes: BNBP_ERR_INVALID with the reason in bnbp_last_error()).  Limits the reference does not have: at most 128 states
+ * per node and 8 parents per node.  The first run on a network compiles its kernels (NVRTC, cached on disk; see
+ * bnbp_precompile for doing that ahead of time, without a GPU). */
 int  bnbp_create(const bnbp_flat_network* net, const bnbp_options* opt, bnbp_handle** out);
 void bnbp_destroy(bnbp_handle* h);
 
